@@ -1,0 +1,164 @@
+/*
+ * kmerscuda.h -- C ABI of libkmerscuda.so: B200 (sm_100a) k-mer extraction behind
+ * the Kmers.jl iterator API.
+ *
+ * The reference (BioJulia/Kmers.jl v1.2.0, pure Julia) has no FFI; its boundary for
+ * this path is Julia's iteration protocol on four iterator types plus fx_hash.  Each
+ * entry point below names the reference interface it replaces (paths relative to the
+ * reference tree).  A Julia module (KmersCUDA) binds these with
+ * `ccall`; in this repository the same symbols are bound with Python ctypes
+ * (kmers.jl_b200/kmerscuda/_abi.py).
+ *
+ * Conventions
+ *  - every function returns an int32 status: 0 = KMC_OK, > 0 = domain error below,
+ *    < 0 = -(cudaError_t).  No C++ exception crosses the ABI.
+ *  - plain pointers and sizes only.  "device" pointers are CUDA device addresses on
+ *    the context's device (from kmc_malloc or from any other allocator, e.g. a torch
+ *    tensor's data_ptr); "host" pointers are ordinary host addresses.
+ *  - k-mers are Kmer{A,K,N}.data: N = cld(2K, 64) UInt64 limbs, head (most
+ *    significant) limb first, first symbol in the highest used bits, unused bits
+ *    (top of limb 0) zero (src/kmer.jl:32-51).  Output alphabets are the 2-bit ones
+ *    (DNAAlphabet{2} / RNAAlphabet{2} are bit-identical: A,C,G,T/U = 0,1,2,3).
+ *  - sequences are LongSequence{<:NucleicAcidAlphabet{2|4}}.data words: symbol i
+ *    (0-based) at bits [i*bps mod 64, +bps) of word i*bps div 64.
+ *  - one stream per context; calls on one context must be serialised by the caller;
+ *    distinct contexts are independent.
+ */
+#ifndef KMERSCUDA_H
+#define KMERSCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMC_VERSION 100 /* 0.1.0 */
+#define KMC_MAX_K 128   /* N <= 4 limbs */
+
+/* status codes */
+#define KMC_OK 0
+#define KMC_E_BAD_K 1         /* K < 1 ("K must be at least 1", FwKmers.jl:32-33) or K > KMC_MAX_K */
+#define KMC_E_BAD_ARG 2       /* null / inconsistent descriptor */
+#define KMC_E_AMBIGUOUS 3     /* strict 4->2 recoding hit an uncertain symbol: the caller throws
+                                 BioSequences.EncodeError as construction.jl:108-110 does */
+#define KMC_E_OUT_TOO_SMALL 4 /* kmc_out.capacity < number of elements to write */
+#define KMC_E_NO_DEVICE 5
+#define KMC_E_UNSUPPORTED 6
+
+/* iterator selected (kmc_extract `mode`) */
+#define KMC_FW 0      /* FwKmers{A,K}            src/iterators/FwKmers.jl:28-59,88-115      */
+#define KMC_FWRV 1    /* FwRvIterator{A,K}       src/iterators/CanonicalKmers.jl:25-56,94-144 */
+#define KMC_CANON 2   /* CanonicalKmers{A,K}     src/iterators/CanonicalKmers.jl:199-225    */
+#define KMC_UNAMBIG 3 /* UnambiguousKmers{A,K}   src/iterators/UnambiguousKmers.jl:29-148   */
+
+/* flags */
+#define KMC_HASH_FX 0x1u /* also emit fx_hash(x, 0) (src/kmer.jl:255-261) of the k-mer written to
+                            out.a (fw for FW/FWRV/UNAMBIG, canonical for CANON) */
+#define KMC_AOS 0x2u     /* Julia element layout for tuple eltypes: FWRV -> out.a holds
+                            Tuple{Kmer,Kmer} = u64[n][2][N]; UNAMBIG -> out.a holds
+                            Tuple{Kmer,Int} = {u64[N]; i64}[n].  Default is SoA
+                            (out.a / out.b / out.index separate). */
+#define KMC_NO_SYNC 0x4u /* do not synchronise the stream before returning (2-bit sources,
+                            fixed-count modes only; result->n_written is still exact) */
+
+typedef struct kmc_ctx kmc_ctx;
+
+/* A set of sequences resident in device memory.  n_seqs == 1 is a single LongSequence.
+ * Ragged sets give word-aligned CSR offsets; uniform sets (every read the same length,
+ * fixed word stride) leave seq_word_offset / seq_len NULL. */
+typedef struct kmc_seqs {
+    const uint64_t *words;           /* device: concatenated LongSequence.data */
+    uint64_t n_words;                /* number of u64 words addressable at `words` */
+    uint64_t n_seqs;
+    const uint64_t *seq_word_offset; /* device u64[n_seqs] first word of each sequence, or NULL */
+    const uint64_t *seq_len;         /* device u64[n_seqs] symbols per sequence, or NULL */
+    uint64_t uniform_len;            /* used when seq_len == NULL */
+    uint64_t uniform_stride_words;   /* used when seq_word_offset == NULL */
+    uint32_t src_bits;               /* 2 (Copyable, construction.jl:75-80) or 4 (FourToTwo, :85-86) */
+    uint32_t first_symbol_offset;    /* symbols skipped at the start of every sequence (LongSubSeq view) */
+} kmc_seqs;
+
+/* Output buffers (device for kmc_extract, host for kmc_extract_host).  Unused ones NULL. */
+typedef struct kmc_out {
+    uint64_t *a;              /* FW/FWRV: fw k-mers; CANON: canonical; UNAMBIG: k-mers. (AoS: tuples) */
+    uint64_t *b;              /* FWRV SoA: reverse-complement k-mers */
+    uint64_t *hash;           /* KMC_HASH_FX: u64[n] */
+    int64_t *index;           /* UNAMBIG SoA: 1-based start of each k-mer in its sequence */
+    uint64_t *seq_out_offset; /* optional u64[n_seqs+1]: element offset of each sequence's output */
+    uint64_t capacity;        /* elements (k-mers) each buffer can hold */
+    int64_t index_base;       /* added to every emitted index (shards of one long sequence) */
+} kmc_out;
+
+typedef struct kmc_result {
+    uint64_t n_written; /* elements produced (== length(iterator) summed over sequences) */
+    uint64_t err_seq;   /* KMC_E_AMBIGUOUS: 0-based sequence, */
+    uint64_t err_pos;   /*   1-based symbol position within it, */
+    uint32_t err_sym;   /*   and the offending 4-bit encoding (reinterpret(DNA, x)) */
+    float kernel_ms;    /* device time of the launches of this call (cudaEvents), 0 with KMC_NO_SYNC */
+} kmc_result;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+int32_t kmc_version(void);
+int32_t kmc_device_count(int32_t *n);
+int32_t kmc_ctx_create(int32_t device, kmc_ctx **ctx);
+int32_t kmc_ctx_destroy(kmc_ctx *ctx);
+/* Launch on an existing CUDA stream (cudaStream_t / CUstream handle, e.g. torch's current
+ * stream) instead of the context's own.  NULL restores the context's own stream. */
+int32_t kmc_ctx_set_stream(kmc_ctx *ctx, void *cuda_stream);
+int32_t kmc_sync(kmc_ctx *ctx);
+const char *kmc_last_error(kmc_ctx *ctx);
+const char *kmc_status_string(int32_t status);
+int32_t kmc_device_info(kmc_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, char *name, int32_t name_len);
+
+/* ---- memory ----------------------------------------------------------------------- */
+int32_t kmc_malloc(kmc_ctx *ctx, uint64_t bytes, void **dptr);
+int32_t kmc_free(kmc_ctx *ctx, void *dptr);
+int32_t kmc_memset(kmc_ctx *ctx, void *dptr, int32_t value, uint64_t bytes);
+int32_t kmc_upload(kmc_ctx *ctx, void *dptr, const void *host, uint64_t bytes);   /* async on the stream */
+int32_t kmc_download(kmc_ctx *ctx, void *host, const void *dptr, uint64_t bytes); /* synchronises */
+int32_t kmc_host_alloc(kmc_ctx *ctx, uint64_t bytes, void **hptr); /* pinned */
+int32_t kmc_host_free(kmc_ctx *ctx, void *hptr);
+int32_t kmc_host_register(kmc_ctx *ctx, void *hptr, uint64_t bytes); /* pin caller memory (a Julia Vector) */
+int32_t kmc_host_unregister(kmc_ctx *ctx, void *hptr);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+/* Base.length(it) summed over the set (FwKmers.jl:40-43); for KMC_UNAMBIG over a 4-bit
+ * source (IteratorSize = SizeUnknown, UnambiguousKmers.jl:33-37) runs the count pass. */
+int32_t kmc_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, uint64_t *n_out);
+
+/* collect(Iterator{A,K}(seq)) for every sequence of the set, concatenated in order.
+ * Replaces the per-symbol loops of FwKmers.jl:88-115, CanonicalKmers.jl:94-144,220-225
+ * and UnambiguousKmers.jl:64-77,134-148 with batched device launches. */
+int32_t kmc_extract(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, uint32_t flags,
+                    const kmc_out *out, kmc_result *result);
+
+/* Same call with HOST buffers (seqs->words/offsets/lens and every kmc_out pointer are host
+ * addresses, ideally pinned): uploads, extracts and downloads in pipelined chunks on
+ * internal streams.  This is the call a Julia `collect(it)` replacement makes. */
+int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *host_seqs, int32_t k, int32_t mode, uint32_t flags,
+                         const kmc_out *host_out, kmc_result *result);
+
+/* fx_hash.(v, h0) over n k-mers of n_limbs limbs each already in device memory
+ * (src/kmer.jl:255-261). */
+int32_t kmc_fx_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n_limbs, uint64_t h0,
+                    uint64_t *out);
+
+/* north_star extension (not in the reference): histogram of
+ * fx_hash(canonical k-mer) >> (64 - bucket_bits) over the set, accumulated into
+ * table[2^bucket_bits] (u32, device, caller-zeroed).  Tables of several GPUs are summed
+ * by the caller's collective (torch.distributed / NCCL all-reduce). */
+int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
+                         uint32_t *table, kmc_result *result);
+
+/* ---- timing (cudaEvents on the context's stream) ------------------------------------ */
+int32_t kmc_timer_begin(kmc_ctx *ctx);
+int32_t kmc_timer_end(kmc_ctx *ctx, float *ms); /* synchronises */
+
+/* ---- measurement aid: pure 256-bit streaming store of `bytes` (write roofline probe) -- */
+int32_t kmc_store_probe(kmc_ctx *ctx, void *dptr, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERSCUDA_H */

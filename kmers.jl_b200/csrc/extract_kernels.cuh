@@ -1,0 +1,288 @@
+// extract_kernels.cuh -- the batched replacement of the reference's per-symbol iterator loops
+// (FwKmers.jl:88-94, CanonicalKmers.jl:94-105,220-225, UnambiguousKmers.jl:64-77).
+//
+// Work decomposition.  The output of a read set is one flat array of windows ("flat index"):
+// read r owns flat indices [f0_r, f0_r + wcount_r).  The flat array is cut into aligned groups
+// of G windows (G*N*8 bytes = a multiple of 32, so a full group is written with 256-bit stores).
+// A work item is (read r, group slot gi): the gi-th aligned group that intersects read r.  An item
+// therefore only ever touches ONE read (no divergent slow path at read boundaries); groups
+// that straddle two reads are emitted as two partial items by two threads.
+//   uniform sets  : item -> (r, gi) by one division per thread at kernel start, then an
+//                   incremental update per grid-stride step (no division in the loop)
+//   ragged sets   : item -> r by binary search in the exclusive scan of group slots
+#pragma once
+#include "kmer_core.cuh"
+
+namespace kmc {
+
+enum : int { MODE_FW = 0, MODE_FWRV = 1, MODE_CANON = 2 };
+// where the k-mers go: the output streams, or (north_star extension) a hash-bucket count table
+enum : int { SINK_STREAMS = 0, SINK_BUCKETS = 1 };
+
+constexpr int kBlockThreads = 256;
+
+struct ExtractParams {
+    const uint32_t *w32; // sequence stream viewed as 32-bit words
+    int64_t nw32;        // addressable 32-bit words (loads are clamped into it)
+    uint32_t unit_bits;  // bits per offset unit: 64 (LongSequence words) or 32 (recoded 4-bit stream)
+    uint64_t unit_bias;  // subtracted from every sequence offset (chunk views of a larger set)
+    uint32_t first;      // first_symbol_offset
+    int32_t k;
+    uint32_t s0;         // 32*NX - 2K - 2(G-1)
+    uint64_t head_mask;
+    uint64_t n_seqs;
+    uint64_t items;      // total work items (group slots)
+    // uniform locator
+    uint64_t stride_units;
+    uint64_t wpr;        // windows per read
+    uint64_t gprm;       // group slots per read
+    uint64_t it_dq, it_dr; // divmod(grid stride in items, gprm)
+    // ragged locator
+    const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
+    const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
+    const uint64_t *item_off;     // [n_seqs+1] exclusive scan of group slots
+    // outputs
+    uint64_t *out_a;
+    uint64_t *out_b;
+    uint64_t *out_hash;
+    int64_t *out_index;
+    int64_t index_base;
+    uint32_t aos;    // Julia tuple layout for FWRV / index
+    uint32_t vec_ok; // every output base pointer is 32-byte aligned
+    // fused bucket count (MODE_CANON only): table[fx_hash >> bucket_shift] += 1
+    uint32_t *bucket_table;
+    uint32_t bucket_shift;
+    // 4-bit sources: bit P of vstart = "no uncertain symbol in [P, P+K)" (absolute symbol index)
+    const uint32_t *vstart;
+};
+
+// G windows per thread for N limbs: G*N*8 must be a multiple of 32 bytes.
+template <int N> struct GroupOf { static constexpr int G = (N == 1) ? 4 : (N == 2) ? 2 : (N == 3) ? 4 : 1; };
+
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS>
+__global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractParams p)
+{
+    constexpr int G = GroupOf<N>::G;
+    constexpr bool WANT_FW = true;
+    constexpr bool WANT_RV = (MODE != MODE_FW);
+
+    uint64_t item = static_cast<uint64_t>(blockIdx.x) * kBlockThreads + threadIdx.x;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kBlockThreads;
+    uint64_t r = 0, gi = 0;
+    if (!RAGGED) {
+        r = item / p.gprm;
+        gi = item - r * p.gprm;
+    }
+
+    for (; item < p.items; item += stride) {
+        uint64_t f0, wcount, unit_off;
+        if (RAGGED) {
+            // largest r with item_off[r] <= item
+            uint64_t lo = 0, hi = p.n_seqs;
+            while (hi - lo > 1) {
+                uint64_t mid = (lo + hi) >> 1;
+                if (__ldg(p.item_off + mid) <= item) lo = mid; else hi = mid;
+            }
+            r = lo;
+            gi = item - __ldg(p.item_off + r);
+            f0 = __ldg(p.win_off + r);
+            wcount = __ldg(p.win_off + r + 1) - f0;
+        } else {
+            f0 = r * p.wpr;
+            wcount = p.wpr;
+        }
+        unit_off = p.seq_unit_off ? __ldg(p.seq_unit_off + r) - p.unit_bias : r * p.stride_units;
+        const uint64_t q = f0 / G + gi;                                   // aligned flat group
+        const int64_t wbase = static_cast<int64_t>(q * G - f0);           // window of slot 0, in (-G, wcount)
+        const int64_t rem = static_cast<int64_t>(wcount) - wbase;         // windows available from slot 0
+        const int jlo = wbase < 0 ? static_cast<int>(-wbase) : 0;
+        const int jhi = rem < G ? static_cast<int>(rem) : G;
+
+        if (jhi > jlo) {
+            const int64_t bit = static_cast<int64_t>(unit_off) * p.unit_bits +
+                                2 * (static_cast<int64_t>(p.first) + wbase);
+            uint32_t x[NX];
+            load_block<NX>(p.w32, p.nw32, bit, x);
+            uint64_t fw[G][N], rv[G][N];
+            block_kmers<N, NX, G, WANT_FW, WANT_RV>(x, p.s0, p.head_mask, fw, rv);
+
+            // what lands in out_a, and its hash
+            uint64_t a[G][N], h[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                bool take_fw = true;
+                if (MODE == MODE_CANON) take_fw = limbs_less<N>(fw[j], rv[j]); // fw < rv ? fw : rv
+#pragma unroll
+                for (int i = 0; i < N; ++i) a[j][i] = take_fw ? fw[j][i] : rv[j][i];
+                if (HASH) h[j] = fx_hash<N>(a[j], 0);
+            }
+
+            if (SINK == SINK_BUCKETS) {
+                // canonical k-mer -> fx_hash -> bucket -> counter (no k-mer stream is written)
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (j >= jlo && j < jhi) atomicAdd(p.bucket_table + (h[j] >> p.bucket_shift), 1u);
+                goto next_item;
+            }
+
+            const uint64_t fbase = q * G; // flat index of slot 0
+            const bool full = (jlo == 0) && (jhi == G);
+            const bool tuple_rv = (MODE == MODE_FWRV) && p.aos;
+            const bool tuple_ix = (p.out_index != nullptr) && p.aos;
+
+            if (full && p.vec_ok) {
+                if (tuple_rv) {
+                    uint64_t buf[2 * G * N];
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            buf[j * 2 * N + i] = fw[j][i];
+                            buf[j * 2 * N + N + i] = rv[j][i];
+                        }
+                    store_run<2 * G * N>(p.out_a + fbase * (2 * N), buf, true);
+                } else if (tuple_ix) {
+                    // {u64[N]; i64} elements
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        uint64_t *e = p.out_a + (fbase + j) * (N + 1);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) st_u64(e + i, a[j][i]);
+                        st_u64(e + N, static_cast<uint64_t>(wbase + j + 1 + p.index_base));
+                    }
+                } else {
+                    uint64_t buf[G * N];
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) buf[j * N + i] = a[j][i];
+                    store_run<G * N>(p.out_a + fbase * N, buf, true);
+                    if (MODE == MODE_FWRV) {
+#pragma unroll
+                        for (int j = 0; j < G; ++j)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) buf[j * N + i] = rv[j][i];
+                        store_run<G * N>(p.out_b + fbase * N, buf, true);
+                    }
+                    if (p.out_index) {
+                        uint64_t ib[G];
+#pragma unroll
+                        for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(wbase + j + 1 + p.index_base);
+                        store_run<G>(reinterpret_cast<uint64_t *>(p.out_index) + fbase, ib, G % 4 == 0);
+                    }
+                }
+                if (HASH) store_run<G>(p.out_hash + fbase, h, G % 4 == 0);
+            } else {
+                // partial group (read boundary) or unaligned output buffers: per-window stores
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    if (j < jlo || j >= jhi) continue;
+                    const uint64_t f = fbase + j;
+                    if (tuple_rv) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            st_u64(p.out_a + f * (2 * N) + i, fw[j][i]);
+                            st_u64(p.out_a + f * (2 * N) + N + i, rv[j][i]);
+                        }
+                    } else if (tuple_ix) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) st_u64(p.out_a + f * (N + 1) + i, a[j][i]);
+                        st_u64(p.out_a + f * (N + 1) + N, static_cast<uint64_t>(wbase + j + 1 + p.index_base));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) st_u64(p.out_a + f * N + i, a[j][i]);
+                        if (MODE == MODE_FWRV) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) st_u64(p.out_b + f * N + i, rv[j][i]);
+                        }
+                        if (p.out_index)
+                            st_u64(reinterpret_cast<uint64_t *>(p.out_index) + f,
+                                   static_cast<uint64_t>(wbase + j + 1 + p.index_base));
+                    }
+                    if (HASH) st_u64(p.out_hash + f, h[j]);
+                }
+            }
+        }
+
+    next_item:
+        if (!RAGGED) {
+            r += p.it_dq;
+            gi += p.it_dr;
+            if (gi >= p.gprm) {
+                gi -= p.gprm;
+                ++r;
+            }
+        }
+    }
+}
+
+// Host-side launcher.  The grid is exactly the resident capacity of the device (persistent
+// grid-stride kernel: blocks-per-SM from the occupancy calculator x SM count), or fewer blocks when
+// the problem is smaller.  Defined per N in extract_n*.cu so the instantiations compile in parallel.
+using ExtractLaunchFn = cudaError_t (*)(ExtractParams, int sm_count, cudaStream_t);
+
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS>
+cudaError_t launch_extract(ExtractParams p, int sm_count, cudaStream_t stream)
+{
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extract_kernel<N, NX, MODE, HASH, RAGGED, SINK>,
+                                                                      kBlockThreads, 0);
+        if (e != cudaSuccess) return e;
+        blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    const uint64_t want = (p.items + kBlockThreads - 1) / kBlockThreads;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * blocks_per_sm;
+    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+    if (grid == 0) return cudaSuccess;
+    const uint64_t stride = static_cast<uint64_t>(grid) * kBlockThreads;
+    p.it_dq = stride / p.gprm;
+    p.it_dr = stride % p.gprm;
+    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK><<<grid, kBlockThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// table lookup implemented in extract_n{1,2,3,4}.cu
+ExtractLaunchFn get_extract_launcher_n1(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_extract_launcher_n2(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_extract_launcher_n3(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_extract_launcher_n4(int nx, int mode, bool hash, bool ragged);
+// mode == -1 selects the bucket-count sink (canonical + fx_hash -> table)
+constexpr int MODE_BUCKETS = -1;
+
+// One translation unit per N instantiates its 3 NX variants x 3 modes x hash x locator.
+#define KMC_DEFINE_LAUNCHER_TABLE(FN, N)                                                            \
+    template <int NX, int MODE, bool HASH>                                                          \
+    static ExtractLaunchFn pick_loc_##N(bool ragged)                                                \
+    {                                                                                               \
+        return ragged ? &launch_extract<N, NX, MODE, HASH, true> : &launch_extract<N, NX, MODE, HASH, false>; \
+    }                                                                                               \
+    template <int NX, int MODE>                                                                     \
+    static ExtractLaunchFn pick_hash_##N(bool hash, bool ragged)                                    \
+    {                                                                                               \
+        return hash ? pick_loc_##N<NX, MODE, true>(ragged) : pick_loc_##N<NX, MODE, false>(ragged); \
+    }                                                                                               \
+    template <int NX>                                                                               \
+    static ExtractLaunchFn pick_mode_##N(int mode, bool hash, bool ragged)                          \
+    {                                                                                               \
+        switch (mode) {                                                                             \
+        case MODE_BUCKETS:                                                                          \
+            return ragged ? &launch_extract<N, NX, MODE_CANON, true, true, SINK_BUCKETS>            \
+                          : &launch_extract<N, NX, MODE_CANON, true, false, SINK_BUCKETS>;          \
+        case MODE_FW: return pick_hash_##N<NX, MODE_FW>(hash, ragged);                              \
+        case MODE_FWRV: return pick_hash_##N<NX, MODE_FWRV>(hash, ragged);                          \
+        case MODE_CANON: return pick_hash_##N<NX, MODE_CANON>(hash, ragged);                        \
+        }                                                                                           \
+        return nullptr;                                                                             \
+    }                                                                                               \
+    ExtractLaunchFn FN(int nx, int mode, bool hash, bool ragged)                                    \
+    {                                                                                               \
+        constexpr int NXMAX = (64 * N + 2 * GroupOf<N>::G - 2 + 31) / 32;                           \
+        if (nx == NXMAX) return pick_mode_##N<NXMAX>(mode, hash, ragged);                           \
+        if (nx == NXMAX - 1) return pick_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
+        if (nx == NXMAX - 2) return pick_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
+        return nullptr;                                                                             \
+    }
+
+} // namespace kmc

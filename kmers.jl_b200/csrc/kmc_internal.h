@@ -1,0 +1,47 @@
+// kmc_internal.h -- shared host-side declarations of libkmerscuda (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+#include "../../include/kmerscuda.h"
+
+struct kmc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr; // the stream launches go to (own_stream or the caller's)
+    cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr}; // kmc_extract_host pipeline slots
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // kmc_timer_*
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;      // per-call kernel timing
+    // grow-only scratch (scans, recoded 4-bit streams, compaction counters)
+    void *scratch = nullptr;
+    uint64_t scratch_bytes = 0;
+    // host-pipeline device buffers, one per slot (grow-only)
+    void *pipe_buf[3] = {nullptr, nullptr, nullptr};
+    uint64_t pipe_bytes[3] = {0, 0, 0};
+    std::string last_error;
+};
+
+namespace kmc {
+
+// scratch carving -------------------------------------------------------------------------
+int32_t ensure_scratch(kmc_ctx *ctx, uint64_t bytes);
+
+// scan.cu -----------------------------------------------------------------------------------
+// out[0] = 0, out[i+1] = sum_{j<=i} in[j]  (n+1 outputs), all on `stream`.
+// tmp must hold scan_tmp_elems(n) u64.
+uint64_t scan_tmp_elems(uint64_t n);
+cudaError_t inclusive_offsets_u64(const uint64_t *in, uint64_t *out, uint64_t n, uint64_t *tmp, cudaStream_t stream);
+// per-sequence window counts (FwKmers.jl:40-43: max(0, len - K + 1)) -> cnt[n]
+cudaError_t window_counts(const uint64_t *seq_len, uint64_t n, int k, uint64_t *cnt, cudaStream_t stream);
+// group slots per sequence from the window offsets: slots[r] = #aligned groups of G that intersect
+// [win_off[r], win_off[r+1])
+cudaError_t group_slots(const uint64_t *win_off, uint64_t n, int g, uint64_t *slots, cudaStream_t stream);
+
+// misc_kernels.cu -----------------------------------------------------------------------------
+cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,
+                           cudaStream_t stream);
+cudaError_t launch_store_probe(void *dptr, uint64_t bytes, int sm_count, cudaStream_t stream);
+
+} // namespace kmc

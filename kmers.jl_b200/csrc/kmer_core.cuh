@@ -1,0 +1,182 @@
+// kmer_core.cuh -- register-level k-mer primitives for sm_100a.
+//
+// The reference derives k-mer i from k-mer i-1 (shift_encoding,
+// src/construction_utils.jl:129-134; shift_first_encoding, src/kmer.jl:511-518).  Here every
+// window is computed independently from the packed sequence words:
+//
+//   Let S be the little-endian 2-bit stream of a LongSequence (symbol i at bits [2i, 2i+2)) and
+//   W_p = S[2p, 2p+2K) the raw bits of the window starting at symbol p.  Because LongSequence
+//   stores the first symbol in the LOWEST bits while Kmer stores it in the HIGHEST,
+//     reverse-complement k-mer  rv = ~W_p  (masked to 2K bits)          -- no bit reversal at all
+//     forward k-mer             fw = rev2(W_p)  (order of 2-bit groups reversed)
+//   (the closed form the reference itself uses in build_kmer(::Copyable), src/construction.jl:213-219:
+//   reversebits of the raw words, right-aligned).
+//
+// A thread owns G consecutive windows.  It loads a block of NX 32-bit words that covers the
+// 2K + 2(G-1) bits of its windows, aligns it once with funnel shifts, bit-reverses the block once,
+// and then every window is two static funnel shifts per 32-bit half:
+//   x-stream (aligned to the first window) -> rv_j  = ~(x >> 2j)
+//   t-stream (rev2 of the block, aligned to the LAST window) -> fw_j = t >> 2(G-1-j)
+// NX is a template parameter chosen as ceil((2K + 2G - 2) / 32) so that every word index is a
+// compile-time constant (registers, never local memory) and the run-time alignment shifts are < 32.
+#pragma once
+#include <cstdint>
+
+namespace kmc {
+
+#define KMC_DEV __device__ __forceinline__
+
+constexpr uint64_t FX_CONSTANT = 0x517cc1b727220a95ull; // src/kmer.jl:218
+
+// reversebits(x, BitsPerSymbol{2}) on a 32-bit word: reverse the order of the 16 two-bit groups.
+KMC_DEV uint32_t rev2_32(uint32_t x)
+{
+    x = __brev(x);
+    return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
+KMC_DEV uint64_t pack64(uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; }
+
+// 64 bits of a 32-bit-word stream starting at bit offset `off`.  `off` is a compile-time
+// constant at every call site once the caller's loops are unrolled, so all indices are static
+// (words past the end of the block read as zero; they only ever feed masked-out bits).
+template <int NW>
+KMC_DEV uint64_t stream64(const uint32_t (&s)[NW], int off)
+{
+    const int c = off >> 5, sh = off & 31;
+    auto W = [&](int i) -> uint32_t { return i < NW ? s[i < NW ? i : 0] : 0u; };
+    uint32_t lo, hi;
+    if (sh == 0) {
+        lo = W(c);
+        hi = W(c + 1);
+    } else {
+        lo = __funnelshift_r(W(c), W(c + 1), sh);
+        hi = __funnelshift_r(W(c + 1), W(c + 2), sh);
+    }
+    return pack64(lo, hi);
+}
+
+// cmp(x.data, y.data) == -1 (src/kmer.jl:176-201): limb-lexicographic, head first.
+template <int N>
+KMC_DEV bool limbs_less(const uint64_t (&a)[N], const uint64_t (&b)[N])
+{
+    bool lt = false, decided = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        lt = lt || (!decided && a[i] < b[i]);
+        decided = decided || (a[i] != b[i]);
+    }
+    return lt;
+}
+
+// fx_hash (src/kmer.jl:255-261)
+template <int N>
+KMC_DEV uint64_t fx_hash(const uint64_t (&d)[N], uint64_t h)
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i) h = (((h << 5) | (h >> 59)) ^ d[i]) * FX_CONSTANT;
+    return h;
+}
+
+// ---- streaming stores --------------------------------------------------------------------
+KMC_DEV void st_u64(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+KMC_DEV void st_v2(uint64_t *p, uint64_t a, uint64_t b)
+{
+    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+// 256-bit store: one STG.E.256 on sm_100a
+KMC_DEV void st_v4(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d)
+                 : "memory");
+}
+
+// CNT contiguous u64 values; `aligned32` says p is 32-byte aligned.
+template <int CNT>
+KMC_DEV void store_run(uint64_t *p, const uint64_t (&v)[CNT], bool aligned32)
+{
+    if (CNT % 4 == 0 && aligned32) {
+#pragma unroll
+        for (int i = 0; i + 3 < CNT; i += 4) st_v4(p + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if (CNT % 2 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i + 1 < CNT; i += 2) st_v2(p + i, v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) st_u64(p + i, v[i]);
+    }
+}
+
+// ---- the window block ----------------------------------------------------------------------
+// Loads NX+1 words at 32-bit word index floor(bit/32) (clamped into [0, nw32) so that slots
+// outside the sequence buffer never fault; such bits only ever feed windows that are not
+// emitted) and produces the aligned x-stream.
+template <int NX>
+KMC_DEV void load_block(const uint32_t *__restrict__ w32, int64_t nw32, int64_t bit, uint32_t (&x)[NX])
+{
+    const int64_t idx = bit >> 5;
+    const uint32_t s = static_cast<uint32_t>(bit) & 31u;
+    uint32_t a[NX + 1];
+    if (idx >= 0 && idx + NX < nw32) {
+#pragma unroll
+        for (int i = 0; i <= NX; ++i) a[i] = __ldg(w32 + idx + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i <= NX; ++i) {
+            int64_t k = idx + i;
+            k = k < 0 ? 0 : (k >= nw32 ? nw32 - 1 : k);
+            a[i] = __ldg(w32 + k);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = __funnelshift_r(a[i], a[i + 1], s);
+}
+
+// fw[j] / rv[j] for the G windows of a block, limbs head first.
+//   s0        = 32*NX - 2K - 2(G-1), in [0, 32)
+//   head_mask = get_mask (src/kmer.jl:603-605)
+template <int N, int NX, int G, bool WANT_FW, bool WANT_RV>
+KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mask, uint64_t (&fw)[G][N],
+                         uint64_t (&rv)[G][N])
+{
+    if (WANT_RV) {
+        // complement once per block (complement_bitpar for 2-bit alphabets is ~x,
+        // src/transformations.jl:21-25), then each window is a static funnel shift.
+        uint32_t nx[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) nx[i] = ~x[i];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+#pragma unroll
+            for (int m = 0; m < N; ++m) { // m = 0 is the least significant limb
+                uint64_t v = stream64<NX>(nx, 2 * j + 64 * m);
+                if (m == N - 1) v &= head_mask;
+                rv[j][N - 1 - m] = v;
+            }
+        }
+    }
+    if (WANT_FW) {
+        // rev2 of the whole block: symbol i of the x-stream lands at symbol 16*NX-1-i.
+        uint32_t y[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) y[i] = rev2_32(x[NX - 1 - i]);
+        // drop the s0 bits that lie beyond the last window
+        uint32_t t[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) t[i] = __funnelshift_r(y[i], i + 1 < NX ? y[i + 1 < NX ? i + 1 : 0] : 0u, s0);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+#pragma unroll
+            for (int m = 0; m < N; ++m) {
+                uint64_t v = stream64<NX>(t, 2 * (G - 1 - j) + 64 * m);
+                if (m == N - 1) v &= head_mask;
+                fw[j][N - 1 - m] = v;
+            }
+        }
+    }
+}
+
+} // namespace kmc

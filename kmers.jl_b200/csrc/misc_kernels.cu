@@ -1,0 +1,60 @@
+// misc_kernels.cu -- standalone fx_hash over an existing device k-mer array (src/kmer.jl:255-261)
+// and the pure-store probe used to measure the write roofline of the device.
+#include "kmc_internal.h"
+#include "kmer_core.cuh"
+
+namespace kmc {
+
+template <int N>
+__global__ void __launch_bounds__(256) fx_hash_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t h0,
+                                                      uint64_t *__restrict__ out)
+{
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t d[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) d[j] = __ldg(kmers + i * N + j);
+        st_u64(out + i, fx_hash<N>(d, h0));
+    }
+}
+
+__global__ void __launch_bounds__(256) fx_hash_empty_kernel(uint64_t n, uint64_t h0, uint64_t *__restrict__ out)
+{
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = h0;
+}
+
+cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,
+                           cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    uint64_t want = (n + 255) / 256;
+    unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 16 ? want : static_cast<uint64_t>(sm_count) * 16);
+    switch (n_limbs) {
+    case 0: fx_hash_empty_kernel<<<grid, 256, 0, stream>>>(n, h0, out); break; // empty k-mer hashes to h0 (0 by default)
+    case 1: fx_hash_kernel<1><<<grid, 256, 0, stream>>>(kmers, n, h0, out); break;
+    case 2: fx_hash_kernel<2><<<grid, 256, 0, stream>>>(kmers, n, h0, out); break;
+    case 3: fx_hash_kernel<3><<<grid, 256, 0, stream>>>(kmers, n, h0, out); break;
+    case 4: fx_hash_kernel<4><<<grid, 256, 0, stream>>>(kmers, n, h0, out); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// Every thread writes 32 bytes per step with one 256-bit store; grid-stride; nothing is read.
+__global__ void __launch_bounds__(256) store_probe_kernel(uint64_t *__restrict__ p, uint64_t n_vec)
+{
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride)
+        st_v4(p + 4 * i, i, i + 1, i + 2, i + 3);
+}
+
+cudaError_t launch_store_probe(void *dptr, uint64_t bytes, int sm_count, cudaStream_t stream)
+{
+    uint64_t n_vec = bytes / 32;
+    if (n_vec == 0) return cudaSuccess;
+    store_probe_kernel<<<sm_count * 8, 256, 0, stream>>>(static_cast<uint64_t *>(dptr), n_vec);
+    return cudaGetLastError();
+}
+
+} // namespace kmc

@@ -1,0 +1,114 @@
+"""ctypes binding of libkmerscuda.so -- exactly the symbols include/kmerscuda.h declares.
+
+This is the same binding a Julia `ccall` stub makes; there is no CPU
+fallback: if the shared library is missing the import fails, and if no CUDA device is present
+every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libkmerscuda.so")
+
+KMC_OK = 0
+KMC_E_BAD_K = 1
+KMC_E_BAD_ARG = 2
+KMC_E_AMBIGUOUS = 3
+KMC_E_OUT_TOO_SMALL = 4
+KMC_E_NO_DEVICE = 5
+KMC_E_UNSUPPORTED = 6
+
+KMC_FW, KMC_FWRV, KMC_CANON, KMC_UNAMBIG = 0, 1, 2, 3
+KMC_HASH_FX, KMC_AOS, KMC_NO_SYNC = 0x1, 0x2, 0x4
+KMC_MAX_K = 128
+
+
+class kmc_seqs(C.Structure):
+    _fields_ = [
+        ("words", C.c_void_p),
+        ("n_words", C.c_uint64),
+        ("n_seqs", C.c_uint64),
+        ("seq_word_offset", C.c_void_p),
+        ("seq_len", C.c_void_p),
+        ("uniform_len", C.c_uint64),
+        ("uniform_stride_words", C.c_uint64),
+        ("src_bits", C.c_uint32),
+        ("first_symbol_offset", C.c_uint32),
+    ]
+
+
+class kmc_out(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p),
+        ("b", C.c_void_p),
+        ("hash", C.c_void_p),
+        ("index", C.c_void_p),
+        ("seq_out_offset", C.c_void_p),
+        ("capacity", C.c_uint64),
+        ("index_base", C.c_int64),
+    ]
+
+
+class kmc_result(C.Structure):
+    _fields_ = [
+        ("n_written", C.c_uint64),
+        ("err_seq", C.c_uint64),
+        ("err_pos", C.c_uint64),
+        ("err_sym", C.c_uint32),
+        ("kernel_ms", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); must list every function of include/kmerscuda.h
+SIGNATURES = {
+    "kmc_version": (C.c_int32, []),
+    "kmc_device_count": (C.c_int32, [C.POINTER(C.c_int32)]),
+    "kmc_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "kmc_ctx_destroy": (C.c_int32, [C.c_void_p]),
+    "kmc_ctx_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "kmc_sync": (C.c_int32, [C.c_void_p]),
+    "kmc_last_error": (C.c_char_p, [C.c_void_p]),
+    "kmc_status_string": (C.c_char_p, [C.c_int32]),
+    "kmc_device_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_char_p, C.c_int32]),
+    "kmc_malloc": (C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "kmc_free": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "kmc_memset": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64]),
+    "kmc_upload": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "kmc_download": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "kmc_host_alloc": (C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "kmc_host_free": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "kmc_host_register": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "kmc_host_unregister": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "kmc_count": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "kmc_extract": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint32,
+                                C.POINTER(kmc_out), C.POINTER(kmc_result)]),
+    "kmc_extract_host": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint32,
+                                     C.POINTER(kmc_out), C.POINTER(kmc_result)]),
+    "kmc_fx_hash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]),
+    "kmc_bucket_count": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p,
+                                     C.POINTER(kmc_result)]),
+    "kmc_timer_begin": (C.c_int32, [C.c_void_p]),
+    "kmc_timer_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
+    "kmc_store_probe": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree CUDA library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C kmers.jl_b200/csrc).  There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,522 @@
+"""Host-side mirror of the reference's iterator interface for the k-mer extraction path.
+
+Same names, argument meaning and error behaviour as Kmers.jl (paths relative to the reference):
+
+  FwKmers(A, K, seq)            src/iterators/FwKmers.jl:28-59
+  FwRvIterator(A, K, seq)       src/iterators/CanonicalKmers.jl:25-56
+  CanonicalKmers(A, K, seq)     src/iterators/CanonicalKmers.jl:199-225
+  UnambiguousKmers(A, K, seq)   src/iterators/UnambiguousKmers.jl:29-62
+  fx_hash(kmers, h)             src/kmer.jl:255-261
+  LongSequence                  BioSequences.LongSequence{A}(data::Vector{UInt64}, len) (L0 substrate)
+
+`collect(it)` returns what Julia's `collect` would hold in memory: an array of `Kmer{A,K,N}.data`
+limbs (`NTuple{N,UInt64}`, head first), tuples in the Julia element layout.  All arithmetic happens
+in libkmerscuda.so on the GPU; this module only maps types to integers and owns buffers.  There
+is no CPU fallback: without the library or a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import (KMC_AOS, KMC_CANON, KMC_E_AMBIGUOUS, KMC_E_BAD_K, KMC_FW, KMC_FWRV, KMC_HASH_FX, KMC_MAX_K,
+                   KMC_NO_SYNC, KMC_OK, KMC_UNAMBIG, kmc_out, kmc_result, kmc_seqs)
+
+# ----------------------------------------------------------------------------------------------
+# alphabets (only what the path needs: the 2- and 4-bit nucleic acid alphabets)
+# ----------------------------------------------------------------------------------------------
+
+
+@dataclass(frozen=True)
+class Alphabet:
+    name: str
+    bits: int
+
+
+DNAAlphabet2 = Alphabet("DNAAlphabet{2}", 2)
+RNAAlphabet2 = Alphabet("RNAAlphabet{2}", 2)
+DNAAlphabet4 = Alphabet("DNAAlphabet{4}", 4)
+RNAAlphabet4 = Alphabet("RNAAlphabet{4}", 4)
+
+_CODE2 = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 3}
+_CODE4 = {"-": 0, "A": 1, "C": 2, "M": 3, "G": 4, "R": 5, "S": 6, "V": 7, "T": 8, "U": 8, "W": 9, "Y": 10,
+          "H": 11, "K": 12, "D": 13, "B": 14, "N": 15}
+_SYM4_DNA = "-ACMGRSVTWYHKDBN"
+
+
+class EncodeError(Exception):
+    """BioSequences.EncodeError as thrown through src/construction.jl:108-110."""
+
+    def __init__(self, alphabet: Alphabet, symbol: str, seq_index: int = 0, position: int = 0):
+        super().__init__(f"cannot encode {symbol} in {alphabet.name}")
+        self.alphabet, self.symbol, self.seq_index, self.position = alphabet, symbol, seq_index, position
+
+
+class KmersCUDAError(RuntimeError):
+    pass
+
+
+def n_limbs(K: int) -> int:
+    """N of Kmer{A,K,N} for a 2-bit alphabet (src/kmer.jl:97-111)."""
+    return (2 * K + 63) // 64
+
+
+def _check_K(K):
+    # FwKmers.jl:31-33
+    if not isinstance(K, (int, np.integer)) or isinstance(K, bool):
+        raise TypeError("K must be an Int")
+    if K < 1:
+        raise ValueError("K must be at least 1")
+
+
+# ----------------------------------------------------------------------------------------------
+# sequences
+# ----------------------------------------------------------------------------------------------
+
+
+class LongSequence:
+    """LongSequence{A}: `data` are the packed UInt64 words, `len` the number of symbols."""
+
+    def __init__(self, alphabet: Alphabet, data: np.ndarray, length: int):
+        self.alphabet = alphabet
+        self.data = np.ascontiguousarray(data, dtype=np.uint64)
+        self.len = int(length)
+        need = (self.len * alphabet.bits + 63) // 64
+        if self.data.size < need:
+            raise ValueError("data holds fewer words than `length` symbols need")
+
+    def __len__(self):
+        return self.len
+
+    @classmethod
+    def from_string(cls, alphabet: Alphabet, s: str) -> "LongSequence":
+        table = _CODE2 if alphabet.bits == 2 else _CODE4
+        try:
+            codes = np.fromiter((table[c] for c in s.upper()), dtype=np.uint64, count=len(s))
+        except KeyError as e:  # what LongDNA{2}("...N...") does
+            raise EncodeError(alphabet, e.args[0]) from None
+        per = 64 // alphabet.bits
+        nw = (len(s) + per - 1) // per
+        padded = np.zeros(nw * per, dtype=np.uint64)
+        padded[: len(s)] = codes
+        shifts = np.arange(per, dtype=np.uint64) * np.uint64(alphabet.bits)
+        data = np.bitwise_or.reduce(padded.reshape(nw, per) << shifts, axis=1) if nw else np.zeros(0, np.uint64)
+        return cls(alphabet, data.astype(np.uint64), len(s))
+
+
+def LongDNA2(s: str) -> LongSequence:
+    return LongSequence.from_string(DNAAlphabet2, s)
+
+
+def LongDNA4(s: str) -> LongSequence:
+    return LongSequence.from_string(DNAAlphabet4, s)
+
+
+class ReadSet:
+    """A batch of LongSequences in one word-aligned CSR buffer (what `Vector{LongDNA{2}}` becomes).
+
+    Either ragged (`seq_word_offset`, `seq_len` arrays) or uniform (`uniform_len`, `uniform_stride_words`).
+    """
+
+    def __init__(self, bits: int, words: np.ndarray, n_seqs: int, *, seq_word_offset=None, seq_len=None,
+                 uniform_len: int = 0, uniform_stride_words: int = 0, first_symbol_offset: int = 0):
+        self.bits = bits
+        self.words = np.ascontiguousarray(words, dtype=np.uint64)
+        self.n_seqs = int(n_seqs)
+        self.seq_word_offset = None if seq_word_offset is None else np.ascontiguousarray(seq_word_offset, np.uint64)
+        self.seq_len = None if seq_len is None else np.ascontiguousarray(seq_len, np.uint64)
+        self.uniform_len = int(uniform_len)
+        self.uniform_stride_words = int(uniform_stride_words)
+        self.first_symbol_offset = int(first_symbol_offset)
+
+    @classmethod
+    def from_sequences(cls, seqs: Sequence[LongSequence]) -> "ReadSet":
+        bits = seqs[0].alphabet.bits if seqs else 2
+        need = [(len(s) * bits + 63) // 64 for s in seqs]
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(need)
+        words = np.zeros(int(off[-1]), dtype=np.uint64)
+        for s, o, n in zip(seqs, off[:-1], need):
+            words[int(o): int(o) + n] = s.data[:n]
+        return cls(bits, words, len(seqs), seq_word_offset=off[:-1].copy(),
+                   seq_len=np.array([len(s) for s in seqs], dtype=np.uint64))
+
+    @classmethod
+    def single(cls, seq: LongSequence, first_symbol_offset: int = 0, length: Optional[int] = None) -> "ReadSet":
+        n = len(seq) if length is None else length
+        return cls(seq.alphabet.bits, seq.data, 1, uniform_len=n, uniform_stride_words=seq.data.size,
+                   first_symbol_offset=first_symbol_offset)
+
+    def window_counts(self, K: int) -> np.ndarray:
+        if self.seq_len is None:
+            return np.full(self.n_seqs, max(0, self.uniform_len - K + 1), dtype=np.uint64)
+        return np.where(self.seq_len >= K, self.seq_len - np.uint64(K) + np.uint64(1), np.uint64(0)).astype(np.uint64)
+
+
+# ----------------------------------------------------------------------------------------------
+# device context
+# ----------------------------------------------------------------------------------------------
+
+
+class DeviceBuffer:
+    """Device memory owned by the library (kmc_malloc / kmc_free)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        ctx._check(ctx.lib.kmc_malloc(ctx.handle, max(self.nbytes, 1), C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        if arr.nbytes:
+            self.ctx._check(self.ctx.lib.kmc_upload(self.ctx.handle, self.ptr, arr.ctypes.data, arr.nbytes))
+            self.ctx.sync()  # `arr` may be a temporary
+        return self
+
+    def download(self, dtype, count: int, offset_bytes: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        self.ctx._check(self.ctx.lib.kmc_download(self.ctx.handle, out.ctypes.data, self.ptr + offset_bytes, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.kmc_free(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One kmc_ctx: a device, a stream, scratch.  Not thread-safe (one caller at a time)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _abi.load()
+        h = C.c_void_p()
+        st = self.lib.kmc_ctx_create(device, C.byref(h))
+        if st != KMC_OK:
+            raise KmersCUDAError(
+                f"kmc_ctx_create(device={device}) failed: {self.lib.kmc_status_string(st).decode()} "
+                "-- KmersCUDA needs a CUDA device; there is no CPU fallback")
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.kmc_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != KMC_OK:
+            msg = self.lib.kmc_last_error(self.handle).decode() or self.lib.kmc_status_string(st).decode()
+            raise KmersCUDAError(f"libkmerscuda status {st}: {msg}")
+
+    def sync(self):
+        self._check(self.lib.kmc_sync(self.handle))
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._check(self.lib.kmc_ctx_set_stream(self.handle, cuda_stream))
+
+    def device_info(self):
+        sm, mem, name = C.c_int32(), C.c_uint64(), C.create_string_buffer(128)
+        self._check(self.lib.kmc_device_info(self.handle, C.byref(sm), C.byref(mem), name, 128))
+        return {"sm_count": sm.value, "total_mem": mem.value, "name": name.value.decode()}
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr: np.ndarray) -> DeviceBuffer:
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, arr.nbytes).upload(arr)
+
+    def pinned(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        """numpy view of pinned host memory (kmc_host_alloc); keep the returned array alive."""
+        p = C.c_void_p()
+        self._check(self.lib.kmc_host_alloc(self.handle, max(int(nbytes), 1), C.byref(p)))
+        buf = (C.c_uint8 * max(int(nbytes), 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=int(nbytes)).view(dtype)
+        _PINNED[arr.ctypes.data] = (self, p.value)
+        return arr
+
+    def timer_begin(self):
+        self._check(self.lib.kmc_timer_begin(self.handle))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.kmc_timer_end(self.handle, C.byref(ms)))
+        return ms.value
+
+
+_PINNED: dict = {}
+_DEFAULT: dict = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _DEFAULT:
+        _DEFAULT[device] = Context(device)
+    return _DEFAULT[device]
+
+
+# ----------------------------------------------------------------------------------------------
+# device-resident read sets and results
+# ----------------------------------------------------------------------------------------------
+
+
+class DeviceReadSet:
+    """A ReadSet uploaded once; the kmc_seqs descriptor points at device memory."""
+
+    def __init__(self, ctx: Context, rs: ReadSet):
+        self.ctx, self.host = ctx, rs
+        self.words = ctx.to_device(rs.words)
+        self.off = None if rs.seq_word_offset is None else ctx.to_device(rs.seq_word_offset)
+        self.len = None if rs.seq_len is None else ctx.to_device(rs.seq_len)
+        self.desc = kmc_seqs(self.words.ptr, rs.words.size, rs.n_seqs, self.off.ptr if self.off else None,
+                             self.len.ptr if self.len else None, rs.uniform_len, rs.uniform_stride_words, rs.bits,
+                             rs.first_symbol_offset)
+
+
+def _host_desc(rs: ReadSet) -> kmc_seqs:
+    return kmc_seqs(rs.words.ctypes.data if rs.words.size else None, rs.words.size, rs.n_seqs,
+                    None if rs.seq_word_offset is None else rs.seq_word_offset.ctypes.data,
+                    None if rs.seq_len is None else rs.seq_len.ctypes.data, rs.uniform_len, rs.uniform_stride_words,
+                    rs.bits, rs.first_symbol_offset)
+
+
+@dataclass
+class Extracted:
+    """Result of one extraction (host arrays).  Shapes follow the Julia element layout."""
+    kmers: np.ndarray                 # [n, N]  (FWRV + aos: [n, 2, N])
+    rv: Optional[np.ndarray] = None   # FWRV SoA: [n, N]
+    hash: Optional[np.ndarray] = None
+    index: Optional[np.ndarray] = None
+    seq_out_offset: Optional[np.ndarray] = None
+    n: int = 0
+    kernel_ms: float = 0.0
+
+
+_MODE_NAMES = {KMC_FW: "FwKmers", KMC_FWRV: "FwRvIterator", KMC_CANON: "CanonicalKmers", KMC_UNAMBIG: "UnambiguousKmers"}
+
+
+def _raise_ambiguous(rs_bits: int, A: Alphabet, res: kmc_result):
+    sym = _SYM4_DNA[res.err_sym & 15]
+    if A.name.startswith("RNA") and sym == "T":
+        sym = "U"
+    raise EncodeError(A, sym, int(res.err_seq), int(res.err_pos))
+
+
+def _upper_bound(ctx: Context, desc: kmc_seqs, rs: ReadSet, K: int, mode: int) -> int:
+    return int(rs.window_counts(K).sum())
+
+
+def extract(mode: int, rs, K: int, *, A: Alphabet = DNAAlphabet2, hash: bool = False, aos: bool = False,
+            want_seq_offsets: bool = False, ctx: Optional[Context] = None, host_path: bool = False,
+            index_base: int = 0) -> Extracted:
+    """Batched `collect` of one iterator type over a ReadSet / DeviceReadSet.
+
+    host_path=False: descriptors are uploaded (or already resident), kmc_extract runs on device
+    buffers and the outputs are downloaded.  host_path=True: one kmc_extract_host call on host
+    buffers (the pipelined entry point a Julia `collect` replacement uses).
+    """
+    _check_K(K)
+    if K > KMC_MAX_K:
+        raise ValueError(f"K must be at most {KMC_MAX_K}")
+    if A.bits != 2:
+        raise NotImplementedError("only 2-bit output alphabets are on the accelerated path")
+    ctx = ctx or default_context()
+    lib = ctx.lib
+    N = n_limbs(K)
+    if isinstance(rs, DeviceReadSet):
+        drs, hrs = rs, rs.host
+    else:
+        drs, hrs = None, rs
+    cap = _upper_bound(ctx, None, hrs, K, mode)
+    two = mode == KMC_FWRV
+    want_index = mode == KMC_UNAMBIG
+    a_elems = (2 * N if two else N + 1 if want_index else N) if aos else N
+    flags = (KMC_HASH_FX if hash else 0) | (KMC_AOS if aos else 0)
+    res = kmc_result()
+
+    if host_path:
+        a = np.zeros(max(cap, 1) * a_elems, dtype=np.uint64)
+        b = np.zeros(max(cap, 1) * N, dtype=np.uint64) if (two and not aos) else None
+        h = np.zeros(max(cap, 1), dtype=np.uint64) if hash else None
+        ix = np.zeros(max(cap, 1), dtype=np.int64) if (want_index and not aos) else None
+        so = np.zeros(hrs.n_seqs + 1, dtype=np.uint64) if want_seq_offsets else None
+        out = kmc_out(a.ctypes.data, None if b is None else b.ctypes.data, None if h is None else h.ctypes.data,
+                      None if ix is None else ix.ctypes.data, None if so is None else so.ctypes.data, cap, index_base)
+        desc = _host_desc(hrs)
+        st = lib.kmc_extract_host(ctx.handle, C.byref(desc), K, mode, flags, C.byref(out), C.byref(res))
+    else:
+        if drs is None:
+            drs = DeviceReadSet(ctx, hrs)
+        da = ctx.alloc(max(cap, 1) * a_elems * 8)
+        db = ctx.alloc(max(cap, 1) * N * 8) if (two and not aos) else None
+        dh = ctx.alloc(max(cap, 1) * 8) if hash else None
+        di = ctx.alloc(max(cap, 1) * 8) if (want_index and not aos) else None
+        dso = ctx.alloc((hrs.n_seqs + 1) * 8) if want_seq_offsets else None
+        out = kmc_out(da.ptr, db.ptr if db else None, dh.ptr if dh else None, di.ptr if di else None,
+                      dso.ptr if dso else None, cap, index_base)
+        st = lib.kmc_extract(ctx.handle, C.byref(drs.desc), K, mode, flags, C.byref(out), C.byref(res))
+    if st == KMC_E_AMBIGUOUS:
+        _raise_ambiguous(hrs.bits, A, res)
+    ctx._check(st)
+    n = int(res.n_written)
+    if not host_path:
+        a = da.download(np.uint64, n * a_elems)
+        b = db.download(np.uint64, n * N) if db else None
+        h = dh.download(np.uint64, n) if dh else None
+        ix = di.download(np.int64, n) if di else None
+        so = dso.download(np.uint64, hrs.n_seqs + 1) if dso else None
+        for d in (da, db, dh, di, dso):
+            if d:
+                d.free()
+    a = a[: n * a_elems]
+    if aos and two:
+        kmers = a.reshape(n, 2, N)
+    elif aos and want_index:
+        kmers = a.reshape(n, N + 1)
+    else:
+        kmers = a.reshape(n, N)
+    return Extracted(kmers=kmers, rv=None if b is None else b[: n * N].reshape(n, N),
+                     hash=None if h is None else h[:n], index=None if ix is None else ix[:n],
+                     seq_out_offset=so, n=n, kernel_ms=float(res.kernel_ms))
+
+
+# ----------------------------------------------------------------------------------------------
+# the four iterator types
+# ----------------------------------------------------------------------------------------------
+
+
+class _KmerIterator:
+    mode = KMC_FW
+
+    def __init__(self, A: Alphabet, K: int, seq: LongSequence):
+        _check_K(K)
+        if not isinstance(seq, LongSequence):
+            raise TypeError("the accelerated path takes LongSequence sources (ASCII sources are the next row)")
+        self.A, self.K, self.seq = A, K, seq
+
+    def __len__(self):
+        # FwKmers.jl:40-43
+        return max(0, len(self.seq) - self.K + 1)
+
+    def _extract(self, **kw) -> Extracted:
+        return extract(self.mode, ReadSet.single(self.seq), self.K, A=self.A, **kw)
+
+
+class FwKmers(_KmerIterator):
+    """Every k-mer of `seq`, in order.  collect() -> u64[n, N]."""
+    mode = KMC_FW
+
+    def collect(self, **kw) -> np.ndarray:
+        return self._extract(**kw).kmers
+
+
+class FwRvIterator(_KmerIterator):
+    """(kmer, reverse_complement(kmer)) for every window.  collect() -> u64[n, 2, N] (Tuple{Kmer,Kmer})."""
+    mode = KMC_FWRV
+
+    def collect(self, **kw) -> np.ndarray:
+        return self._extract(aos=True, **kw).kmers
+
+
+class CanonicalKmers(_KmerIterator):
+    """min(kmer, reverse_complement(kmer)) for every window.  collect() -> u64[n, N]."""
+    mode = KMC_CANON
+
+    def collect(self, **kw) -> np.ndarray:
+        return self._extract(**kw).kmers
+
+
+class UnambiguousKmers(_KmerIterator):
+    """(kmer, start) for every window without ambiguous symbols.  collect() -> (u64[n, N], i64[n])."""
+    mode = KMC_UNAMBIG
+
+    def __len__(self):
+        # IteratorSize is SizeUnknown unless the source is 2-bit (UnambiguousKmers.jl:33-37)
+        if self.seq.alphabet.bits != 2:
+            raise TypeError("length is unknown for a 4-bit source (Base.SizeUnknown)")
+        return super().__len__()
+
+    def collect(self, **kw):
+        e = self._extract(**kw)
+        return e.kmers, e.index
+
+
+def FwDNAMers(K, seq):
+    return FwKmers(DNAAlphabet2, K, seq)
+
+
+def FwRNAMers(K, seq):
+    return FwKmers(RNAAlphabet2, K, seq)
+
+
+def FwRvDNAIterator(K, seq):
+    return FwRvIterator(DNAAlphabet2, K, seq)
+
+
+def CanonicalDNAMers(K, seq):
+    return CanonicalKmers(DNAAlphabet2, K, seq)
+
+
+def CanonicalRNAMers(K, seq):
+    return CanonicalKmers(RNAAlphabet2, K, seq)
+
+
+def UnambiguousDNAMers(K, seq):
+    return UnambiguousKmers(DNAAlphabet2, K, seq)
+
+
+def UnambiguousRNAMers(K, seq):
+    return UnambiguousKmers(RNAAlphabet2, K, seq)
+
+
+def fx_hash(kmers: np.ndarray, h: int = 0, ctx: Optional[Context] = None) -> np.ndarray:
+    """fx_hash.(kmers, h) on the device; `kmers` is u64[n, N] (N may be 0: the empty k-mer)."""
+    ctx = ctx or default_context()
+    km = np.ascontiguousarray(kmers, dtype=np.uint64)
+    if km.ndim == 1:
+        km = km.reshape(-1, 1)
+    n, N = km.shape
+    dk = ctx.to_device(km) if km.size else None
+    do = ctx.alloc(max(n, 1) * 8)
+    ctx._check(ctx.lib.kmc_fx_hash(ctx.handle, dk.ptr if dk else None, n, N, h, do.ptr))
+    out = do.download(np.uint64, n)
+    if dk:
+        dk.free()
+    do.free()
+    return out
+
+
+def bucket_count(rs, K: int, bucket_bits: int, ctx: Optional[Context] = None, table: Optional[DeviceBuffer] = None):
+    """Histogram of fx_hash(canonical k-mer) >> (64 - bucket_bits) (north_star extension).
+    Returns (table u32[2^bucket_bits] on the host, n_kmers, kernel_ms)."""
+    _check_K(K)
+    ctx = ctx or default_context()
+    drs = rs if isinstance(rs, DeviceReadSet) else DeviceReadSet(ctx, rs)
+    own = table is None
+    if own:
+        table = ctx.alloc(4 << bucket_bits)
+        ctx._check(ctx.lib.kmc_memset(ctx.handle, table.ptr, 0, 4 << bucket_bits))
+    res = kmc_result()
+    ctx._check(ctx.lib.kmc_bucket_count(ctx.handle, C.byref(drs.desc), K, bucket_bits, table.ptr, C.byref(res)))
+    host = table.download(np.uint32, 1 << bucket_bits)
+    if own:
+        table.free()
+    return host, int(res.n_written), float(res.kernel_ms)

@@ -1,0 +1,341 @@
+"""GPU parity: libkmerscuda (through the C ABI) against the CPU oracle, bit-exact.
+
+Every test here calls the CUDA library; the oracle (oracle/) is only the checker.  The bar is
+bit-exact equality of every limb, hash and index.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import kmertools as kt
+from oracle import oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+DIFF = KATS["differential_sequences"]
+MODES = {"fw": 0, "fwrv": 1, "canon": 2, "unambig": 3}
+
+
+@pytest.fixture(scope="module")
+def kc():
+    import kmerscuda
+    return kmerscuda
+
+
+@pytest.fixture(scope="module")
+def ctx(kc):
+    return kc.default_context()
+
+
+def dna(s):
+    return s.upper().replace("U", "T")
+
+
+def rows(a):
+    return [tuple(int(v) for v in r) for r in a]
+
+
+# ----------------------------------------------------------------------------- golden vectors
+def test_kat_fx_hash(kc):
+    for e in KATS["fx_hash"]:
+        limbs = [int(x, 16) for x in e["limbs"]] if "limbs" in e else list(kt.kmer_limbs(dna(e["kmer"])))
+        got = kc.fx_hash(np.array([limbs], dtype=np.uint64).reshape(1, len(limbs)))
+        assert int(got[0]) == int(e["hash"], 16), e
+
+
+def test_kat_canonical(kc):
+    for e in KATS["canonical"]:
+        got = kc.CanonicalDNAMers(e["k"], kc.LongDNA2(dna(e["seq"]))).collect()
+        assert rows(got) == [kt.kmer_limbs(dna(x)) for x in e["expect"]]
+
+
+def test_kat_fwrv(kc):
+    for e in KATS["fwrv"]:
+        got = kc.FwRvDNAIterator(e["k"], kc.LongDNA2(dna(e["seq"]))).collect()  # [n, 2, N]
+        assert rows(got[:, 0, :]) == [kt.kmer_limbs(p[0]) for p in e["expect"]]
+        assert rows(got[:, 1, :]) == [kt.kmer_limbs(p[1]) for p in e["expect"]]
+
+
+def test_kat_encoding(kc):
+    for e in KATS["as_integer"]:
+        got = kc.FwDNAMers(len(e["kmer"]), kc.LongDNA2(e["kmer"])).collect()
+        assert rows(got) == [(int(e["value"], 16),)]
+
+
+def test_kat_iscanonical(kc):
+    for e in KATS["iscanonical"]:
+        k = len(e["kmer"])
+        fwrv = kc.FwRvDNAIterator(k, kc.LongDNA2(e["kmer"])).collect()
+        fw, rv = tuple(map(int, fwrv[0, 0])), tuple(map(int, fwrv[0, 1]))
+        assert (fw <= rv) == e["value"]
+        assert rv == kt.kmer_limbs(kt.revcomp(e["kmer"]))
+
+
+@pytest.mark.parametrize("key", ["fw_2bit", "smaller_than_k", "fwrv", "fwrv_k9", "canonical", "unambiguous_2bit"])
+def test_reference_differential_sequences_2bit(kc, key):
+    e = DIFF[key]
+    k = e["k"]
+    for s in map(dna, e["seqs"]):
+        seq = kc.LongDNA2(s)
+        assert rows(kc.FwDNAMers(k, seq).collect()) == kt.naive_fw(s, k)
+        fr = kc.FwRvDNAIterator(k, seq).collect()
+        want = kt.naive_fwrv(s, k)
+        assert rows(fr[:, 0, :]) == [w[0] for w in want] and rows(fr[:, 1, :]) == [w[1] for w in want]
+        assert rows(kc.CanonicalDNAMers(k, seq).collect()) == kt.naive_canonical(s, k)
+        km, pos = kc.UnambiguousDNAMers(k, seq).collect()
+        assert rows(km) == kt.naive_fw(s, k) and pos.tolist() == list(range(1, len(s) - k + 2))
+
+
+# ------------------------------------------------------------------- randomised, vs the oracle
+KS = [1, 2, 5, 13, 14, 16, 29, 30, 31, 32, 33, 47, 48, 49, 63, 64, 65, 80, 81, 96, 97, 112, 113, 127, 128]
+
+
+@pytest.mark.parametrize("k", KS)
+def test_single_sequence_all_modes(kc, k):
+    rng = np.random.default_rng(0xCCFB + k)
+    for length in sorted({0, k - 1, k, k + 1, k + 2, k + 3, k + 4, k + 5, k + 31, k + 32, k + 33, 3 * k + 257, 1000}):
+        s = kt.random_dna(rng, max(length, 0))
+        w = kt.pack2(s)
+        seq = kc.LongSequence(kc.DNAAlphabet2, w, len(s))
+        rs = kc.ReadSet.single(seq)
+        a, b, h = ko.iterate(w, len(s), k, ko.FWRV, want_hash=True)
+        e = kc.extract(MODES["fwrv"], rs, k, hash=True)
+        assert np.array_equal(e.kmers, a) and np.array_equal(e.rv, b) and np.array_equal(e.hash, h)
+        e = kc.extract(MODES["fwrv"], rs, k, aos=True)
+        assert np.array_equal(e.kmers[:, 0, :], a) and np.array_equal(e.kmers[:, 1, :], b)
+        c, _, hc = ko.iterate(w, len(s), k, ko.CANON, want_hash=True)
+        e = kc.extract(MODES["canon"], rs, k, hash=True)
+        assert np.array_equal(e.kmers, c) and np.array_equal(e.hash, hc)
+        e = kc.extract(MODES["fw"], rs, k)
+        assert np.array_equal(e.kmers, a)
+        km, pos = ko.unambiguous(w, len(s), k, src_bits=2)
+        e = kc.extract(MODES["unambig"], rs, k)
+        assert np.array_equal(e.kmers, km) and np.array_equal(e.index, pos)
+        e = kc.extract(MODES["unambig"], rs, k, aos=True)
+        N = kc.n_limbs(k)
+        assert np.array_equal(e.kmers[:, :N], km) and np.array_equal(e.kmers[:, N].astype(np.int64), pos)
+
+
+def make_ragged(rng, lens):
+    seqs = [kt.random_dna(rng, n) for n in lens]
+    packed = [kt.pack2(s) for s in seqs]
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(p) for p in packed])
+    words = np.concatenate([p for p in packed if len(p)] + [np.zeros(1, np.uint64)])
+    return seqs, words, off[:-1].copy(), np.array(lens, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("k", [1, 7, 31, 32, 33, 63, 64, 96, 127])
+def test_ragged_read_set(kc, k):
+    rng = np.random.default_rng(100 + k)
+    lens = [0, 1, k - 1, k, k + 1, k + 2, k + 3, 150, 151, 152, 153, 0, 0, k, 40, 999, k + 5] + \
+        rng.integers(0, 400, size=300).tolist()
+    lens = [max(0, int(x)) for x in lens]
+    seqs, words, off, ln = make_ragged(rng, lens)
+    rs = kc.ReadSet(2, words, len(lens), seq_word_offset=off, seq_len=ln)
+    for mode, omode in (("fw", ko.FW), ("fwrv", ko.FWRV), ("canon", ko.CANON)):
+        a, b, h, out_off = ko.batch_iterate(words, len(lens), k, omode, word_off=off, seq_len=ln, want_hash=True)
+        e = kc.extract(MODES[mode], rs, k, hash=True, want_seq_offsets=True)
+        assert e.n == a.shape[0]
+        assert np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+        assert np.array_equal(e.seq_out_offset, out_off)
+        if b is not None:
+            assert np.array_equal(e.rv, b)
+    # UnambiguousKmers over 2-bit reads: every window, 1-based index within its read
+    e = kc.extract(MODES["unambig"], rs, k)
+    want_idx = np.concatenate([np.arange(1, max(0, n - k + 1) + 1) for n in lens] + [np.zeros(0, np.int64)])
+    assert np.array_equal(e.index, want_idx)
+
+
+@pytest.mark.parametrize("k,length", [(31, 150), (31, 151), (31, 149), (21, 100), (63, 150), (63, 151), (5, 36),
+                                      (31, 31), (31, 30), (32, 250), (97, 300)])
+def test_uniform_read_set(kc, k, length):
+    rng = np.random.default_rng(k * 1000 + length)
+    n_reads = 3000
+    stride = (length + 31) // 32 + (1 if length % 7 == 0 else 0)  # sometimes padded strides
+    words = rng.integers(0, 2**64, size=n_reads * stride, dtype=np.uint64)
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    for mode, omode in (("canon", ko.CANON), ("fwrv", ko.FWRV)):
+        a, b, h, _ = ko.batch_iterate(words, n_reads, k, omode, uniform_len=length, uniform_stride=stride,
+                                      want_hash=True)
+        e = kc.extract(MODES[mode], rs, k, hash=True)
+        assert e.n == a.shape[0]
+        assert np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+        if b is not None:
+            assert np.array_equal(e.rv, b)
+
+
+def test_subsequence_views(kc):
+    """first_symbol_offset: a LongSubSeq-style view starting inside a word."""
+    rng = np.random.default_rng(77)
+    s = kt.random_dna(rng, 700)
+    w = kt.pack2(s)
+    for first in (1, 15, 16, 31, 32, 33, 77):
+        for k in (5, 31, 33, 64):
+            n = 400
+            rs = kc.ReadSet(2, w, 1, uniform_len=n, uniform_stride_words=w.size, first_symbol_offset=first)
+            a, _, h = ko.iterate(w, n, k, ko.CANON, first=first, want_hash=True)
+            e = kc.extract(MODES["canon"], rs, k, hash=True)
+            assert np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+
+
+def test_unaligned_output_buffers(kc, ctx):
+    """Output pointers that are only 8-byte aligned take the scalar-store path."""
+    from kmerscuda import _abi
+    rng = np.random.default_rng(5)
+    k, n = 31, 5000
+    s = kt.random_dna(rng, n)
+    w = kt.pack2(s)
+    drs = kc.DeviceReadSet(ctx, kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet2, w, n)))
+    nw = n - k + 1
+    da, dh = ctx.alloc((nw + 4) * 8), ctx.alloc((nw + 4) * 8)
+    out = _abi.kmc_out(da.ptr + 8, None, dh.ptr + 24, None, None, nw, 0)
+    res = _abi.kmc_result()
+    st = ctx.lib.kmc_extract(ctx.handle, C.byref(drs.desc), k, MODES["canon"], _abi.KMC_HASH_FX, C.byref(out),
+                             C.byref(res))
+    assert st == 0 and res.n_written == nw
+    a, _, h = ko.iterate(w, n, k, ko.CANON, want_hash=True)
+    assert np.array_equal(da.download(np.uint64, nw, 8), a[:, 0])
+    assert np.array_equal(dh.download(np.uint64, nw, 24), h)
+
+
+def test_errors(kc, ctx):
+    from kmerscuda import _abi
+    rs = kc.ReadSet.single(kc.LongDNA2("ACGTACGTAC"))
+    drs = kc.DeviceReadSet(ctx, rs)
+    da = ctx.alloc(64)
+    res = _abi.kmc_result()
+    out = _abi.kmc_out(da.ptr, None, None, None, None, 2, 0)  # too small: 8 windows for K=3
+    assert ctx.lib.kmc_extract(ctx.handle, C.byref(drs.desc), 3, 0, 0, C.byref(out), C.byref(res)) == _abi.KMC_E_OUT_TOO_SMALL
+    assert ctx.lib.kmc_extract(ctx.handle, C.byref(drs.desc), 0, 0, 0, C.byref(out), C.byref(res)) == _abi.KMC_E_BAD_K
+    assert b"at least 1" in ctx.lib.kmc_last_error(ctx.handle)
+    assert ctx.lib.kmc_extract(ctx.handle, C.byref(drs.desc), 129, 0, 0, C.byref(out), C.byref(res)) == _abi.KMC_E_BAD_K
+    assert ctx.lib.kmc_extract(ctx.handle, C.byref(drs.desc), 3, 9, 0, C.byref(out), C.byref(res)) == _abi.KMC_E_BAD_ARG
+    n = C.c_uint64()
+    assert ctx.lib.kmc_count(ctx.handle, C.byref(drs.desc), 3, 0, C.byref(n)) == 0 and n.value == 8
+
+
+def test_standalone_fx_hash(kc):
+    rng = np.random.default_rng(9)
+    for N in (1, 2, 3, 4):
+        km = rng.integers(0, 2**64, size=(10_000, N), dtype=np.uint64)
+        for h0 in (0, 1, 0xDEADBEEF12345678):
+            assert np.array_equal(kc.fx_hash(km, h0), ko.fx_hash(km, h0))
+
+
+# --------------------------------------------------------------------- pipelined host path
+@pytest.mark.parametrize("k", [31, 63])
+def test_host_path_single_sequence_chunked(kc, k):
+    """> 4 Mi windows so that kmc_extract_host splits the sequence into several chunks."""
+    n = 9_000_011
+    words = kt.splitmix64(np.arange((n + 31) // 32, dtype=np.uint64) + np.uint64(0xCCFB2D5055D8C990))
+    rs = kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet2, words, n))
+    a, _, h = ko.iterate(words, n, k, ko.CANON, want_hash=True)
+    e = kc.extract(MODES["canon"], rs, k, hash=True, host_path=True)
+    assert e.n == n - k + 1 and np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+    km, pos = ko.unambiguous(words, n, k, src_bits=2)
+    e = kc.extract(MODES["unambig"], rs, k, host_path=True)
+    assert np.array_equal(e.kmers, km) and np.array_equal(e.index, pos)
+
+
+def test_host_path_uniform_reads_chunked(kc):
+    k, length, stride, n_reads = 31, 150, 5, 90_000  # 10.8 M windows -> 3 chunks
+    words = kt.splitmix64(np.arange(n_reads * stride, dtype=np.uint64) + np.uint64(439824))
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    a, b, h, _ = ko.batch_iterate(words, n_reads, k, ko.FWRV, uniform_len=length, uniform_stride=stride, want_hash=True)
+    e = kc.extract(MODES["fwrv"], rs, k, hash=True, host_path=True, want_seq_offsets=True)
+    assert np.array_equal(e.kmers, a) and np.array_equal(e.rv, b) and np.array_equal(e.hash, h)
+    assert np.array_equal(e.seq_out_offset, np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(120))
+    e = kc.extract(MODES["fwrv"], rs, k, aos=True, host_path=True)
+    assert np.array_equal(e.kmers[:, 0, :], a) and np.array_equal(e.kmers[:, 1, :], b)
+
+
+def test_host_path_ragged_reads_chunked(kc):
+    rng = np.random.default_rng(21)
+    k = 31
+    lens = rng.integers(0, 400, size=60_000).tolist()  # ~ 10 M windows -> several chunks
+    ln = np.array(lens, dtype=np.uint64)
+    nw = (ln + np.uint64(31)) // np.uint64(32)
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(nw)
+    words = kt.splitmix64(np.arange(int(off[-1]) + 1, dtype=np.uint64) + np.uint64(7))
+    rs = kc.ReadSet(2, words, len(lens), seq_word_offset=off[:-1].copy(), seq_len=ln)
+    a, _, h, out_off = ko.batch_iterate(words, len(lens), k, ko.CANON, word_off=off[:-1].copy(), seq_len=ln,
+                                        want_hash=True)
+    e = kc.extract(MODES["canon"], rs, k, hash=True, host_path=True, want_seq_offsets=True)
+    assert e.n == a.shape[0] and np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+    assert np.array_equal(e.seq_out_offset, out_off)
+    e2 = kc.extract(MODES["canon"], rs, k, hash=True)
+    assert np.array_equal(e2.kmers, a) and np.array_equal(e2.hash, h)
+
+
+# ---------------------------------------------------------------------- bucket count table
+@pytest.mark.parametrize("k,bits", [(31, 20), (63, 12), (15, 28)])
+def test_bucket_count(kc, k, bits):
+    rng = np.random.default_rng(k)
+    n_reads, length, stride = 20_000, 150, 5
+    words = rng.integers(0, 2**64, size=n_reads * stride, dtype=np.uint64)
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    table, n, _ = kc.bucket_count(rs, k, bits)
+    _, _, h, _ = ko.batch_iterate(words, n_reads, k, ko.CANON, uniform_len=length, uniform_stride=stride, want_hash=True)
+    want = np.bincount((h >> np.uint64(64 - bits)).astype(np.int64), minlength=1 << bits).astype(np.uint32)
+    assert n == h.size and int(table.sum()) == h.size
+    assert np.array_equal(table, want)
+
+
+# ----------------------------------------------- full-size properties (BASELINE config C2 shape)
+def test_full_size_properties(kc, ctx):
+    """10 M x 150 bp reads, K=31, canonical + fx_hash, outputs resident on the device (19.2 GB).
+    Size-independent checks: (1) the fused hash stream equals kmc_fx_hash over the canonical
+    stream, (2) canonical(read) == canonical(reverse-complemented read) reversed -- checked on
+    the device with torch, (3) a random sample of reads equals the oracle bit for bit."""
+    import torch
+    from kmerscuda import _abi
+    free, _ = torch.cuda.mem_get_info()
+    n_reads = 10_000_000 if free > 60e9 else 1_000_000
+    k, length, stride = 31, 150, 5
+    wpr = length - k + 1
+    g = torch.Generator(device="cuda").manual_seed(439824)
+    words = torch.randint(-2**63, 2**63 - 1, (n_reads * stride,), dtype=torch.int64, device="cuda", generator=g)
+    # trailing bits of each read's last word are zero in a LongSequence (150 = 4*32 + 22 symbols)
+    words.view(n_reads, stride)[:, stride - 1] &= (1 << (2 * (length - 32 * (stride - 1)))) - 1
+    canon = torch.empty(n_reads * wpr, dtype=torch.int64, device="cuda")
+    hsh = torch.empty(n_reads * wpr, dtype=torch.int64, device="cuda")
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), n_reads, None, None, length, stride, 2, 0)
+    out = _abi.kmc_out(canon.data_ptr(), None, hsh.data_ptr(), None, None, n_reads * wpr, 0)
+    res = _abi.kmc_result()
+    torch.cuda.synchronize()
+    ctx._check(ctx.lib.kmc_extract(ctx.handle, C.byref(desc), k, MODES["canon"], _abi.KMC_HASH_FX, C.byref(out), C.byref(res)))
+    assert res.n_written == n_reads * wpr
+    # (1) fused hash == standalone hash of the canonical stream
+    h2 = torch.empty_like(hsh)
+    ctx._check(ctx.lib.kmc_fx_hash(ctx.handle, canon.data_ptr(), canon.numel(), 1, 0, h2.data_ptr()))
+    ctx.sync()
+    assert torch.equal(hsh, h2)
+    del h2
+    # (2) strand symmetry: the canonical k-mers of the reverse-complemented reads are the same
+    #     multiset per read, in reverse order.  Build the RC reads with the library itself:
+    #     rv k-mer of window 0 of a K=L "read" is the RC read; cheaper: check on a 200k-read slice.
+    m = min(n_reads, 200_000)
+    sl = words[: m * stride].cpu().numpy().view(np.uint64)
+    codes = ((sl.reshape(m, stride, 1) >> (np.arange(32, dtype=np.uint64) * np.uint64(2))) & np.uint64(3)).reshape(m, -1)[:, :length]
+    rc_codes = (3 - codes[:, ::-1]).astype(np.uint64)
+    pad = np.zeros((m, stride * 32), dtype=np.uint64)
+    pad[:, :length] = rc_codes
+    rc_words = np.bitwise_or.reduce(pad.reshape(m, stride, 32) << (np.arange(32, dtype=np.uint64) * np.uint64(2)), axis=2).reshape(-1)
+    rs_rc = kc.ReadSet(2, rc_words, m, uniform_len=length, uniform_stride_words=stride)
+    e = kc.extract(MODES["canon"], rs_rc, k, hash=True)
+    fwd = canon[: m * wpr].cpu().numpy().view(np.uint64).reshape(m, wpr)
+    assert np.array_equal(e.kmers.reshape(m, wpr)[:, ::-1], fwd)
+    # (3) sampled reads against the oracle
+    rng = np.random.default_rng(1)
+    idx = np.sort(rng.choice(n_reads, size=2000, replace=False))
+    for r in idx[:: 1 if n_reads <= 1_000_000 else 1]:
+        w = words[r * stride:(r + 1) * stride].cpu().numpy().view(np.uint64)
+        a, _, h = ko.iterate(w, length, k, ko.CANON, want_hash=True)
+        assert np.array_equal(canon[r * wpr:(r + 1) * wpr].cpu().numpy().view(np.uint64), a[:, 0])
+        assert np.array_equal(hsh[r * wpr:(r + 1) * wpr].cpu().numpy().view(np.uint64), h)
