@@ -204,8 +204,8 @@ enum { KO_FW = 0, KO_FWRV = 1, KO_CANON = 2 };
  * Outputs are N limbs per k-mer, head first.  Returns status; *n_out = k-mers
  * yielded before any error; on KO_E_AMBIGUOUS *err_pos is the 1-based symbol
  * index (relative to the sequence) and *err_enc the offending nibble. */
-INL int iterate_one(const u64 *words, u64 first, u64 len, int src_bits, int K, const int N,
-                    int mode, u64 *out_a, u64 *out_b, u64 *out_hash,
+INL int iterate_one(const u64 *words, u64 first, u64 len, const int src_bits, int K, const int N,
+                    const int mode, u64 *out_a, u64 *out_b, u64 *out_hash,
                     u64 *n_out, u64 *err_pos, u64 *err_enc)
 {
     u64 fw[KO_MAX_LIMBS], rv[KO_MAX_LIMBS];
@@ -297,6 +297,19 @@ INL void unambiguous_one(const u64 *words, u64 first, u64 len, int src_bits, int
     }
 }
 
+/* Constant (mode, src_bits) instantiation: Julia specialises iterate() on the iterator type and
+ * the RecodingScheme (construction.jl:75-100 is constant-folded), so the CPU baseline gets the
+ * same treatment.  MM and SB are literal constants inside CALL. */
+#define DISPATCH_MODE_BITS(mode, src_bits, CALL)                                   \
+    switch ((mode) * 8 + (src_bits)) {                                             \
+    case KO_FW * 8 + 2: { enum { MM = KO_FW, SB = 2 }; CALL; } break;              \
+    case KO_FW * 8 + 4: { enum { MM = KO_FW, SB = 4 }; CALL; } break;              \
+    case KO_FWRV * 8 + 2: { enum { MM = KO_FWRV, SB = 2 }; CALL; } break;          \
+    case KO_FWRV * 8 + 4: { enum { MM = KO_FWRV, SB = 4 }; CALL; } break;          \
+    case KO_CANON * 8 + 2: { enum { MM = KO_CANON, SB = 2 }; CALL; } break;        \
+    default: { enum { MM = KO_CANON, SB = 4 }; CALL; } break;                      \
+    }
+
 /* Constant-N instantiation so the compiler unrolls the limb loops the way
  * Julia specialises on NTuple{N,UInt64}. */
 #define DISPATCH_N(N, CALL)                                         \
@@ -332,8 +345,10 @@ int ko_iterate(const uint64_t *words, uint64_t first, uint64_t len, int src_bits
     int st = check_k(K);
     if (st) return st;
     int N = n_limbs(K, 2);
-    DISPATCH_N(N, st = iterate_one(words, first, len, src_bits, K, NN, mode, out_a, out_b,
-                                   out_hash, n_out, err_pos, err_enc));
+    if (mode < KO_FW || mode > KO_CANON || (src_bits != 2 && src_bits != 4)) return KO_E_BAD_K;
+    DISPATCH_MODE_BITS(mode, src_bits,
+                       DISPATCH_N(N, st = iterate_one(words, first, len, SB, K, NN, MM, out_a, out_b,
+                                                      out_hash, n_out, err_pos, err_enc)));
     return st;
 }
 
@@ -414,6 +429,7 @@ int ko_batch_iterate(const uint64_t *words, uint64_t n_seqs, const uint64_t *wor
 {
     int st0 = check_k(K);
     if (st0) return st0;
+    if (mode < KO_FW || mode > KO_CANON || (src_bits != 2 && src_bits != 4)) return KO_E_BAD_K;
     const int N = n_limbs(K, 2);
     int failed = 0;
     u64 best_seq = ~(u64)0, best_pos = 0, best_enc = 0;
@@ -427,9 +443,10 @@ int ko_batch_iterate(const uint64_t *words, uint64_t n_seqs, const uint64_t *wor
         u64 oo = out_off ? out_off[r] : (u64)r * ko_n_windows(uniform_len, K);
         u64 n = 0, ep = 0, ee = 0;
         int st = KO_OK;
-        DISPATCH_N(N, st = iterate_one(words + wo, 0, len, src_bits, K, NN, mode,
-                                       out_a + oo * (u64)N, out_b ? out_b + oo * (u64)N : NULL,
-                                       out_hash ? out_hash + oo : NULL, &n, &ep, &ee));
+        DISPATCH_MODE_BITS(mode, src_bits,
+                           DISPATCH_N(N, st = iterate_one(words + wo, 0, len, SB, K, NN, MM,
+                                                          out_a + oo * (u64)N, out_b ? out_b + oo * (u64)N : NULL,
+                                                          out_hash ? out_hash + oo : NULL, &n, &ep, &ee)));
         if (st == KO_E_AMBIGUOUS) {
 #pragma omp critical
             {
