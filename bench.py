@@ -88,7 +88,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -213,7 +213,11 @@ def run_ours(args, rank, local_rank, world):
     d_words = torch.empty(n_reads * STRIDE, dtype=torch.int64, device="cuda")
     d_canon = torch.empty(n_kmers, dtype=torch.int64, device="cuda")
     d_hash = torch.empty(n_kmers, dtype=torch.int64, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it and torch.cuda.Event
+    # records on it, so the events bracket exactly the kernels they are meant to time
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     ctx._check(lib.kmc_upload(ctx.handle, d_words.data_ptr(), pinned_in.ctypes.data, pinned_in.nbytes))
     ctx.sync()
@@ -356,7 +360,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")

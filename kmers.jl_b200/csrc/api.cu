@@ -644,14 +644,12 @@ int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t mo
                 r += take;
             } else {
                 uint64_t acc = 0, items = 0;
-                uint64_t f = total; // running flat offset, for the group-slot count
                 while (r < n && (acc < target || c.nseq == 0)) {
                     uint64_t len = hs->seq_len[r];
                     uint64_t wc = len >= K ? len - K + 1 : 0;
                     acc += wc;
                     ++r;
                     ++c.nseq;
-                    (void)f;
                 }
                 // group slots are relative to the chunk's own flat origin (0), recomputed on device;
                 // the host only needs the total to skip the read-back

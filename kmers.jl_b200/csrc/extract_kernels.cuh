@@ -20,6 +20,8 @@ enum : int { MODE_FW = 0, MODE_FWRV = 1, MODE_CANON = 2 };
 enum : int { SINK_STREAMS = 0, SINK_BUCKETS = 1 };
 
 constexpr int kBlockThreads = 256;
+constexpr int kTileIters = 8;                                // work items per thread per tile
+constexpr int kTileItems = kBlockThreads * kTileIters;       // work items per block
 
 struct ExtractParams {
     const uint32_t *w32; // sequence stream viewed as 32-bit words
@@ -36,7 +38,7 @@ struct ExtractParams {
     uint64_t stride_units;
     uint64_t wpr;        // windows per read
     uint64_t gprm;       // group slots per read
-    uint64_t it_dq, it_dr; // divmod(grid stride in items, gprm)
+    uint64_t it_dq, it_dr; // divmod(kBlockThreads, gprm): per-iteration advance of (r, gi)
     // ragged locator
     const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
     const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
@@ -66,15 +68,37 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     constexpr bool WANT_FW = true;
     constexpr bool WANT_RV = (MODE != MODE_FW);
 
-    uint64_t item = static_cast<uint64_t>(blockIdx.x) * kBlockThreads + threadIdx.x;
-    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kBlockThreads;
+    // One tile of kTileIters x 256 consecutive work items per block; blocks are scheduled by the
+    // hardware as SMs drain, which balances the SMs (a static persistent partition left the
+    // fastest SMs idle for 25 % of the kernel: profiles/r01_notes.md).
+    const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
     uint64_t r = 0, gi = 0;
     if (!RAGGED) {
-        r = item / p.gprm;
-        gi = item - r * p.gprm;
+        // (r, gi) = divmod(item, gprm): one 64-bit division per BLOCK, then a 32-bit one per thread
+        __shared__ uint64_t s_r0, s_gi0;
+        if (threadIdx.x == 0) {
+            s_r0 = tile_base / p.gprm;
+            s_gi0 = tile_base - s_r0 * p.gprm;
+        }
+        __syncthreads();
+        r = s_r0;
+        gi = s_gi0 + threadIdx.x;
+        if (p.gprm > 0xffffffffull - kTileItems) { // gi0 + tid wraps at most once
+            if (gi >= p.gprm) {
+                gi -= p.gprm;
+                ++r;
+            }
+        } else {
+            const uint32_t q = static_cast<uint32_t>(gi) / static_cast<uint32_t>(p.gprm);
+            gi -= static_cast<uint64_t>(q) * p.gprm;
+            r += q;
+        }
     }
 
-    for (; item < p.items; item += stride) {
+#pragma unroll 1
+    for (int it = 0; it < kTileIters; ++it) {
+        const uint64_t item = tile_base + static_cast<uint64_t>(it) * kBlockThreads + threadIdx.x;
+        if (item >= p.items) break;
         uint64_t f0, wcount, unit_off;
         if (RAGGED) {
             // largest r with item_off[r] <= item
@@ -216,30 +240,19 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     }
 }
 
-// Host-side launcher.  The grid is exactly the resident capacity of the device (persistent
-// grid-stride kernel: blocks-per-SM from the occupancy calculator x SM count), or fewer blocks when
-// the problem is smaller.  Defined per N in extract_n*.cu so the instantiations compile in parallel.
+// Host-side launcher: one block per tile of kTileItems work items.  Defined per N in
+// extract_n*.cu so the instantiations compile in parallel.
 using ExtractLaunchFn = cudaError_t (*)(ExtractParams, int sm_count, cudaStream_t);
 
 template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS>
-cudaError_t launch_extract(ExtractParams p, int sm_count, cudaStream_t stream)
+cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t stream)
 {
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extract_kernel<N, NX, MODE, HASH, RAGGED, SINK>,
-                                                                      kBlockThreads, 0);
-        if (e != cudaSuccess) return e;
-        blocks_per_sm = nb > 0 ? nb : 1;
-    }
-    const uint64_t want = (p.items + kBlockThreads - 1) / kBlockThreads;
-    const uint64_t cap = static_cast<uint64_t>(sm_count) * blocks_per_sm;
-    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-    if (grid == 0) return cudaSuccess;
-    const uint64_t stride = static_cast<uint64_t>(grid) * kBlockThreads;
-    p.it_dq = stride / p.gprm;
-    p.it_dr = stride % p.gprm;
-    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK><<<grid, kBlockThreads, 0, stream>>>(p);
+    const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
+    if (tiles == 0) return cudaSuccess;
+    if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    p.it_dq = kBlockThreads / p.gprm;
+    p.it_dr = kBlockThreads % p.gprm;
+    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -41,19 +41,24 @@ cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint6
     return cudaGetLastError();
 }
 
-// Every thread writes 32 bytes per step with one 256-bit store; grid-stride; nothing is read.
+// Every thread writes 32 bytes per step with one 256-bit store; nothing is read.  Same launch shape
+// as the extraction kernels (one tile of 8 x 256 stores per block, hardware-scheduled), so it is the
+// write ceiling for exactly that store pattern.
 __global__ void __launch_bounds__(256) store_probe_kernel(uint64_t *__restrict__ p, uint64_t n_vec)
 {
-    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride)
-        st_v4(p + 4 * i, i, i + 1, i + 2, i + 3);
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * 2048 + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const uint64_t i = base + static_cast<uint64_t>(it) * 256;
+        if (i < n_vec) st_v4(p + 4 * i, i, i + 1, i + 2, i + 3);
+    }
 }
 
-cudaError_t launch_store_probe(void *dptr, uint64_t bytes, int sm_count, cudaStream_t stream)
+cudaError_t launch_store_probe(void *dptr, uint64_t bytes, int /*sm_count*/, cudaStream_t stream)
 {
     uint64_t n_vec = bytes / 32;
     if (n_vec == 0) return cudaSuccess;
-    store_probe_kernel<<<sm_count * 8, 256, 0, stream>>>(static_cast<uint64_t *>(dptr), n_vec);
+    store_probe_kernel<<<static_cast<unsigned>((n_vec + 2047) / 2048), 256, 0, stream>>>(static_cast<uint64_t *>(dptr), n_vec);
     return cudaGetLastError();
 }
 
