@@ -54,14 +54,29 @@ struct ExtractParams {
     // fused bucket count (MODE_CANON only): table[fx_hash >> bucket_shift] += 1
     uint32_t *bucket_table;
     uint32_t bucket_shift;
-    // 4-bit sources: bit P of vstart = "no uncertain symbol in [P, P+K)" (absolute symbol index)
+    // 4-bit sources (FourToTwo): the kernels run on the recoded 2-bit stream (unit_bits = 32, one
+    // unit per source word) and consult vstart: bit P = "no uncertain symbol in [P, P+K)", P the
+    // absolute symbol index in the stream.
     const uint32_t *vstart;
+    unsigned long long *err_flat;  // strict modes: atomicMin of the first flat window with an uncertain symbol
+    const uint64_t *tile_out_off;  // UnambiguousKmers: exclusive scan of the per-tile emitted counts
+    uint64_t *tile_count;          // UnambiguousKmers count pass: emitted k-mers per tile
 };
+
+// Validity bits of the slots [jlo, jhi) of one item: bit j set <=> window j has no uncertain symbol.
+// sym0 = absolute symbol index (in the recoded stream) of slot 0; sym0 + jlo >= 0.
+KMC_DEV uint32_t valid_slots(const uint32_t *__restrict__ vstart, int64_t sym0, int jlo, int jhi)
+{
+    const int64_t q = sym0 + jlo;
+    const uint32_t w0 = __ldg(vstart + (q >> 5)), w1 = __ldg(vstart + (q >> 5) + 1);
+    const uint32_t bits = __funnelshift_r(w0, w1, static_cast<uint32_t>(q) & 31u);
+    return (bits & ((1u << (jhi - jlo)) - 1u)) << jlo;
+}
 
 // G windows per thread for N limbs: G*N*8 must be a multiple of 32 bytes.
 template <int N> struct GroupOf { static constexpr int G = (N == 1) ? 4 : (N == 2) ? 2 : (N == 3) ? 4 : 1; };
 
-template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS>
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false>
 __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractParams p)
 {
     constexpr int G = GroupOf<N>::G;
@@ -125,6 +140,14 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
         if (jhi > jlo) {
             const int64_t bit = static_cast<int64_t>(unit_off) * p.unit_bits +
                                 2 * (static_cast<int64_t>(p.first) + wbase);
+            if (STRICT4) {
+                // FourToTwo, strict (FwKmers.jl:104-115, CanonicalKmers.jl:131-144): an uncertain symbol
+                // is an error.  Record the first offending window; the host resolves it to the symbol
+                // the reference would have thrown on.
+                const uint32_t ok = valid_slots(p.vstart, bit >> 1, jlo, jhi);
+                const uint32_t want = ((1u << (jhi - jlo)) - 1u) << jlo;
+                if (ok != want) atomicMin(p.err_flat, static_cast<unsigned long long>(q * G + (__ffs(ok ^ want) - 1)));
+            }
             uint32_t x[NX];
             load_block<NX>(p.w32, p.nw32, bit, x);
             uint64_t fw[G][N], rv[G][N];
@@ -240,11 +263,190 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// UnambiguousKmers over a 4-bit source (UnambiguousKmers.jl:134-148): every window whose K symbols
+// are all certain, with its 1-based start, in order -- a variable-length, ORDERED output.
+//
+// Same work decomposition as extract_kernel.  Per block iteration (256 items = up to 256*G windows)
+//   1. each thread reads the validity bits of its G windows and counts them,
+//   2. a block-wide exclusive scan turns the counts into compacted slots,
+//   3. threads stage their surviving k-mers / indices / hashes in shared memory (XOR-swizzled so
+//      that the 4-consecutive-slots-per-thread pattern is bank-conflict free),
+//   4. the block copies the staged run to global memory with fully coalesced stores.
+// The output position of a tile comes from an exclusive scan of per-tile counts produced by the
+// COUNT_ONLY instantiation of this kernel (which reads one validity word per item and nothing else).
+// ---------------------------------------------------------------------------------------------
+KMC_DEV uint32_t swz(uint32_t w) { return w ^ ((w >> 4) & 3u); }
+
+template <int N, int NX, bool HASH, bool RAGGED, bool COUNT_ONLY>
+__global__ void __launch_bounds__(kBlockThreads) compact_kernel(const ExtractParams p)
+{
+    constexpr int G = GroupOf<N>::G;
+    constexpr int CAP = kBlockThreads * G; // staged elements per iteration
+    __shared__ uint64_t s_a[COUNT_ONLY ? 1 : CAP * N];
+    __shared__ uint64_t s_i[COUNT_ONLY ? 1 : CAP];
+    __shared__ uint64_t s_h[(COUNT_ONLY || !HASH) ? 1 : CAP];
+    __shared__ uint32_t s_w[kBlockThreads / 32];
+    __shared__ uint64_t s_r0, s_gi0;
+
+    const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t r = 0, gi = 0;
+    if (!RAGGED) {
+        if (threadIdx.x == 0) {
+            s_r0 = tile_base / p.gprm;
+            s_gi0 = tile_base - s_r0 * p.gprm;
+        }
+        __syncthreads();
+        r = s_r0;
+        gi = s_gi0 + threadIdx.x;
+        if (p.gprm > 0xffffffffull - kTileItems) {
+            if (gi >= p.gprm) {
+                gi -= p.gprm;
+                ++r;
+            }
+        } else {
+            const uint32_t q = static_cast<uint32_t>(gi) / static_cast<uint32_t>(p.gprm);
+            gi -= static_cast<uint64_t>(q) * p.gprm;
+            r += q;
+        }
+    }
+    uint64_t out_run = COUNT_ONLY ? 0 : __ldg(p.tile_out_off + blockIdx.x); // next output element of this tile
+    uint32_t my_count = 0;
+    const bool aos = p.aos != 0;
+
+#pragma unroll 1
+    for (int it = 0; it < kTileIters; ++it) {
+        const uint64_t item0 = tile_base + static_cast<uint64_t>(it) * kBlockThreads;
+        if (item0 >= p.items) break; // block-uniform
+        const uint64_t item = item0 + threadIdx.x;
+        uint32_t m = 0;
+        int64_t wbase = 0, bit = 0;
+        if (item < p.items) {
+            uint64_t f0, wcount;
+            if (RAGGED) {
+                uint64_t lo = 0, hi = p.n_seqs;
+                while (hi - lo > 1) {
+                    uint64_t mid = (lo + hi) >> 1;
+                    if (__ldg(p.item_off + mid) <= item) lo = mid; else hi = mid;
+                }
+                r = lo;
+                gi = item - __ldg(p.item_off + r);
+                f0 = __ldg(p.win_off + r);
+                wcount = __ldg(p.win_off + r + 1) - f0;
+            } else {
+                f0 = r * p.wpr;
+                wcount = p.wpr;
+            }
+            const uint64_t unit_off = p.seq_unit_off ? __ldg(p.seq_unit_off + r) - p.unit_bias : r * p.stride_units;
+            const uint64_t q = f0 / G + gi;
+            wbase = static_cast<int64_t>(q * G - f0);
+            const int64_t rem = static_cast<int64_t>(wcount) - wbase;
+            const int jlo = wbase < 0 ? static_cast<int>(-wbase) : 0;
+            const int jhi = rem < G ? static_cast<int>(rem) : G;
+            bit = static_cast<int64_t>(unit_off) * p.unit_bits + 2 * (static_cast<int64_t>(p.first) + wbase);
+            if (jhi > jlo) m = valid_slots(p.vstart, bit >> 1, jlo, jhi);
+        }
+        const uint32_t cnt = __popc(m);
+        if (COUNT_ONLY) {
+            my_count += cnt;
+        } else {
+            // block-wide exclusive scan of cnt (thread order == output order)
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) s_w[warp] = incl;
+            __syncthreads(); // also: every thread has finished copying out the previous iteration
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kBlockThreads / 32; ++w) {
+                const uint32_t v = s_w[w];
+                before += (w < warp) ? v : 0u;
+                total += v;
+            }
+            uint32_t slot = before + incl - cnt;
+
+            if (m) {
+                uint32_t x[NX];
+                load_block<NX>(p.w32, p.nw32, bit, x);
+                uint64_t fw[G][N], rv[G][N];
+                block_kmers<N, NX, G, true, false>(x, p.s0, p.head_mask, fw, rv);
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    if ((m >> j) & 1u) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) s_a[swz(slot * N + i)] = fw[j][i];
+                        s_i[swz(slot)] = static_cast<uint64_t>(wbase + j + 1 + p.index_base);
+                        if (HASH) s_h[swz(slot)] = fx_hash<N>(fw[j], 0);
+                        ++slot;
+                    }
+                }
+            }
+            __syncthreads();
+            // coalesced copy-out of `total` elements starting at output element out_run
+            if (aos) {
+                // Tuple{Kmer,Int} = {u64[N]; i64}
+                uint64_t *dst = p.out_a + out_run * (N + 1);
+                for (uint32_t w = threadIdx.x; w < total * (N + 1); w += kBlockThreads) {
+                    const uint32_t e = w / (N + 1), c = w - e * (N + 1);
+                    st_u64(dst + w, c < N ? s_a[swz(e * N + c)] : s_i[swz(e)]);
+                }
+            } else {
+                uint64_t *dst = p.out_a + out_run * N;
+                for (uint32_t w = threadIdx.x; w < total * N; w += kBlockThreads) st_u64(dst + w, s_a[swz(w)]);
+                uint64_t *di = reinterpret_cast<uint64_t *>(p.out_index) + out_run;
+                for (uint32_t w = threadIdx.x; w < total; w += kBlockThreads) st_u64(di + w, s_i[swz(w)]);
+            }
+            if (HASH) {
+                uint64_t *dh = p.out_hash + out_run;
+                for (uint32_t w = threadIdx.x; w < total; w += kBlockThreads) st_u64(dh + w, s_h[swz(w)]);
+            }
+            out_run += total;
+        }
+        if (!RAGGED) {
+            r += p.it_dq;
+            gi += p.it_dr;
+            if (gi >= p.gprm) {
+                gi -= p.gprm;
+                ++r;
+            }
+        }
+    }
+
+    if (COUNT_ONLY) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_count += __shfl_xor_sync(0xffffffffu, my_count, d);
+        if (lane == 0) s_w[warp] = my_count;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kBlockThreads / 32; ++w) t += s_w[w];
+            p.tile_count[blockIdx.x] = t;
+        }
+    }
+}
+
+template <int N, int NX, bool HASH, bool RAGGED, bool COUNT_ONLY>
+cudaError_t launch_compact(ExtractParams p, int /*sm_count*/, cudaStream_t stream)
+{
+    const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
+    if (tiles == 0) return cudaSuccess;
+    if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    p.it_dq = kBlockThreads / p.gprm;
+    p.it_dr = kBlockThreads % p.gprm;
+    compact_kernel<N, NX, HASH, RAGGED, COUNT_ONLY><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 // Host-side launcher: one block per tile of kTileItems work items.  Defined per N in
 // extract_n*.cu so the instantiations compile in parallel.
 using ExtractLaunchFn = cudaError_t (*)(ExtractParams, int sm_count, cudaStream_t);
 
-template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS>
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false>
 cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t stream)
 {
     const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
@@ -252,7 +454,8 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     p.it_dq = kBlockThreads / p.gprm;
     p.it_dr = kBlockThreads % p.gprm;
-    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
+    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4>
+        <<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -295,6 +498,64 @@ constexpr int MODE_BUCKETS = -1;
         if (nx == NXMAX) return pick_mode_##N<NXMAX>(mode, hash, ragged);                           \
         if (nx == NXMAX - 1) return pick_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
         if (nx == NXMAX - 2) return pick_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
+        return nullptr;                                                                             \
+    }
+
+// 4-bit (FourToTwo) launchers, one translation unit per N (extract4_n{1,2,3,4}.cu):
+//   strict  FwKmers / FwRvIterator / CanonicalKmers with the uncertain-symbol check
+//   compact UnambiguousKmers (ordered compaction) and its count pass
+ExtractLaunchFn get_strict4_launcher_n1(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_strict4_launcher_n2(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_strict4_launcher_n3(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_strict4_launcher_n4(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_compact_launcher_n1(int nx, bool hash, bool ragged, bool count_only);
+ExtractLaunchFn get_compact_launcher_n2(int nx, bool hash, bool ragged, bool count_only);
+ExtractLaunchFn get_compact_launcher_n3(int nx, bool hash, bool ragged, bool count_only);
+ExtractLaunchFn get_compact_launcher_n4(int nx, bool hash, bool ragged, bool count_only);
+
+#define KMC_DEFINE_FOURBIT_TABLES(FN_STRICT, FN_COMPACT, N)                                         \
+    template <int NX, int MODE>                                                                     \
+    static ExtractLaunchFn pick4_##N(bool hash, bool ragged)                                        \
+    {                                                                                               \
+        if (hash)                                                                                   \
+            return ragged ? &launch_extract<N, NX, MODE, true, true, SINK_STREAMS, true>            \
+                          : &launch_extract<N, NX, MODE, true, false, SINK_STREAMS, true>;          \
+        return ragged ? &launch_extract<N, NX, MODE, false, true, SINK_STREAMS, true>               \
+                      : &launch_extract<N, NX, MODE, false, false, SINK_STREAMS, true>;             \
+    }                                                                                               \
+    template <int NX>                                                                               \
+    static ExtractLaunchFn pick4_mode_##N(int mode, bool hash, bool ragged)                         \
+    {                                                                                               \
+        switch (mode) {                                                                             \
+        case MODE_FW: return pick4_##N<NX, MODE_FW>(hash, ragged);                                  \
+        case MODE_FWRV: return pick4_##N<NX, MODE_FWRV>(hash, ragged);                              \
+        case MODE_CANON: return pick4_##N<NX, MODE_CANON>(hash, ragged);                            \
+        }                                                                                           \
+        return nullptr;                                                                             \
+    }                                                                                               \
+    ExtractLaunchFn FN_STRICT(int nx, int mode, bool hash, bool ragged)                             \
+    {                                                                                               \
+        constexpr int NXMAX = (64 * N + 2 * GroupOf<N>::G - 2 + 31) / 32;                           \
+        if (nx == NXMAX) return pick4_mode_##N<NXMAX>(mode, hash, ragged);                          \
+        if (nx == NXMAX - 1) return pick4_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
+        if (nx == NXMAX - 2) return pick4_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
+        return nullptr;                                                                             \
+    }                                                                                               \
+    template <int NX>                                                                               \
+    static ExtractLaunchFn pickc_##N(bool hash, bool ragged)                                        \
+    {                                                                                               \
+        if (hash)                                                                                   \
+            return ragged ? &launch_compact<N, NX, true, true, false> : &launch_compact<N, NX, true, false, false>; \
+        return ragged ? &launch_compact<N, NX, false, true, false> : &launch_compact<N, NX, false, false, false>;   \
+    }                                                                                               \
+    ExtractLaunchFn FN_COMPACT(int nx, bool hash, bool ragged, bool count_only)                     \
+    {                                                                                               \
+        constexpr int NXMAX = (64 * N + 2 * GroupOf<N>::G - 2 + 31) / 32;                           \
+        if (count_only)                                                                             \
+            return ragged ? &launch_compact<N, NXMAX, false, true, true> : &launch_compact<N, NXMAX, false, false, true>; \
+        if (nx == NXMAX) return pickc_##N<NXMAX>(hash, ragged);                                     \
+        if (nx == NXMAX - 1) return pickc_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(hash, ragged);       \
+        if (nx == NXMAX - 2) return pickc_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(hash, ragged);       \
         return nullptr;                                                                             \
     }
 

@@ -1,23 +1,352 @@
-// fourbit.cu -- 4-bit sources (FourToTwo).  Filled in after the 2-bit path is parity-green.
+// fourbit.cu -- 4-bit sources (FourToTwo, src/construction.jl:85-86): device recoding, the
+// valid-start bit stream, the strict-mode error resolution and the two-phase orchestration of
+// UnambiguousKmers' ordered compaction.  See fourbit.h for the scheme.
 #include "fourbit.h"
 
 namespace kmc {
 
-int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *, int32_t, int32_t, uint32_t, const kmc_out *, kmc_result *,
-                            cudaStream_t, bool)
+namespace {
+
+constexpr uint64_t kNone = ~0ull;
+
+// ---- bit-parallel recoding of one LongSequence{<:NucleicAcidAlphabet{4}} word (16 nibbles) ------
+// 2-bit code of a one-hot nibble = trailing_zeros (A=1,C=2,G=4,T=8 -> 0,1,2,3;
+// construction_utils.jl:51): bit0 = x1|x3, bit1 = x2|x3.
+__device__ __forceinline__ uint32_t recode_word(uint64_t w)
 {
-    ctx->last_error = "4-bit sources are not implemented yet";
-    return KMC_E_UNSUPPORTED;
+    const uint64_t ones = 0x1111111111111111ull;
+    const uint64_t b0 = ((w >> 1) | (w >> 3)) & ones;
+    const uint64_t b1 = ((w >> 2) | (w >> 3)) & ones;
+    uint64_t c = b0 | (b1 << 1); // nibble i holds the code in its low 2 bits
+    c = (c | (c >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    c = (c | (c >> 4)) & 0x00ff00ff00ff00ffull;
+    c = (c | (c >> 8)) & 0x0000ffff0000ffffull;
+    c = (c | (c >> 16)) & 0x00000000ffffffffull;
+    return static_cast<uint32_t>(c);
 }
-int32_t count_unambiguous_4bit(kmc_ctx *ctx, const kmc_seqs *, int32_t, uint64_t *, cudaStream_t)
+
+// bit i set <=> nibble i is not one-hot (count_ones(enc) != 1: the reference's uncertainty test,
+// FwKmers.jl:112, UnambiguousKmers.jl:145; covers IUPAC ambiguity codes, N and gap)
+__device__ __forceinline__ uint32_t uncertain_word(uint64_t w)
 {
-    ctx->last_error = "4-bit sources are not implemented yet";
-    return KMC_E_UNSUPPORTED;
+    const uint64_t s = (w & 0x5555555555555555ull) + ((w >> 1) & 0x5555555555555555ull);
+    const uint64_t t = (s & 0x3333333333333333ull) + ((s >> 2) & 0x3333333333333333ull); // popcount per nibble
+    const uint64_t u = t ^ 0x1111111111111111ull;                                          // zero nibble <=> popcount 1
+    uint64_t n = (u | (u >> 1) | (u >> 2) | (u >> 3)) & 0x1111111111111111ull;
+    n = (n | (n >> 3)) & 0x0303030303030303ull;
+    n = (n | (n >> 6)) & 0x000f000f000f000full;
+    n = (n | (n >> 12)) & 0x000000ff000000ffull;
+    n = (n | (n >> 24)) & 0x000000000000ffffull;
+    return static_cast<uint32_t>(n);
 }
-int32_t extract_host_4bit(kmc_ctx *ctx, const kmc_seqs *, int32_t, int32_t, uint32_t, const kmc_out *, kmc_result *)
+
+// One thread per PAIR of source words: 2 x u32 of 2-bit codes, 1 x u32 of uncertainty flags.
+__global__ void __launch_bounds__(256) recode_kernel(const uint64_t *__restrict__ words, uint64_t n_words,
+                                                     uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
+                                                     uint64_t n_pairs_padded)
 {
-    ctx->last_error = "4-bit sources are not implemented yet";
-    return KMC_E_UNSUPPORTED;
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_pairs_padded) return;
+    const uint64_t w0 = (2 * i < n_words) ? __ldg(words + 2 * i) : 0x1111111111111111ull;
+    const uint64_t w1 = (2 * i + 1 < n_words) ? __ldg(words + 2 * i + 1) : 0x1111111111111111ull;
+    reinterpret_cast<uint2 *>(rec)[i] = make_uint2(recode_word(w0), recode_word(w1));
+    bad[i] = uncertain_word(w0) | (uncertain_word(w1) << 16);
+}
+
+// vstart word i: bit t set <=> no uncertain symbol in [32i + t, 32i + t + K).
+__global__ void __launch_bounds__(256) vstart_kernel(const uint32_t *__restrict__ bad, uint64_t n_bad, int k,
+                                                     uint32_t *__restrict__ vstart, uint64_t n_out)
+{
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int span = (k + 30) >> 5; // extra words that windows starting in word i can reach
+    uint32_t inv = 0;
+    for (int d = 0; d <= span && inv != 0xffffffffu; ++d) {
+        uint32_t b = (i + d < n_bad) ? __ldg(bad + i + d) : 0u;
+        while (b) {
+            const int q = 32 * d + (__ffs(b) - 1); // position of an uncertain symbol relative to 32i
+            b &= b - 1;
+            const int lo = q - k + 1 > 0 ? q - k + 1 : 0;
+            const int hi = q < 31 ? q : 31;
+            if (lo <= hi) inv |= (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        }
+    }
+    vstart[i] = ~inv;
+}
+
+// Turns the first offending flat window of a strict mode into what the reference throws on:
+// the first symbol with count_ones != 1 of that sequence (its 0-based sequence, 1-based position
+// and 4-bit encoding).  One thread.
+__global__ void resolve_error_kernel(ExtractParams p, int g, const uint64_t *__restrict__ words4,
+                                     const uint32_t *__restrict__ bad, uint64_t flat, uint64_t *__restrict__ err_out)
+{
+    uint64_t r, f0;
+    if (p.win_off) {
+        uint64_t lo = 0, hi = p.n_seqs;
+        while (hi - lo > 1) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (p.win_off[mid] <= flat) lo = mid; else hi = mid;
+        }
+        // skip sequences without windows that share the same offset
+        r = lo;
+        f0 = p.win_off[r];
+    } else {
+        r = flat / p.wpr;
+        f0 = r * p.wpr;
+    }
+    const uint64_t w = flat - f0;
+    const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[r] - p.unit_bias : r * p.stride_units;
+    const uint64_t s0 = unit_off * 16 + p.first; // absolute symbol index of the sequence's first symbol
+    uint64_t pos0 = w + static_cast<uint64_t>(p.k) - 1; // windows before w were clean => only the last symbol can be new
+    if (w == 0) {
+        for (uint64_t j = 0; j < static_cast<uint64_t>(p.k); ++j) {
+            const uint64_t a = s0 + j;
+            if ((bad[a >> 5] >> (a & 31)) & 1u) {
+                pos0 = j;
+                break;
+            }
+        }
+    }
+    const uint64_t a = s0 + pos0;
+    err_out[0] = r;
+    err_out[1] = pos0 + 1;
+    err_out[2] = (words4[a >> 4] >> (4 * (a & 15))) & 15u;
+}
+
+// Emitted k-mers per sequence (UnambiguousKmers): popcount of the valid-start bits over the
+// sequence's windows.  One warp per sequence.
+__global__ void __launch_bounds__(256) seq_valid_counts_kernel(ExtractParams p, uint64_t *__restrict__ cnt)
+{
+    const uint64_t r = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= p.n_seqs) return;
+    uint64_t wcount;
+    if (p.win_off) wcount = p.win_off[r + 1] - p.win_off[r]; else wcount = p.wpr;
+    const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[r] - p.unit_bias : r * p.stride_units;
+    const uint64_t a = unit_off * 16 + p.first, b = a + wcount; // valid-start bits [a, b)
+    uint64_t c = 0;
+    if (wcount) {
+        for (uint64_t w = (a >> 5) + lane; w <= ((b - 1) >> 5); w += 32) {
+            uint32_t v = __ldg(p.vstart + w);
+            if (w == (a >> 5)) v &= 0xffffffffu << (a & 31);
+            if (w == ((b - 1) >> 5)) v &= 0xffffffffu >> (31 - ((b - 1) & 31));
+            c += __popc(v);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) cnt[r] = c;
+}
+
+ExtractLaunchFn strict_launcher(const Geometry &ge, int mode, bool hash, bool ragged)
+{
+    switch (ge.n_limbs) {
+    case 1: return get_strict4_launcher_n1(ge.nx, mode, hash, ragged);
+    case 2: return get_strict4_launcher_n2(ge.nx, mode, hash, ragged);
+    case 3: return get_strict4_launcher_n3(ge.nx, mode, hash, ragged);
+    case 4: return get_strict4_launcher_n4(ge.nx, mode, hash, ragged);
+    }
+    return nullptr;
+}
+
+ExtractLaunchFn compact_launcher(const Geometry &ge, bool hash, bool ragged, bool count_only)
+{
+    switch (ge.n_limbs) {
+    case 1: return get_compact_launcher_n1(ge.nx, hash, ragged, count_only);
+    case 2: return get_compact_launcher_n2(ge.nx, hash, ragged, count_only);
+    case 3: return get_compact_launcher_n3(ge.nx, hash, ragged, count_only);
+    case 4: return get_compact_launcher_n4(ge.nx, hash, ragged, count_only);
+    }
+    return nullptr;
+}
+
+// upper bound of the number of tiles a set can need (windows <= symbols; at most two partial
+// group slots per sequence)
+uint64_t tiles_bound(const kmc_seqs *s, int g)
+{
+    const uint64_t items = s->n_words * 16 / static_cast<uint64_t>(g) + 2 * s->n_seqs + 2;
+    return (items + kTileItems - 1) / kTileItems + 1;
+}
+
+} // namespace
+
+uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
+{
+    const Geometry ge = geometry(k);
+    const uint64_t nb = (s->n_words + 1) / 2;
+    const uint64_t tb = tiles_bound(s, ge.g);
+    uint64_t need = 0;
+    need += round_up(8 * (nb + 2), 256);      // rec32
+    need += 2 * round_up(4 * (nb + 8), 256);  // bad, vstart
+    need += 2 * 256;                          // err_flat, err_out
+    need += layout_scratch_bytes(s);
+    if (mode == KMC_UNAMBIG) {
+        need += round_up(8 * (tb + 1), 256) + round_up(8 * (tb + 2), 256) + round_up(8 * scan_tmp_elems(tb), 256);
+        need += round_up(8 * (s->n_seqs + 1), 256) + round_up(8 * scan_tmp_elems(s->n_seqs), 256); // seq_out_offset
+    }
+    return need + 1024;
+}
+
+int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,
+                        cudaStream_t stream, const KnownTotals &known, uint64_t unit_bias, Scratch &scratch,
+                        uint64_t *host_small, FourBitState *st)
+{
+    st->seqs = s;
+    st->words4 = s->words;
+    st->k = k;
+    st->mode = mode;
+    st->flags = flags;
+    st->ge = geometry(k);
+    st->host_small = host_small;
+    st->unit_bias = unit_bias;
+    st->unambig = (mode == KMC_UNAMBIG);
+    host_small[0] = 0;
+    host_small[1] = kNone;
+    const Geometry &ge = st->ge;
+    const bool hash = (flags & KMC_HASH_FX) != 0;
+
+    const uint64_t nb = (s->n_words + 1) / 2; // pairs of source words = u32 words of flag bits
+    uint32_t *rec = static_cast<uint32_t *>(scratch.take(8 * (nb + 2)));
+    uint32_t *bad = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
+    uint32_t *vstart = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
+    unsigned long long *err_flat = static_cast<unsigned long long *>(scratch.take(8));
+    uint64_t *err_out = static_cast<uint64_t *>(scratch.take(24));
+    if (!rec || !bad || !vstart || !err_flat || !err_out) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+    st->bad = bad;
+    st->err_out = err_out;
+
+    if (nb) {
+        recode_kernel<<<static_cast<unsigned>((nb + 255) / 256), 256, 0, stream>>>(s->words, s->n_words, rec, bad, nb);
+        CU(cudaGetLastError());
+    }
+    vstart_kernel<<<static_cast<unsigned>((nb + 2 + 255) / 256), 256, 0, stream>>>(bad, nb, k, vstart, nb + 2);
+    CU(cudaGetLastError());
+
+    int32_t rc = plan_layout(ctx, s, k, ge, stream, known, scratch, &st->L);
+    if (rc) return rc;
+    const Layout &L = st->L;
+
+    ExtractParams p = base_params(s, k, ge, L, unit_bias);
+    p.w32 = rec;
+    p.nw32 = static_cast<int64_t>(s->n_words);
+    p.unit_bits = 32;
+    p.vstart = vstart;
+    p.err_flat = err_flat;
+    st->p = p;
+    if (L.total == 0) {
+        if (st->unambig && out && out->seq_out_offset)
+            CU(cudaMemsetAsync(out->seq_out_offset, 0, (s->n_seqs + 1) * sizeof(uint64_t), stream));
+        return KMC_OK;
+    }
+
+    if (!st->unambig) {
+        if (L.total > out->capacity) return fail(ctx, KMC_E_OUT_TOO_SMALL, "output capacity smaller than the number of k-mers");
+        rc = bind_outputs(ctx, out, mode, flags, &st->p);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(err_flat, 0xff, 8, stream));
+        ExtractLaunchFn fn = strict_launcher(ge, mode, hash, !L.uniform_len);
+        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+        CU(fn(st->p, ctx->sm_count, stream));
+        CU(cudaMemcpyAsync(&host_small[1], err_flat, 8, cudaMemcpyDeviceToHost, stream));
+        return KMC_OK;
+    }
+
+    // UnambiguousKmers: count pass -> per-tile offsets -> total
+    const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
+    uint64_t *tile_cnt = static_cast<uint64_t *>(scratch.take(8 * (tiles + 1)));
+    uint64_t *tile_off = static_cast<uint64_t *>(scratch.take(8 * (tiles + 2)));
+    uint64_t *tmp = static_cast<uint64_t *>(scratch.take(8 * scan_tmp_elems(tiles)));
+    if (!tile_cnt || !tile_off || !tmp) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+    st->tile_off = tile_off;
+    st->p.tile_count = tile_cnt;
+    st->p.tile_out_off = tile_off;
+    ExtractLaunchFn cf = compact_launcher(ge, false, !L.uniform_len, true);
+    if (!cf) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+    CU(cf(st->p, ctx->sm_count, stream));
+    CU(inclusive_offsets_u64(tile_cnt, tile_off, tiles, tmp, stream));
+    CU(cudaMemcpyAsync(&host_small[0], tile_off + tiles, 8, cudaMemcpyDeviceToHost, stream));
+    if (out && out->seq_out_offset) {
+        uint64_t *cnt = static_cast<uint64_t *>(scratch.take(8 * (s->n_seqs + 1)));
+        uint64_t *tmp2 = static_cast<uint64_t *>(scratch.take(8 * scan_tmp_elems(s->n_seqs)));
+        if (!cnt || !tmp2) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+        const uint64_t threads = s->n_seqs * 32;
+        seq_valid_counts_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(st->p, cnt);
+        CU(cudaGetLastError());
+        CU(inclusive_offsets_u64(cnt, out->seq_out_offset, s->n_seqs, tmp2, stream));
+    }
+    return KMC_OK;
+}
+
+int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, kmc_result *res)
+{
+    const Layout &L = st->L;
+    if (!st->unambig) {
+        if (st->host_small[1] != kNone) {
+            resolve_error_kernel<<<1, 1, 0, stream>>>(st->p, st->ge.g, st->words4, st->bad, st->host_small[1], st->err_out);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(&st->host_small[2], st->err_out, 24, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            res->n_written = 0;
+            res->err_seq = st->host_small[2];
+            res->err_pos = st->host_small[3];
+            res->err_sym = static_cast<uint32_t>(st->host_small[4]);
+            return fail(ctx, KMC_E_AMBIGUOUS, "cannot encode an uncertain symbol in a 2-bit alphabet");
+        }
+        res->n_written = L.total;
+        return KMC_OK;
+    }
+    const uint64_t total = L.total ? st->host_small[0] : 0;
+    res->n_written = total;
+    if (total == 0) return KMC_OK;
+    if (total > out->capacity) return fail(ctx, KMC_E_OUT_TOO_SMALL, "output capacity smaller than the number of k-mers");
+    int32_t rc = bind_outputs(ctx, out, KMC_UNAMBIG, st->flags, &st->p);
+    if (rc) return rc;
+    ExtractLaunchFn fn = compact_launcher(st->ge, (st->flags & KMC_HASH_FX) != 0, !L.uniform_len, false);
+    if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+    CU(fn(st->p, ctx->sm_count, stream));
+    return KMC_OK;
+}
+
+int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags,
+                            const kmc_out *out, kmc_result *res, cudaStream_t stream)
+{
+    int32_t rc = ensure_scratch(ctx, fourbit_scratch_bytes(s, k, mode));
+    if (rc) return rc;
+    rc = ensure_host_small(ctx);
+    if (rc) return rc;
+    Scratch scratch{static_cast<char *>(ctx->scratch), ctx->scratch_bytes, 0};
+    FourBitState st;
+    CU(cudaEventRecord(ctx->ev_k0, stream));
+    rc = fourbit_phase_a(ctx, s, k, mode, flags, out, stream, KnownTotals(), 0, scratch, ctx->host_small, &st);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    rc = fourbit_phase_b(ctx, &st, out, stream, res);
+    if (rc) return rc;
+    if (mode != KMC_UNAMBIG && out->seq_out_offset) {
+        if (st.L.uniform_len)
+            CU(fill_uniform_offsets(out->seq_out_offset, s->n_seqs + 1, st.L.wpr, stream));
+        else
+            CU(cudaMemcpyAsync(out->seq_out_offset, st.L.win_off, (s->n_seqs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+    }
+    CU(cudaEventRecord(ctx->ev_k1, stream));
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaEventElapsedTime(&res->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+    return KMC_OK;
+}
+
+int32_t count_unambiguous_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, uint64_t *n_out, cudaStream_t stream)
+{
+    int32_t rc = ensure_scratch(ctx, fourbit_scratch_bytes(s, k, KMC_UNAMBIG));
+    if (rc) return rc;
+    rc = ensure_host_small(ctx);
+    if (rc) return rc;
+    Scratch scratch{static_cast<char *>(ctx->scratch), ctx->scratch_bytes, 0};
+    FourBitState st;
+    rc = fourbit_phase_a(ctx, s, k, KMC_UNAMBIG, 0, nullptr, stream, KnownTotals(), 0, scratch, ctx->host_small, &st);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    *n_out = st.L.total ? ctx->host_small[0] : 0;
+    return KMC_OK;
 }
 
 } // namespace kmc

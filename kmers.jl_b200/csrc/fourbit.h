@@ -1,16 +1,52 @@
-// fourbit.h -- 4-bit (DNAAlphabet{4}) sources: FourToTwo recoding scheme (construction.jl:85-86).
+// fourbit.h -- 4-bit (DNAAlphabet{4} / RNAAlphabet{4}) sources: the FourToTwo recoding scheme
+// (src/construction.jl:85-86).
+//
+// A 4-bit source is first recoded on the device into (i) a 2-bit stream (trailing_zeros of each
+// one-hot nibble, construction_utils.jl:41-54) and (ii) a bit stream that flags every uncertain
+// symbol (count_ones != 1: IUPAC ambiguity codes, N and gap).  From (ii) a "valid start" bit
+// stream is derived: bit P = no uncertain symbol in [P, P+K).  The 2-bit extraction kernels then
+// run unchanged on (i) and consult the valid-start bits:
+//   strict FwKmers / FwRvIterator / CanonicalKmers (FwKmers.jl:104-115, CanonicalKmers.jl:131-144):
+//     the first window with an uncertain symbol is reported; the call fails with KMC_E_AMBIGUOUS
+//     and the position / encoding the reference's throw_uncertain (construction.jl:108-110) names;
+//   UnambiguousKmers (UnambiguousKmers.jl:134-148): windows with an uncertain symbol are skipped,
+//     the survivors are compacted in order with their 1-based start.
 #pragma once
-#include "kmc_internal.h"
+#include "plan.h"
 
 namespace kmc {
 
-// FwKmers / FwRvIterator / CanonicalKmers over a 4-bit source (strict: an uncertain symbol is an
-// EncodeError, FwKmers.jl:104-115, CanonicalKmers.jl:131-144) and UnambiguousKmers (skip/restart,
-// UnambiguousKmers.jl:134-148).  Device-resident descriptors.
+// What one 4-bit extraction needs between its two phases.  Phase A enqueues everything whose size
+// is known up front and leaves two words in `host_small` (pinned): [0] = number of k-mers
+// UnambiguousKmers will emit, [1] = first offending flat window of a strict mode (~0 = none).
+// Phase B runs after the caller has synchronised the stream.
+struct FourBitState {
+    const kmc_seqs *seqs = nullptr; // device descriptor (must outlive phase B)
+    const uint64_t *words4 = nullptr;
+    int k = 0, mode = 0;
+    uint32_t flags = 0;
+    Geometry ge{};
+    Layout L{};
+    ExtractParams p{};
+    uint32_t *bad = nullptr;
+    uint64_t *tile_off = nullptr;
+    uint64_t *err_out = nullptr; // device u64[3]: seq, 1-based pos, encoding
+    uint64_t *host_small = nullptr;
+    uint64_t unit_bias = 0;
+    bool unambig = false;
+};
+
+uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode);
+
+int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,
+                        cudaStream_t stream, const KnownTotals &known, uint64_t unit_bias, Scratch &scratch,
+                        uint64_t *host_small, FourBitState *st);
+// Fills res->n_written (and err_* with KMC_E_AMBIGUOUS).  Enqueues the compaction for UnambiguousKmers.
+int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, kmc_result *res);
+
+// kmc_extract on device buffers: phase A, sync, phase B, sync.
 int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags,
-                            const kmc_out *out, kmc_result *res, cudaStream_t stream, bool sync);
+                            const kmc_out *out, kmc_result *res, cudaStream_t stream);
 int32_t count_unambiguous_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, uint64_t *n_out, cudaStream_t stream);
-int32_t extract_host_4bit(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t mode, uint32_t flags,
-                          const kmc_out *ho, kmc_result *res);
 
 } // namespace kmc

@@ -12,6 +12,7 @@ struct kmc_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr; // the stream launches go to (own_stream or the caller's)
     cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr}; // kmc_extract_host pipeline slots
+    cudaEvent_t pipe_events[3] = {nullptr, nullptr, nullptr};   // phase-A completion per slot
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // kmc_timer_*
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;      // per-call kernel timing
     // grow-only scratch (scans, recoded 4-bit streams, compaction counters)
@@ -20,6 +21,9 @@ struct kmc_ctx {
     // host-pipeline device buffers, one per slot (grow-only)
     void *pipe_buf[3] = {nullptr, nullptr, nullptr};
     uint64_t pipe_bytes[3] = {0, 0, 0};
+    // small pinned host block for device->host read-backs of counts and error records:
+    // 16 u64 per pipeline slot, slot 3 = the context's own stream
+    uint64_t *host_small = nullptr;
     std::string last_error;
 };
 
@@ -27,6 +31,7 @@ namespace kmc {
 
 // scratch carving -------------------------------------------------------------------------
 int32_t ensure_scratch(kmc_ctx *ctx, uint64_t bytes);
+int32_t ensure_host_small(kmc_ctx *ctx);
 
 // scan.cu -----------------------------------------------------------------------------------
 // out[0] = 0, out[i+1] = sum_{j<=i} in[j]  (n+1 outputs), all on `stream`.
