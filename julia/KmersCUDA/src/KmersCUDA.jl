@@ -1,0 +1,253 @@
+"""
+    KmersCUDA
+
+Drop-in GPU (NVIDIA B200, sm_100a) replacement for the k-mer *extraction* path of Kmers.jl:
+`collect` of `FwKmers`, `FwRvIterator`, `CanonicalKmers` and `UnambiguousKmers` over
+`LongSequence{<:NucleicAcidAlphabet{2|4}}`, plus `fx_hash`.  Every number is computed by
+`libkmerscuda.so` (hand-written CUDA) through `ccall`; there is no CUDA.jl codegen and no CPU
+fallback.  Results are bit-identical to the reference's own iterators.
+
+NOTE: this module is written against include/kmerscuda.h but could not be executed in the build
+environment (no Julia toolchain there); the Python mirror `kmers.jl_b200/kmerscuda` binds the
+same symbols and is what the test-suite exercises.
+"""
+module KmersCUDA
+
+using BioSequences
+using Kmers
+using Kmers: FwKmers, FwRvIterator, CanonicalKmers, UnambiguousKmers, Kmer, derive_type
+using Libdl
+
+export fx_hash_device, extract, set_library!
+
+# ---------------------------------------------------------------------------------------------
+# library handle
+# ---------------------------------------------------------------------------------------------
+const LIB = Ref{String}(get(ENV, "KMERSCUDA_LIB", "libkmerscuda.so"))
+set_library!(path::AbstractString) = (LIB[] = String(path))
+
+const KMC_OK = Int32(0)
+const KMC_E_BAD_K = Int32(1)
+const KMC_E_AMBIGUOUS = Int32(3)
+const KMC_FW, KMC_FWRV, KMC_CANON, KMC_UNAMBIG = Int32(0), Int32(1), Int32(2), Int32(3)
+const KMC_HASH_FX, KMC_AOS = UInt32(1), UInt32(2)
+
+# struct kmc_seqs / kmc_out / kmc_result of include/kmerscuda.h (same field order and sizes)
+struct KmcSeqs
+    words::Ptr{UInt64}
+    n_words::UInt64
+    n_seqs::UInt64
+    seq_word_offset::Ptr{UInt64}
+    seq_len::Ptr{UInt64}
+    uniform_len::UInt64
+    uniform_stride_words::UInt64
+    src_bits::UInt32
+    first_symbol_offset::UInt32
+end
+
+struct KmcOut
+    a::Ptr{UInt64}
+    b::Ptr{UInt64}
+    hash::Ptr{UInt64}
+    index::Ptr{Int64}
+    seq_out_offset::Ptr{UInt64}
+    capacity::UInt64
+    index_base::Int64
+end
+
+mutable struct KmcResult
+    n_written::UInt64
+    err_seq::UInt64
+    err_pos::UInt64
+    err_sym::UInt32
+    kernel_ms::Float32
+    KmcResult() = new(0, 0, 0, 0, 0.0f0)
+end
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        st = ccall((:kmc_ctx_create, LIB[]), Int32, (Int32, Ptr{Ptr{Cvoid}}), device, h)
+        st == KMC_OK || error("KmersCUDA: kmc_ctx_create failed ($(status_string(st))); a CUDA device is required, there is no CPU fallback")
+        ctx = new(h[])
+        finalizer(c -> ccall((:kmc_ctx_destroy, LIB[]), Int32, (Ptr{Cvoid},), c.handle), ctx)
+        return ctx
+    end
+end
+
+status_string(st::Int32) = unsafe_string(ccall((:kmc_status_string, LIB[]), Cstring, (Int32,), st))
+last_error(ctx::Context) = unsafe_string(ccall((:kmc_last_error, LIB[]), Cstring, (Ptr{Cvoid},), ctx.handle))
+
+const DEFAULT_CTX = Ref{Union{Nothing, Context}}(nothing)
+default_context() = something(DEFAULT_CTX[], (DEFAULT_CTX[] = Context(0)))
+
+# ---------------------------------------------------------------------------------------------
+# type parameters -> runtime integers
+# ---------------------------------------------------------------------------------------------
+src_bits(::Type{<:LongSequence{<:NucleicAcidAlphabet{2}}}) = UInt32(2)
+src_bits(::Type{<:LongSequence{<:NucleicAcidAlphabet{4}}}) = UInt32(4)
+
+mode_of(::FwKmers) = KMC_FW
+mode_of(::FwRvIterator) = KMC_FWRV
+mode_of(::CanonicalKmers) = KMC_CANON
+mode_of(::UnambiguousKmers) = KMC_UNAMBIG
+
+source(it::Union{FwKmers, FwRvIterator}) = it.seq
+source(it::CanonicalKmers) = it.it.seq
+source(it::UnambiguousKmers) = it.it.seq
+
+# FwRvIterator and UnambiguousKmers are not AbstractKmerIterators in the reference
+# (CanonicalKmers.jl:25, UnambiguousKmers.jl:29), so the parameters are read per type.
+const AnyIter{A, K} = Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, K}, UnambiguousKmers{A, K}}
+ksize_of(::AnyIter{A, K}) where {A, K} = K
+ksize_of(::Type{<:AnyIter{A, K}}) where {A, K} = K
+alphabet_of(::Type{<:AnyIter{A, K}}) where {A, K} = A
+mode_of(::Type{<:FwKmers}) = KMC_FW
+mode_of(::Type{<:FwRvIterator}) = KMC_FWRV
+mode_of(::Type{<:CanonicalKmers}) = KMC_CANON
+mode_of(::Type{<:UnambiguousKmers}) = KMC_UNAMBIG
+
+function throw_status(ctx::Context, st::Int32, res::KmcResult, ::Type{A}) where {A}
+    if st == KMC_E_AMBIGUOUS
+        # what src/construction.jl:108-110 throws: EncodeError(Alphabet, symbol)
+        throw(BioSequences.EncodeError(A(), reinterpret(DNA, UInt8(res.err_sym))))
+    elseif st == KMC_E_BAD_K
+        error("K must be at least 1")            # src/iterators/FwKmers.jl:32-33
+    else
+        error("libkmerscuda status $st: $(last_error(ctx))")
+    end
+end
+
+# ---------------------------------------------------------------------------------------------
+# collect(it): one kmc_extract_host call straight into the memory of the result Vector
+# ---------------------------------------------------------------------------------------------
+"""
+    KmersCUDA.collect(it) -> Vector{eltype}
+
+Same result as `Base.collect(it)` for `FwKmers`, `FwRvIterator`, `CanonicalKmers` and
+`UnambiguousKmers` whose source is a `LongSequence` over a 2- or 4-bit nucleotide alphabet and
+whose k-mer alphabet is 2-bit.  `Kmer{A,K,N}` and tuples of `Kmer`/`Int` are isbits, so the
+device writes the Julia element layout directly into the vector (KMC_AOS).
+"""
+function collect(it::Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, K}, UnambiguousKmers{A, K}};
+        ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
+    seq = source(it)
+    seq isa LongSequence || throw(ArgumentError("KmersCUDA accelerates LongSequence sources"))
+    T = derive_type(Kmer{A, K})
+    mode = mode_of(it)
+    len = length(seq)
+    nwin = max(0, len - K + 1)
+    words = seq.data
+    bits = src_bits(typeof(seq))
+    ET = mode == KMC_FWRV ? Tuple{T, T} : mode == KMC_UNAMBIG ? Tuple{T, Int} : T
+    cap = nwin
+    if mode == KMC_UNAMBIG && bits == UInt32(4)
+        cap = count(it; ctx)   # Base.IteratorSize is SizeUnknown (UnambiguousKmers.jl:33-37)
+    end
+    out = Vector{ET}(undef, cap)
+    res = KmcResult()
+    GC.@preserve words out begin
+        s = Ref(KmcSeqs(pointer(words), length(words), 1, C_NULL, C_NULL, len, length(words), bits, 0))
+        o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, C_NULL, C_NULL, C_NULL, cap, 0))
+        st = ccall((:kmc_extract_host, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
+            ctx.handle, s, K, mode, KMC_AOS, o, pointer_from_objref(res))
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    resize!(out, res.n_written)
+    return out
+end
+
+"Number of elements `collect(it)` returns (runs the device count pass for 4-bit UnambiguousKmers)."
+function count(it; ctx::Context = default_context())
+    seq = source(it)
+    words = seq.data
+    n = Ref{UInt64}(0)
+    GC.@preserve words begin
+        d_words = device_upload(ctx, words)
+        s = Ref(KmcSeqs(d_words, length(words), 1, C_NULL, C_NULL, length(seq), length(words), src_bits(typeof(seq)), 0))
+        st = ccall((:kmc_count, LIB[]), Int32, (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Ptr{UInt64}),
+            ctx.handle, s, ksize_of(it), mode_of(it), n)
+        device_free(ctx, d_words)
+        st == KMC_OK || error("libkmerscuda status $st: $(last_error(ctx))")
+    end
+    return Int(n[])
+end
+
+function device_upload(ctx::Context, v::Vector{UInt64})
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(v), p)
+    ccall((:kmc_upload, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, p[], v, sizeof(v))
+    ccall((:kmc_sync, LIB[]), Int32, (Ptr{Cvoid},), ctx.handle)
+    return Ptr{UInt64}(p[])
+end
+device_free(ctx::Context, p) = ccall((:kmc_free, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, p)
+
+# ---------------------------------------------------------------------------------------------
+# batched extraction over a read set: what `[collect(Iter(r)) for r in reads]` concatenates to
+# ---------------------------------------------------------------------------------------------
+"""
+    extract(Iter, reads::Vector{<:LongSequence}; hash=false) -> (kmers, hashes, offsets)
+
+`Iter` is e.g. `CanonicalDNAMers{31}`.  Packs the reads into one word-aligned CSR buffer
+(multithreaded gather on the host) and makes ONE library call.  `offsets[i]+1 : offsets[i+1]`
+are the elements of read `i`.
+"""
+function extract(::Type{I}, reads::Vector{S}; hash::Bool = false,
+        ctx::Context = default_context()) where {I <: AnyIter, S <: LongSequence}
+    A, K, mode = alphabet_of(I), ksize_of(I), mode_of(I)
+    T = derive_type(Kmer{A, K})
+    n = length(reads)
+    lens = UInt64[length(r) for r in reads]
+    nw = UInt64[length(r.data) for r in reads]
+    woff = cumsum(vcat(UInt64(0), nw))
+    words = Vector{UInt64}(undef, woff[end] + 1)
+    Threads.@threads for i in 1:n
+        copyto!(words, woff[i] + 1, reads[i].data, 1, nw[i])
+    end
+    cap = sum(l -> l >= K ? Int(l) - K + 1 : 0, lens; init = 0)
+    ET = mode == KMC_FWRV ? Tuple{T, T} : mode == KMC_UNAMBIG ? Tuple{T, Int} : T
+    out = Vector{ET}(undef, cap)
+    hashes = hash ? Vector{UInt64}(undef, cap) : UInt64[]
+    offsets = Vector{UInt64}(undef, n + 1)
+    res = KmcResult()
+    GC.@preserve words lens woff out hashes offsets begin
+        s = Ref(KmcSeqs(pointer(words), length(words), n, pointer(woff), pointer(lens), 0, 0, src_bits(S), 0))
+        o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, hash ? pointer(hashes) : C_NULL, C_NULL,
+            pointer(offsets), cap, 0))
+        st = ccall((:kmc_extract_host, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
+            ctx.handle, s, K, mode, KMC_AOS | (hash ? KMC_HASH_FX : UInt32(0)), o, pointer_from_objref(res))
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    resize!(out, res.n_written)
+    hash && resize!(hashes, res.n_written)
+    return out, hashes, offsets
+end
+
+# ---------------------------------------------------------------------------------------------
+# fx_hash.(v) on the device (src/kmer.jl:255-261)
+# ---------------------------------------------------------------------------------------------
+function fx_hash_device(v::Vector{Kmer{A, K, N}}, h::UInt64 = UInt64(0); ctx::Context = default_context()) where {A, K, N}
+    out = Vector{UInt64}(undef, length(v))
+    isempty(v) && return out
+    GC.@preserve v out begin
+        dk, dout = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(v), dk)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(out), dout)
+        ccall((:kmc_upload, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, dk[], v, sizeof(v))
+        st = ccall((:kmc_fx_hash, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Int32, UInt64, Ptr{Cvoid}),
+            ctx.handle, dk[], length(v), N, h, dout[])
+        ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, out, dout[], sizeof(out))
+        ccall((:kmc_free, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, dk[])
+        ccall((:kmc_free, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, dout[])
+        st == KMC_OK || error("libkmerscuda status $st: $(last_error(ctx))")
+    end
+    return out
+end
+
+# Base.hash(kmer, h) = hash(kmer.data, h ⊻ K) (src/kmer.jl:206) depends on the Julia version's tuple
+# hash and is deliberately NOT reimplemented on the device: call Base.hash on the returned k-mers.
+
+end # module

@@ -1,0 +1,231 @@
+#!/usr/bin/env python
+"""Device-resident timings of the BASELINE.json configs other than the headline one (C2 is
+bench.py): C3 UnambiguousDNAMers{31} over 4-bit reads / one long sequence with 1 % N,
+C4 CanonicalDNAMers{63} over 1 Gbp, C5 canonical 31-mer bucket-count table (per-GPU part), plus
+the other iterator modes on the C2 shape.  One JSON line per case: k-mers/s, algorithmic GB/s
+ and the fraction of the measured HBM peak.  Inputs are generated on the device with
+torch (plumbing); every timed call goes through the C ABI.
+
+  python tools/bench_configs.py [--cases c3,c4,c5,modes] [--steps 10] [--scale 1.0]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "kmers.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import kmerscuda as kc  # noqa: E402
+from kmerscuda import _abi  # noqa: E402
+
+FW, FWRV, CANON, UNAMBIG = 0, 1, 2, 3
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+WARMUP = 3
+
+
+def timed(ctx, fn, steps, warmup=None):
+    for _ in range(WARMUP if warmup is None else warmup):
+        fn()
+    ctx.sync()
+    ms = []
+    for _ in range(steps):
+        ctx.timer_begin()
+        fn()
+        ms.append(ctx.timer_end())
+    return float(np.median(ms)), float(np.min(ms))
+
+
+def rand_words_2bit(n_words, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(-2**63, 2**63 - 1, (n_words,), dtype=torch.int64, device="cuda", generator=g)
+
+
+def rand_words_4bit(n_rows, syms_per_row, valid_len, seed, p_n=0.01, chunk_rows=1_000_000):
+    """n_rows x (syms_per_row/16) words; symbols beyond valid_len are gap (0)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    wpr = syms_per_row // 16
+    out = torch.empty(n_rows * wpr, dtype=torch.int64, device="cuda")
+    shifts = torch.arange(16, device="cuda", dtype=torch.int64) * 4
+    for r0 in range(0, n_rows, chunk_rows):
+        r1 = min(n_rows, r0 + chunk_rows)
+        base = torch.randint(0, 4, (r1 - r0, syms_per_row), dtype=torch.int64, device="cuda", generator=g)
+        nib = torch.ones_like(base) << base
+        nib[torch.rand(nib.shape, device="cuda", generator=g) < p_n] = 15
+        nib[:, valid_len:] = 0
+        out[r0 * wpr:r1 * wpr] = (nib.view(r1 - r0, wpr, 16) << shifts).sum(dim=2).reshape(-1)
+    return out
+
+
+def emit(name, n_kmers, bytes_total, ms_med, ms_min, extra=None):
+    pk = peak()
+    gbs = bytes_total / (ms_med / 1e3) / 1e9
+    line = {"case": name, "kmers": n_kmers, "kmers_per_s": n_kmers / (ms_med / 1e3), "ms_median": ms_med, "ms_min": ms_min,
+            "algorithmic_bytes": bytes_total, "achieved_GBps": gbs, "peak_GBps": pk, "frac_of_measured_peak": gbs / pk}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def run_extract(ctx, desc, k, mode, flags, out, res):
+    st = ctx.lib.kmc_extract(ctx.handle, C.byref(desc), k, mode, flags, C.byref(out), C.byref(res))
+    if st != 0:
+        raise RuntimeError(ctx.lib.kmc_last_error(ctx.handle).decode())
+
+
+def case_c3_reads(ctx, steps, scale):
+    n_reads, length, stride, k = int(10_000_000 * scale), 150, 10, 31
+    wpr = length - k + 1
+    words = rand_words_4bit(n_reads, stride * 16, length, 439824)
+    cap = n_reads * wpr
+    km = torch.empty(cap, dtype=torch.int64, device="cuda")
+    idx = torch.empty(cap, dtype=torch.int64, device="cuda")
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), n_reads, None, None, length, stride, 4, 0)
+    out = _abi.kmc_out(km.data_ptr(), None, None, idx.data_ptr(), None, cap, 0)
+    res = _abi.kmc_result()
+    torch.cuda.synchronize()
+    med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, UNAMBIG, 0, out, res), steps)
+    n = int(res.n_written)
+    emit("C3i UnambiguousDNAMers{31}, 4-bit, 1%% N, %d x 150 bp reads (SoA kmer+index)" % n_reads, n,
+         0.5 * n_reads * length + 16 * n, med, mn, {"windows": cap, "survivors_frac": n / cap})
+    km2 = torch.empty(2 * cap, dtype=torch.int64, device="cuda")
+    out = _abi.kmc_out(km2.data_ptr(), None, None, None, None, cap, 0)
+    med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, UNAMBIG, _abi.KMC_AOS, out, res), steps)
+    emit("C3i same, AoS Vector{Tuple{Kmer,Int}}", n, 0.5 * n_reads * length + 16 * n, med, mn)
+
+
+def case_c3_long(ctx, steps, scale):
+    length, k = int(1_000_000_000 * scale), 31
+    nw = (length + 15) // 16
+    rows = 1024
+    per = (nw + rows - 1) // rows
+    words = rand_words_4bit(rows, per * 16, per * 16, 7, chunk_rows=32)[:nw].contiguous()
+    cap = length - k + 1
+    km = torch.empty(cap, dtype=torch.int64, device="cuda")
+    idx = torch.empty(cap, dtype=torch.int64, device="cuda")
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), 1, None, None, length, words.numel(), 4, 0)
+    out = _abi.kmc_out(km.data_ptr(), None, None, idx.data_ptr(), None, cap, 0)
+    res = _abi.kmc_result()
+    torch.cuda.synchronize()
+    med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, UNAMBIG, 0, out, res), steps)
+    n = int(res.n_written)
+    emit("C3ii UnambiguousDNAMers{31}, 4-bit, 1%% N, one %d bp sequence" % length, n, 0.5 * length + 16 * n, med, mn,
+         {"windows": cap, "survivors_frac": n / cap})
+
+
+def case_c4(ctx, steps, scale):
+    length, k = int(1_000_000_000 * scale), 63
+    words = rand_words_2bit((length + 31) // 32, 11)
+    cap = length - k + 1
+    km = torch.empty(2 * cap, dtype=torch.int64, device="cuda")
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), 1, None, None, length, words.numel(), 2, 0)
+    out = _abi.kmc_out(km.data_ptr(), None, None, None, None, cap, 0)
+    res = _abi.kmc_result()
+    torch.cuda.synchronize()
+    med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, CANON, _abi.KMC_NO_SYNC, out, res), steps)
+    emit("C4 CanonicalDNAMers{63} (2 limbs), one %d bp 2-bit sequence" % length, cap, (0.25 + 16) * cap, med, mn)
+    hs = torch.empty(cap, dtype=torch.int64, device="cuda")
+    out = _abi.kmc_out(km.data_ptr(), None, hs.data_ptr(), None, None, cap, 0)
+    med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, CANON, _abi.KMC_NO_SYNC | _abi.KMC_HASH_FX, out, res), steps)
+    emit("C4 same + fx_hash", cap, (0.25 + 24) * cap, med, mn)
+
+
+def case_c5(ctx, steps, scale):
+    n_reads, length, stride, k = int(25_000_000 * scale), 150, 5, 31
+    wpr = length - k + 1
+    words = rand_words_2bit(n_reads * stride, 13)
+    words.view(n_reads, stride)[:, stride - 1] &= (1 << (2 * (length - 32 * (stride - 1)))) - 1
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), n_reads, None, None, length, stride, 2, 0)
+    res = _abi.kmc_result()
+    for bits in (20, 24, 28):
+        table = torch.zeros(1 << bits, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+
+        def step():
+            st = ctx.lib.kmc_bucket_count(ctx.handle, C.byref(desc), k, bits, table.data_ptr(), C.byref(res))
+            if st != 0:
+                raise RuntimeError(ctx.lib.kmc_last_error(ctx.handle).decode())
+        med, mn = timed(ctx, step, steps)
+        n = n_reads * wpr
+        emit("C5 (per-GPU part) canonical 31-mer bucket table, B=%d, %d x 150 bp reads" % (bits, n_reads), n,
+             (0.3125 + 8) * n, med, mn, {"table_bytes": 4 << bits})
+        del table
+
+
+def case_modes(ctx, steps, scale):
+    n_reads, length, stride, k = int(10_000_000 * scale), 150, 5, 31
+    wpr = length - k + 1
+    n = n_reads * wpr
+    words = rand_words_2bit(n_reads * stride, 439824)
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), n_reads, None, None, length, stride, 2, 0)
+    a = torch.empty(2 * n, dtype=torch.int64, device="cuda")
+    b = torch.empty(n, dtype=torch.int64, device="cuda")
+    res = _abi.kmc_result()
+    inb = 0.25 * length / wpr
+    cases = [("FwDNAMers{31}", FW, 0, _abi.kmc_out(a.data_ptr(), None, None, None, None, n, 0), inb + 8),
+             ("FwRvIterator{31} SoA", FWRV, 0, _abi.kmc_out(a.data_ptr(), b.data_ptr(), None, None, None, n, 0), inb + 16),
+             ("FwRvIterator{31} AoS Tuple{Kmer,Kmer}", FWRV, _abi.KMC_AOS, _abi.kmc_out(a.data_ptr(), None, None, None, None, n, 0), inb + 16),
+             ("CanonicalDNAMers{31} (no hash)", CANON, 0, _abi.kmc_out(a.data_ptr(), None, None, None, None, n, 0), inb + 8),
+             ("UnambiguousDNAMers{31} over 2-bit (kmer + index)", UNAMBIG, 0, _abi.kmc_out(a.data_ptr(), None, None, b.data_ptr(), None, n, 0), inb + 16)]
+    for name, mode, fl, out, bpk in cases:
+        med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, mode, fl | _abi.KMC_NO_SYNC, out, res), steps)
+        emit("C2-shape %s, %d x 150 bp" % (name, n_reads), n, bpk * n, med, mn)
+
+
+def case_ragged(ctx, steps, scale):
+    """C2 workload through the ragged (CSR) descriptors: (a) all reads 150 bp, (b) lengths uniform in [100, 250]."""
+    n_reads, k = int(10_000_000 * scale), 31
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for name, lens in (("all 150 bp", torch.full((n_reads,), 150, dtype=torch.int64, device="cuda")),
+                       ("lengths U[100,250]", torch.randint(100, 251, (n_reads,), dtype=torch.int64, device="cuda", generator=g))):
+        nw = (lens + 31) // 32
+        off = torch.zeros(n_reads + 1, dtype=torch.int64, device="cuda")
+        off[1:] = torch.cumsum(nw, 0)
+        words = rand_words_2bit(int(off[-1]) + 1, 439824)
+        n = int((lens - k + 1).clamp(min=0).sum())
+        a = torch.empty(n, dtype=torch.int64, device="cuda")
+        h = torch.empty(n, dtype=torch.int64, device="cuda")
+        desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), n_reads, off.data_ptr(), lens.data_ptr(), 0, 0, 2, 0)
+        out = _abi.kmc_out(a.data_ptr(), None, h.data_ptr(), None, None, n, 0)
+        res = _abi.kmc_result()
+        torch.cuda.synchronize()
+        med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, CANON, _abi.KMC_HASH_FX, out, res), steps)
+        sym = int(lens.sum())
+        emit("ragged CSR CanonicalDNAMers{31}+fx_hash, %d reads, %s (incl. layout scans)" % (n_reads, name), n,
+             0.25 * sym + 16 * n, med, mn)
+        del words, a, h
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="c3,c3long,c4,c5,modes")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    global WARMUP
+    WARMUP = args.warmup
+    torch.cuda.set_device(0)
+    ctx = kc.Context(0)
+    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged}
+    for c in args.cases.split(","):
+        table[c](ctx, args.steps, args.scale)
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
