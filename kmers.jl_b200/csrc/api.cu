@@ -75,7 +75,8 @@ uint64_t layout_scratch_bytes(const kmc_seqs *s)
 {
     if (s->seq_len == nullptr) return 0;
     const uint64_t n = s->n_seqs;
-    return 4 * round_up((n + 1) * 8, 256) + round_up(scan_tmp_elems(n) * 8, 256);
+    return 4 * round_up((n + 1) * 8, 256) + round_up(scan_tmp_elems(n) * 8, 256) +
+           round_up((tiles_upper_bound(s) + 1) * 8, 256);
 }
 
 int32_t plan_layout(kmc_ctx *ctx, const kmc_seqs *s, int k, const Geometry &ge, cudaStream_t stream,
@@ -119,6 +120,13 @@ int32_t plan_layout(kmc_ctx *ctx, const kmc_seqs *s, int k, const Geometry &ge, 
         L->total = h[0];
         L->items = h[1];
     }
+    const uint64_t tiles = (L->items + kTileItems - 1) / kTileItems;
+    if (tiles) {
+        uint64_t *tile_first = static_cast<uint64_t *>(scratch.take((tiles + 1) * 8));
+        if (!tile_first) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+        CU(tile_first_reads(item_off, n, kTileItems, tiles, tile_first, stream));
+        L->tile_first = tile_first;
+    }
     return KMC_OK;
 }
 
@@ -142,6 +150,7 @@ ExtractParams base_params(const kmc_seqs *s, int k, const Geometry &ge, const La
     p.seq_unit_off = s->seq_word_offset;
     p.win_off = L.win_off;
     p.item_off = L.item_off;
+    p.tile_first = L.tile_first;
     return p;
 }
 

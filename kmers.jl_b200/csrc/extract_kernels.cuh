@@ -8,8 +8,11 @@
 // therefore only ever touches ONE read (no divergent slow path at read boundaries); groups
 // that straddle two reads are emitted as two partial items by two threads.
 //   uniform sets  : item -> (r, gi) by one division per thread at kernel start, then an
-//                   incremental update per grid-stride step (no division in the loop)
-//   ragged sets   : item -> r by binary search in the exclusive scan of group slots
+//                   incremental update per step (no division in the loop)
+//   ragged sets   : item -> r through a two-level narrowing of the exclusive scan of group slots:
+//                   a per-tile first read (tile_first, one binary search per TILE in a tiny
+//                   pre-kernel), a per-warp-bucket first read (65 short searches per block, kept
+//                   in shared memory), and a 0-2 step search per item inside its bucket's range
 #pragma once
 #include "kmer_core.cuh"
 
@@ -33,7 +36,8 @@ struct ExtractParams {
     uint32_t s0;         // 32*NX - 2K - 2(G-1)
     uint64_t head_mask;
     uint64_t n_seqs;
-    uint64_t items;      // total work items (group slots)
+    uint64_t items;      // total work items (group slots); the grid covers at least this many
+    const uint64_t *items_dev; // if not NULL the exact total lives on the device (grid is an upper bound)
     // uniform locator
     uint64_t stride_units;
     uint64_t wpr;        // windows per read
@@ -43,6 +47,8 @@ struct ExtractParams {
     const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
     const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
     const uint64_t *item_off;     // [n_seqs+1] exclusive scan of group slots
+    const uint64_t *tile_first;   // [tiles+1] read that owns the first item of each tile
+    const uint64_t *seq_index_base; // [n_seqs] or NULL: added to the emitted index (runs of a larger read)
     // outputs
     uint64_t *out_a;
     uint64_t *out_b;
@@ -76,50 +82,73 @@ KMC_DEV uint32_t valid_slots(const uint32_t *__restrict__ vstart, int64_t sym0, 
 // G windows per thread for N limbs: G*N*8 must be a multiple of 32 bytes.
 template <int N> struct GroupOf { static constexpr int G = (N == 1) ? 4 : (N == 2) ? 2 : (N == 3) ? 4 : 1; };
 
-template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false>
-__global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractParams p)
-{
-    constexpr int G = GroupOf<N>::G;
-    constexpr bool WANT_FW = true;
-    constexpr bool WANT_RV = (MODE != MODE_FW);
+// ---------------------------------------------------------------------------------------------
+// TileCursor: maps the work items of one tile (kTileItems consecutive group slots) to
+// (read, slot) and derives everything the kernels need about the item's windows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileBuckets = kTileItems / 32; // one bucket = the 32 items a warp handles in one step
 
-    // One tile of kTileIters x 256 consecutive work items per block; blocks are scheduled by the
-    // hardware as SMs drain, which balances the SMs (a static persistent partition left the
-    // fastest SMs idle for 25 % of the kernel: profiles/r01_notes.md).
-    const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
-    uint64_t r = 0, gi = 0;
-    if (!RAGGED) {
-        // (r, gi) = divmod(item, gprm): one 64-bit division per BLOCK, then a 32-bit one per thread
-        __shared__ uint64_t s_r0, s_gi0;
-        if (threadIdx.x == 0) {
-            s_r0 = tile_base / p.gprm;
-            s_gi0 = tile_base - s_r0 * p.gprm;
-        }
-        __syncthreads();
-        r = s_r0;
-        gi = s_gi0 + threadIdx.x;
-        if (p.gprm > 0xffffffffull - kTileItems) { // gi0 + tid wraps at most once
-            if (gi >= p.gprm) {
-                gi -= p.gprm;
-                ++r;
+struct TileShared {
+    uint64_t r0, gi0;                // uniform: (read, slot) of the tile's first item
+    uint32_t fr[kTileBuckets + 1];   // ragged: read (relative to r_first) owning the first item of each bucket
+};
+
+template <bool RAGGED, int G>
+struct TileCursor {
+    uint64_t r, gi;       // current item
+    uint64_t r_first;     // ragged: read owning the tile's first item
+    // derived for the current item
+    uint64_t f0, wcount;  // flat index of the read's first window, its window count
+    uint64_t unit_off;    // where the read starts in the stream (units of p.unit_bits)
+    uint64_t q;           // aligned flat group of this item
+    int64_t wbase;        // window (within the read) of slot 0, in (-G, wcount)
+    int jlo, jhi;         // slots [jlo, jhi) are windows of this read
+
+    KMC_DEV void init(const ExtractParams &p, uint64_t tile_base, TileShared &sh)
+    {
+        if (!RAGGED) {
+            // (r, gi) = divmod(item, gprm): one 64-bit division per BLOCK, then a 32-bit one per thread
+            if (threadIdx.x == 0) {
+                sh.r0 = tile_base / p.gprm;
+                sh.gi0 = tile_base - sh.r0 * p.gprm;
+            }
+            __syncthreads();
+            r = sh.r0;
+            gi = sh.gi0 + threadIdx.x;
+            if (p.gprm > 0xffffffffull - kTileItems) { // gi0 + tid wraps at most once
+                if (gi >= p.gprm) {
+                    gi -= p.gprm;
+                    ++r;
+                }
+            } else {
+                const uint32_t d = static_cast<uint32_t>(gi) / static_cast<uint32_t>(p.gprm);
+                gi -= static_cast<uint64_t>(d) * p.gprm;
+                r += d;
             }
         } else {
-            const uint32_t q = static_cast<uint32_t>(gi) / static_cast<uint32_t>(p.gprm);
-            gi -= static_cast<uint64_t>(q) * p.gprm;
-            r += q;
+            r_first = __ldg(p.tile_first + blockIdx.x);
+            if (threadIdx.x <= kTileBuckets) {
+                const uint64_t item = tile_base + 32ull * threadIdx.x;
+                uint64_t lo = r_first, hi = __ldg(p.tile_first + blockIdx.x + 1) + 1;
+                while (hi - lo > 1) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (__ldg(p.item_off + mid) <= item) lo = mid; else hi = mid;
+                }
+                sh.fr[threadIdx.x] = static_cast<uint32_t>(lo - r_first);
+            }
+            __syncthreads();
+            r = gi = 0;
         }
     }
 
-#pragma unroll 1
-    for (int it = 0; it < kTileIters; ++it) {
-        const uint64_t item = tile_base + static_cast<uint64_t>(it) * kBlockThreads + threadIdx.x;
-        if (item >= p.items) break;
-        uint64_t f0, wcount, unit_off;
+    // item = tile_base + it * kBlockThreads + threadIdx.x
+    KMC_DEV void locate(const ExtractParams &p, uint64_t item, int it, const TileShared &sh)
+    {
         if (RAGGED) {
-            // largest r with item_off[r] <= item
-            uint64_t lo = 0, hi = p.n_seqs;
-            while (hi - lo > 1) {
-                uint64_t mid = (lo + hi) >> 1;
+            const int b = (it * kBlockThreads + static_cast<int>(threadIdx.x)) >> 5;
+            uint64_t lo = r_first + sh.fr[b], hi = r_first + sh.fr[b + 1] + 1;
+            while (hi - lo > 1) { // largest r in [lo, hi) with item_off[r] <= item
+                const uint64_t mid = (lo + hi) >> 1;
                 if (__ldg(p.item_off + mid) <= item) lo = mid; else hi = mid;
             }
             r = lo;
@@ -131,15 +160,62 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             wcount = p.wpr;
         }
         unit_off = p.seq_unit_off ? __ldg(p.seq_unit_off + r) - p.unit_bias : r * p.stride_units;
-        const uint64_t q = f0 / G + gi;                                   // aligned flat group
-        const int64_t wbase = static_cast<int64_t>(q * G - f0);           // window of slot 0, in (-G, wcount)
-        const int64_t rem = static_cast<int64_t>(wcount) - wbase;         // windows available from slot 0
-        const int jlo = wbase < 0 ? static_cast<int>(-wbase) : 0;
-        const int jhi = rem < G ? static_cast<int>(rem) : G;
+        q = f0 / G + gi;
+        wbase = static_cast<int64_t>(q * G - f0);
+        const int64_t rem = static_cast<int64_t>(wcount) - wbase; // windows available from slot 0
+        jlo = wbase < 0 ? static_cast<int>(-wbase) : 0;
+        jhi = rem < G ? static_cast<int>(rem) : G;
+    }
+
+    // bit offset in the stream of slot 0's first symbol
+    KMC_DEV int64_t bit(const ExtractParams &p) const
+    {
+        return static_cast<int64_t>(unit_off) * p.unit_bits + 2 * (static_cast<int64_t>(p.first) + wbase);
+    }
+
+    KMC_DEV void advance(const ExtractParams &p)
+    {
+        if (!RAGGED) {
+            r += p.it_dq;
+            gi += p.it_dr;
+            if (gi >= p.gprm) {
+                gi -= p.gprm;
+                ++r;
+            }
+        }
+    }
+};
+
+
+
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false>
+__global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractParams p)
+{
+    constexpr int G = GroupOf<N>::G;
+    constexpr bool WANT_FW = true;
+    constexpr bool WANT_RV = (MODE != MODE_FW);
+
+    // One tile of kTileIters x 256 consecutive work items per block; blocks are scheduled by the
+    // hardware as SMs drain, which balances the SMs (a static persistent partition left the
+    // fastest SMs idle for 25 % of the kernel: profiles/r01_c2_canon31_hash_v1_persistent.txt).
+    __shared__ TileShared sh;
+    const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
+    const uint64_t n_items = p.items_dev ? __ldg(p.items_dev) : p.items;
+    if (tile_base >= n_items) return; // block-uniform
+    TileCursor<RAGGED, G> cur;
+    cur.init(p, tile_base, sh);
+
+#pragma unroll 1
+    for (int it = 0; it < kTileIters; ++it) {
+        const uint64_t item = tile_base + static_cast<uint64_t>(it) * kBlockThreads + threadIdx.x;
+        if (item >= n_items) break;
+        cur.locate(p, item, it, sh);
+        const uint64_t q = cur.q;
+        const int64_t wbase = cur.wbase;
+        const int jlo = cur.jlo, jhi = cur.jhi;
 
         if (jhi > jlo) {
-            const int64_t bit = static_cast<int64_t>(unit_off) * p.unit_bits +
-                                2 * (static_cast<int64_t>(p.first) + wbase);
+            const int64_t bit = cur.bit(p);
             if (STRICT4) {
                 // FourToTwo, strict (FwKmers.jl:104-115, CanonicalKmers.jl:131-144): an uncertain symbol
                 // is an error.  Record the first offending window; the host resolves it to the symbol
@@ -173,6 +249,10 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             }
 
             const uint64_t fbase = q * G; // flat index of slot 0
+            int64_t ibase = 0;            // 1-based start (within its sequence) of slot 0's window
+            if (p.out_index)
+                ibase = wbase + 1 + p.index_base +
+                        (p.seq_index_base ? static_cast<int64_t>(__ldg(p.seq_index_base + cur.r)) : 0);
             const bool full = (jlo == 0) && (jhi == G);
             const bool tuple_rv = (MODE == MODE_FWRV) && p.aos;
             const bool tuple_ix = (p.out_index != nullptr) && p.aos;
@@ -195,7 +275,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
                         uint64_t *e = p.out_a + (fbase + j) * (N + 1);
 #pragma unroll
                         for (int i = 0; i < N; ++i) st_u64(e + i, a[j][i]);
-                        st_u64(e + N, static_cast<uint64_t>(wbase + j + 1 + p.index_base));
+                        st_u64(e + N, static_cast<uint64_t>(ibase + j));
                     }
                 } else {
                     uint64_t buf[G * N];
@@ -214,7 +294,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
                     if (p.out_index) {
                         uint64_t ib[G];
 #pragma unroll
-                        for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(wbase + j + 1 + p.index_base);
+                        for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(ibase + j);
                         store_run<G>(reinterpret_cast<uint64_t *>(p.out_index) + fbase, ib, G % 4 == 0);
                     }
                 }
@@ -234,7 +314,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
                     } else if (tuple_ix) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) st_u64(p.out_a + f * (N + 1) + i, a[j][i]);
-                        st_u64(p.out_a + f * (N + 1) + N, static_cast<uint64_t>(wbase + j + 1 + p.index_base));
+                        st_u64(p.out_a + f * (N + 1) + N, static_cast<uint64_t>(ibase + j));
                     } else {
 #pragma unroll
                         for (int i = 0; i < N; ++i) st_u64(p.out_a + f * N + i, a[j][i]);
@@ -244,7 +324,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
                         }
                         if (p.out_index)
                             st_u64(reinterpret_cast<uint64_t *>(p.out_index) + f,
-                                   static_cast<uint64_t>(wbase + j + 1 + p.index_base));
+                                   static_cast<uint64_t>(ibase + j));
                     }
                     if (HASH) st_u64(p.out_hash + f, h[j]);
                 }
@@ -252,14 +332,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
         }
 
     next_item:
-        if (!RAGGED) {
-            r += p.it_dq;
-            gi += p.it_dr;
-            if (gi >= p.gprm) {
-                gi -= p.gprm;
-                ++r;
-            }
-        }
+        cur.advance(p);
     }
 }
 

@@ -44,6 +44,9 @@ cudaError_t window_counts(const uint64_t *seq_len, uint64_t n, int k, uint64_t *
 // [win_off[r], win_off[r+1])
 cudaError_t group_slots(const uint64_t *win_off, uint64_t n, int g, uint64_t *slots, cudaStream_t stream);
 
+cudaError_t tile_first_reads(const uint64_t *item_off, uint64_t n_seqs, uint64_t tile_items, uint64_t n_tiles,
+                             uint64_t *tile_first, cudaStream_t stream);
+
 // misc_kernels.cu -----------------------------------------------------------------------------
 cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,
                            cudaStream_t stream);

@@ -69,7 +69,16 @@ struct Layout {
     uint64_t gprm;
     const uint64_t *win_off = nullptr;  // device, ragged
     const uint64_t *item_off = nullptr; // device, ragged
+    const uint64_t *tile_first = nullptr; // device, ragged
 };
+
+// upper bound of the tiles any layout of this set can need (windows <= symbols, at most two
+// partial group slots per sequence), for scratch sizing before the exact totals are known
+inline uint64_t tiles_upper_bound(const kmc_seqs *s)
+{
+    const uint64_t spw = s->src_bits == 4 ? 16 : 32;
+    return (s->n_words * spw + 2 * s->n_seqs) / kTileItems + 2;
+}
 
 int32_t check_common(kmc_ctx *ctx, const kmc_seqs *s, int32_t k);
 

@@ -143,4 +143,28 @@ cudaError_t group_slots(const uint64_t *win_off, uint64_t n, int g, uint64_t *sl
     return cudaGetLastError();
 }
 
+// tile_first[t] = the sequence that owns work item t * tile_items (largest r with item_off[r] <= item),
+// for t in [0, n_tiles]; the extraction kernels narrow their per-item searches with it.
+__global__ void tile_first_kernel(const uint64_t *__restrict__ item_off, uint64_t n_seqs, uint64_t tile_items,
+                                  uint64_t n_out, uint64_t *__restrict__ tile_first)
+{
+    const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n_out) return;
+    const uint64_t item = t * tile_items;
+    uint64_t lo = 0, hi = n_seqs;
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (item_off[mid] <= item) lo = mid; else hi = mid;
+    }
+    tile_first[t] = lo;
+}
+
+cudaError_t tile_first_reads(const uint64_t *item_off, uint64_t n_seqs, uint64_t tile_items, uint64_t n_tiles,
+                             uint64_t *tile_first, cudaStream_t stream)
+{
+    const uint64_t n_out = n_tiles + 1;
+    tile_first_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(item_off, n_seqs, tile_items, n_out, tile_first);
+    return cudaGetLastError();
+}
+
 } // namespace kmc
