@@ -300,6 +300,7 @@ int32_t kmc_ctx_destroy(kmc_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->host_small) cudaFreeHost(ctx->host_small);
     for (int i = 0; i < 3; ++i) {
         if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);

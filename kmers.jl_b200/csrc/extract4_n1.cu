@@ -1,6 +1,6 @@
 // 4-bit source (FourToTwo) instantiations for N = 1 limbs: strict Fw/FwRv/Canonical with the
-// uncertain-symbol check, and the UnambiguousKmers compaction kernels.
+// uncertain-symbol check.
 #include "extract_kernels.cuh"
 namespace kmc {
-KMC_DEFINE_FOURBIT_TABLES(get_strict4_launcher_n1, get_compact_launcher_n1, 1)
+KMC_DEFINE_FOURBIT_TABLES(get_strict4_launcher_n1, 1)
 }

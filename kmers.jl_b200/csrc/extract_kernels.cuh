@@ -65,8 +65,6 @@ struct ExtractParams {
     // absolute symbol index in the stream.
     const uint32_t *vstart;
     unsigned long long *err_flat;  // strict modes: atomicMin of the first flat window with an uncertain symbol
-    const uint64_t *tile_out_off;  // UnambiguousKmers: exclusive scan of the per-tile emitted counts
-    uint64_t *tile_count;          // UnambiguousKmers count pass: emitted k-mers per tile
 };
 
 // Validity bits of the slots [jlo, jhi) of one item: bit j set <=> window j has no uncertain symbol.
@@ -87,10 +85,23 @@ template <int N> struct GroupOf { static constexpr int G = (N == 1) ? 4 : (N == 
 // (read, slot) and derives everything the kernels need about the item's windows.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTileBuckets = kTileItems / 32; // one bucket = the 32 items a warp handles in one step
+constexpr int kTileMetaCap = 512;             // sequences of a tile whose descriptors are staged in shared memory
 
-struct TileShared {
-    uint64_t r0, gi0;                // uniform: (read, slot) of the tile's first item
-    uint32_t fr[kTileBuckets + 1];   // ragged: read (relative to r_first) owning the first item of each bucket
+template <bool RAGGED> struct TileShared;
+template <> struct TileShared<false> {
+    uint64_t r0, gi0; // (read, slot) of the tile's first item
+};
+// Ragged sets: the descriptors of the sequences [r_first, r_first + n_meta) that own the tile's items
+// are staged once per tile with coalesced loads, so that locating an item costs shared-memory
+// latency instead of a chain of dependent global loads.  Tiles that span more than kTileMetaCap
+// sequences (very short reads) fall back to the global arrays.
+template <> struct TileShared<true> {
+    uint32_t fr[kTileBuckets + 1]; // sequence (relative to r_first) owning the first item of each bucket
+    uint32_t staged;
+    uint64_t item_off[kTileMetaCap + 1];
+    uint64_t win_off[kTileMetaCap + 1];
+    uint64_t unit_off[kTileMetaCap];
+    uint64_t ibase[kTileMetaCap];
 };
 
 template <bool RAGGED, int G>
@@ -100,13 +111,21 @@ struct TileCursor {
     // derived for the current item
     uint64_t f0, wcount;  // flat index of the read's first window, its window count
     uint64_t unit_off;    // where the read starts in the stream (units of p.unit_bits)
+    uint64_t seq_ibase;   // p.seq_index_base[r] (0 without it)
     uint64_t q;           // aligned flat group of this item
     int64_t wbase;        // window (within the read) of slot 0, in (-G, wcount)
     int jlo, jhi;         // slots [jlo, jhi) are windows of this read
 
-    KMC_DEV void init(const ExtractParams &p, uint64_t tile_base, TileShared &sh)
+    KMC_DEV static uint64_t unit_off_of(const ExtractParams &p, uint64_t rr)
     {
-        if (!RAGGED) {
+        return p.seq_unit_off ? __ldg(p.seq_unit_off + rr) - p.unit_bias : rr * p.stride_units;
+    }
+
+    // li0 = this thread's first local item of the tile (threadIdx.x for the strided item order)
+    KMC_DEV void init(const ExtractParams &p, uint64_t tile_base, TileShared<RAGGED> &sh, uint32_t li0)
+    {
+        seq_ibase = 0;
+        if constexpr (!RAGGED) {
             // (r, gi) = divmod(item, gprm): one 64-bit division per BLOCK, then a 32-bit one per thread
             if (threadIdx.x == 0) {
                 sh.r0 = tile_base / p.gprm;
@@ -114,8 +133,8 @@ struct TileCursor {
             }
             __syncthreads();
             r = sh.r0;
-            gi = sh.gi0 + threadIdx.x;
-            if (p.gprm > 0xffffffffull - kTileItems) { // gi0 + tid wraps at most once
+            gi = sh.gi0 + li0;
+            if (p.gprm > 0xffffffffull - kTileItems) { // gi0 + li0 wraps at most once
                 if (gi >= p.gprm) {
                     gi -= p.gprm;
                     ++r;
@@ -127,39 +146,72 @@ struct TileCursor {
             }
         } else {
             r_first = __ldg(p.tile_first + blockIdx.x);
+            const uint64_t r_last = __ldg(p.tile_first + blockIdx.x + 1);
+            const uint64_t n_meta = r_last - r_first + 1;
+            const bool staged = n_meta <= kTileMetaCap;
+            if (staged) {
+                for (uint32_t t = threadIdx.x; t <= n_meta; t += kBlockThreads) {
+                    sh.item_off[t] = __ldg(p.item_off + r_first + t);
+                    sh.win_off[t] = __ldg(p.win_off + r_first + t);
+                    if (t < n_meta) {
+                        sh.unit_off[t] = unit_off_of(p, r_first + t);
+                        sh.ibase[t] = p.seq_index_base ? __ldg(p.seq_index_base + r_first + t) : 0ull;
+                    }
+                }
+                if (threadIdx.x == 0) sh.staged = 1;
+                __syncthreads();
+            } else if (threadIdx.x == 0) {
+                sh.staged = 0;
+            }
             if (threadIdx.x <= kTileBuckets) {
                 const uint64_t item = tile_base + 32ull * threadIdx.x;
-                uint64_t lo = r_first, hi = __ldg(p.tile_first + blockIdx.x + 1) + 1;
+                uint64_t lo = 0, hi = n_meta; // relative to r_first: largest rr in [lo, hi) with item_off <= item
                 while (hi - lo > 1) {
                     const uint64_t mid = (lo + hi) >> 1;
-                    if (__ldg(p.item_off + mid) <= item) lo = mid; else hi = mid;
+                    const uint64_t v = staged ? sh.item_off[mid] : __ldg(p.item_off + r_first + mid);
+                    if (v <= item) lo = mid; else hi = mid;
                 }
-                sh.fr[threadIdx.x] = static_cast<uint32_t>(lo - r_first);
+                sh.fr[threadIdx.x] = static_cast<uint32_t>(lo);
             }
             __syncthreads();
             r = gi = 0;
         }
     }
 
-    // item = tile_base + it * kBlockThreads + threadIdx.x
-    KMC_DEV void locate(const ExtractParams &p, uint64_t item, int it, const TileShared &sh)
+    // item = tile_base + li
+    KMC_DEV void locate(const ExtractParams &p, uint64_t item, uint32_t li, const TileShared<RAGGED> &sh)
     {
-        if (RAGGED) {
-            const int b = (it * kBlockThreads + static_cast<int>(threadIdx.x)) >> 5;
-            uint64_t lo = r_first + sh.fr[b], hi = r_first + sh.fr[b + 1] + 1;
-            while (hi - lo > 1) { // largest r in [lo, hi) with item_off[r] <= item
-                const uint64_t mid = (lo + hi) >> 1;
-                if (__ldg(p.item_off + mid) <= item) lo = mid; else hi = mid;
+        if constexpr (RAGGED) {
+            const uint32_t b = li >> 5;
+            uint32_t lo = sh.fr[b], hi = sh.fr[b + 1] + 1;
+            if (sh.staged) {
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (sh.item_off[mid] <= item) lo = mid; else hi = mid;
+                }
+                r = r_first + lo;
+                gi = item - sh.item_off[lo];
+                f0 = sh.win_off[lo];
+                wcount = sh.win_off[lo + 1] - f0;
+                unit_off = sh.unit_off[lo];
+                seq_ibase = sh.ibase[lo];
+            } else {
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(p.item_off + r_first + mid) <= item) lo = mid; else hi = mid;
+                }
+                r = r_first + lo;
+                gi = item - __ldg(p.item_off + r);
+                f0 = __ldg(p.win_off + r);
+                wcount = __ldg(p.win_off + r + 1) - f0;
+                unit_off = unit_off_of(p, r);
+                seq_ibase = p.seq_index_base ? __ldg(p.seq_index_base + r) : 0ull;
             }
-            r = lo;
-            gi = item - __ldg(p.item_off + r);
-            f0 = __ldg(p.win_off + r);
-            wcount = __ldg(p.win_off + r + 1) - f0;
         } else {
             f0 = r * p.wpr;
             wcount = p.wpr;
+            unit_off = unit_off_of(p, r);
         }
-        unit_off = p.seq_unit_off ? __ldg(p.seq_unit_off + r) - p.unit_bias : r * p.stride_units;
         q = f0 / G + gi;
         wbase = static_cast<int64_t>(q * G - f0);
         const int64_t rem = static_cast<int64_t>(wcount) - wbase; // windows available from slot 0
@@ -173,6 +225,7 @@ struct TileCursor {
         return static_cast<int64_t>(unit_off) * p.unit_bits + 2 * (static_cast<int64_t>(p.first) + wbase);
     }
 
+    // to the item kBlockThreads further on
     KMC_DEV void advance(const ExtractParams &p)
     {
         if (!RAGGED) {
@@ -180,6 +233,17 @@ struct TileCursor {
             gi += p.it_dr;
             if (gi >= p.gprm) {
                 gi -= p.gprm;
+                ++r;
+            }
+        }
+    }
+
+    // to the next item
+    KMC_DEV void advance1(const ExtractParams &p)
+    {
+        if (!RAGGED) {
+            if (++gi >= p.gprm) {
+                gi = 0;
                 ++r;
             }
         }
@@ -198,18 +262,18 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     // One tile of kTileIters x 256 consecutive work items per block; blocks are scheduled by the
     // hardware as SMs drain, which balances the SMs (a static persistent partition left the
     // fastest SMs idle for 25 % of the kernel: profiles/r01_c2_canon31_hash_v1_persistent.txt).
-    __shared__ TileShared sh;
+    __shared__ TileShared<RAGGED> sh;
     const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
     const uint64_t n_items = p.items_dev ? __ldg(p.items_dev) : p.items;
     if (tile_base >= n_items) return; // block-uniform
     TileCursor<RAGGED, G> cur;
-    cur.init(p, tile_base, sh);
+    cur.init(p, tile_base, sh, threadIdx.x);
 
 #pragma unroll 1
     for (int it = 0; it < kTileIters; ++it) {
         const uint64_t item = tile_base + static_cast<uint64_t>(it) * kBlockThreads + threadIdx.x;
         if (item >= n_items) break;
-        cur.locate(p, item, it, sh);
+        cur.locate(p, item, static_cast<uint32_t>(it) * kBlockThreads + threadIdx.x, sh);
         const uint64_t q = cur.q;
         const int64_t wbase = cur.wbase;
         const int jlo = cur.jlo, jhi = cur.jhi;
@@ -251,8 +315,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             const uint64_t fbase = q * G; // flat index of slot 0
             int64_t ibase = 0;            // 1-based start (within its sequence) of slot 0's window
             if (p.out_index)
-                ibase = wbase + 1 + p.index_base +
-                        (p.seq_index_base ? static_cast<int64_t>(__ldg(p.seq_index_base + cur.r)) : 0);
+                ibase = wbase + 1 + p.index_base + static_cast<int64_t>(cur.seq_ibase);
             const bool full = (jlo == 0) && (jhi == G);
             const bool tuple_rv = (MODE == MODE_FWRV) && p.aos;
             const bool tuple_ix = (p.out_index != nullptr) && p.aos;
@@ -269,14 +332,15 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
                         }
                     store_run<2 * G * N>(p.out_a + fbase * (2 * N), buf, true);
                 } else if (tuple_ix) {
-                    // {u64[N]; i64} elements
+                    // Tuple{Kmer,Int} = {u64[N]; i64} elements
+                    uint64_t buf[G * (N + 1)];
 #pragma unroll
                     for (int j = 0; j < G; ++j) {
-                        uint64_t *e = p.out_a + (fbase + j) * (N + 1);
 #pragma unroll
-                        for (int i = 0; i < N; ++i) st_u64(e + i, a[j][i]);
-                        st_u64(e + N, static_cast<uint64_t>(ibase + j));
+                        for (int i = 0; i < N; ++i) buf[j * (N + 1) + i] = a[j][i];
+                        buf[j * (N + 1) + N] = static_cast<uint64_t>(ibase + j);
                     }
+                    store_run<G * (N + 1)>(p.out_a + fbase * (N + 1), buf, (G * (N + 1)) % 4 == 0);
                 } else {
                     uint64_t buf[G * N];
 #pragma unroll
@@ -334,185 +398,6 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     next_item:
         cur.advance(p);
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// UnambiguousKmers over a 4-bit source (UnambiguousKmers.jl:134-148): every window whose K symbols
-// are all certain, with its 1-based start, in order -- a variable-length, ORDERED output.
-//
-// Same work decomposition as extract_kernel.  Per block iteration (256 items = up to 256*G windows)
-//   1. each thread reads the validity bits of its G windows and counts them,
-//   2. a block-wide exclusive scan turns the counts into compacted slots,
-//   3. threads stage their surviving k-mers / indices / hashes in shared memory (XOR-swizzled so
-//      that the 4-consecutive-slots-per-thread pattern is bank-conflict free),
-//   4. the block copies the staged run to global memory with fully coalesced stores.
-// The output position of a tile comes from an exclusive scan of per-tile counts produced by the
-// COUNT_ONLY instantiation of this kernel (which reads one validity word per item and nothing else).
-// ---------------------------------------------------------------------------------------------
-KMC_DEV uint32_t swz(uint32_t w) { return w ^ ((w >> 4) & 3u); }
-
-template <int N, int NX, bool HASH, bool RAGGED, bool COUNT_ONLY>
-__global__ void __launch_bounds__(kBlockThreads) compact_kernel(const ExtractParams p)
-{
-    constexpr int G = GroupOf<N>::G;
-    constexpr int CAP = kBlockThreads * G; // staged elements per iteration
-    __shared__ uint64_t s_a[COUNT_ONLY ? 1 : CAP * N];
-    __shared__ uint64_t s_i[COUNT_ONLY ? 1 : CAP];
-    __shared__ uint64_t s_h[(COUNT_ONLY || !HASH) ? 1 : CAP];
-    __shared__ uint32_t s_w[kBlockThreads / 32];
-    __shared__ uint64_t s_r0, s_gi0;
-
-    const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t r = 0, gi = 0;
-    if (!RAGGED) {
-        if (threadIdx.x == 0) {
-            s_r0 = tile_base / p.gprm;
-            s_gi0 = tile_base - s_r0 * p.gprm;
-        }
-        __syncthreads();
-        r = s_r0;
-        gi = s_gi0 + threadIdx.x;
-        if (p.gprm > 0xffffffffull - kTileItems) {
-            if (gi >= p.gprm) {
-                gi -= p.gprm;
-                ++r;
-            }
-        } else {
-            const uint32_t q = static_cast<uint32_t>(gi) / static_cast<uint32_t>(p.gprm);
-            gi -= static_cast<uint64_t>(q) * p.gprm;
-            r += q;
-        }
-    }
-    uint64_t out_run = COUNT_ONLY ? 0 : __ldg(p.tile_out_off + blockIdx.x); // next output element of this tile
-    uint32_t my_count = 0;
-    const bool aos = p.aos != 0;
-
-#pragma unroll 1
-    for (int it = 0; it < kTileIters; ++it) {
-        const uint64_t item0 = tile_base + static_cast<uint64_t>(it) * kBlockThreads;
-        if (item0 >= p.items) break; // block-uniform
-        const uint64_t item = item0 + threadIdx.x;
-        uint32_t m = 0;
-        int64_t wbase = 0, bit = 0;
-        if (item < p.items) {
-            uint64_t f0, wcount;
-            if (RAGGED) {
-                uint64_t lo = 0, hi = p.n_seqs;
-                while (hi - lo > 1) {
-                    uint64_t mid = (lo + hi) >> 1;
-                    if (__ldg(p.item_off + mid) <= item) lo = mid; else hi = mid;
-                }
-                r = lo;
-                gi = item - __ldg(p.item_off + r);
-                f0 = __ldg(p.win_off + r);
-                wcount = __ldg(p.win_off + r + 1) - f0;
-            } else {
-                f0 = r * p.wpr;
-                wcount = p.wpr;
-            }
-            const uint64_t unit_off = p.seq_unit_off ? __ldg(p.seq_unit_off + r) - p.unit_bias : r * p.stride_units;
-            const uint64_t q = f0 / G + gi;
-            wbase = static_cast<int64_t>(q * G - f0);
-            const int64_t rem = static_cast<int64_t>(wcount) - wbase;
-            const int jlo = wbase < 0 ? static_cast<int>(-wbase) : 0;
-            const int jhi = rem < G ? static_cast<int>(rem) : G;
-            bit = static_cast<int64_t>(unit_off) * p.unit_bits + 2 * (static_cast<int64_t>(p.first) + wbase);
-            if (jhi > jlo) m = valid_slots(p.vstart, bit >> 1, jlo, jhi);
-        }
-        const uint32_t cnt = __popc(m);
-        if (COUNT_ONLY) {
-            my_count += cnt;
-        } else {
-            // block-wide exclusive scan of cnt (thread order == output order)
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (lane == 31) s_w[warp] = incl;
-            __syncthreads(); // also: every thread has finished copying out the previous iteration
-            uint32_t before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kBlockThreads / 32; ++w) {
-                const uint32_t v = s_w[w];
-                before += (w < warp) ? v : 0u;
-                total += v;
-            }
-            uint32_t slot = before + incl - cnt;
-
-            if (m) {
-                uint32_t x[NX];
-                load_block<NX>(p.w32, p.nw32, bit, x);
-                uint64_t fw[G][N], rv[G][N];
-                block_kmers<N, NX, G, true, false>(x, p.s0, p.head_mask, fw, rv);
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    if ((m >> j) & 1u) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) s_a[swz(slot * N + i)] = fw[j][i];
-                        s_i[swz(slot)] = static_cast<uint64_t>(wbase + j + 1 + p.index_base);
-                        if (HASH) s_h[swz(slot)] = fx_hash<N>(fw[j], 0);
-                        ++slot;
-                    }
-                }
-            }
-            __syncthreads();
-            // coalesced copy-out of `total` elements starting at output element out_run
-            if (aos) {
-                // Tuple{Kmer,Int} = {u64[N]; i64}
-                uint64_t *dst = p.out_a + out_run * (N + 1);
-                for (uint32_t w = threadIdx.x; w < total * (N + 1); w += kBlockThreads) {
-                    const uint32_t e = w / (N + 1), c = w - e * (N + 1);
-                    st_u64(dst + w, c < N ? s_a[swz(e * N + c)] : s_i[swz(e)]);
-                }
-            } else {
-                uint64_t *dst = p.out_a + out_run * N;
-                for (uint32_t w = threadIdx.x; w < total * N; w += kBlockThreads) st_u64(dst + w, s_a[swz(w)]);
-                uint64_t *di = reinterpret_cast<uint64_t *>(p.out_index) + out_run;
-                for (uint32_t w = threadIdx.x; w < total; w += kBlockThreads) st_u64(di + w, s_i[swz(w)]);
-            }
-            if (HASH) {
-                uint64_t *dh = p.out_hash + out_run;
-                for (uint32_t w = threadIdx.x; w < total; w += kBlockThreads) st_u64(dh + w, s_h[swz(w)]);
-            }
-            out_run += total;
-        }
-        if (!RAGGED) {
-            r += p.it_dq;
-            gi += p.it_dr;
-            if (gi >= p.gprm) {
-                gi -= p.gprm;
-                ++r;
-            }
-        }
-    }
-
-    if (COUNT_ONLY) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) my_count += __shfl_xor_sync(0xffffffffu, my_count, d);
-        if (lane == 0) s_w[warp] = my_count;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-#pragma unroll
-            for (int w = 0; w < kBlockThreads / 32; ++w) t += s_w[w];
-            p.tile_count[blockIdx.x] = t;
-        }
-    }
-}
-
-template <int N, int NX, bool HASH, bool RAGGED, bool COUNT_ONLY>
-cudaError_t launch_compact(ExtractParams p, int /*sm_count*/, cudaStream_t stream)
-{
-    const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
-    if (tiles == 0) return cudaSuccess;
-    if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    p.it_dq = kBlockThreads / p.gprm;
-    p.it_dr = kBlockThreads % p.gprm;
-    compact_kernel<N, NX, HASH, RAGGED, COUNT_ONLY><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
-    return cudaGetLastError();
 }
 
 // Host-side launcher: one block per tile of kTileItems work items.  Defined per N in
@@ -575,18 +460,14 @@ constexpr int MODE_BUCKETS = -1;
     }
 
 // 4-bit (FourToTwo) launchers, one translation unit per N (extract4_n{1,2,3,4}.cu):
-//   strict  FwKmers / FwRvIterator / CanonicalKmers with the uncertain-symbol check
-//   compact UnambiguousKmers (ordered compaction) and its count pass
+//   strict FwKmers / FwRvIterator / CanonicalKmers with the uncertain-symbol check.
+// (UnambiguousKmers over a 4-bit source runs the ordinary ragged kernels over a run list, fourbit.cu.)
 ExtractLaunchFn get_strict4_launcher_n1(int nx, int mode, bool hash, bool ragged);
 ExtractLaunchFn get_strict4_launcher_n2(int nx, int mode, bool hash, bool ragged);
 ExtractLaunchFn get_strict4_launcher_n3(int nx, int mode, bool hash, bool ragged);
 ExtractLaunchFn get_strict4_launcher_n4(int nx, int mode, bool hash, bool ragged);
-ExtractLaunchFn get_compact_launcher_n1(int nx, bool hash, bool ragged, bool count_only);
-ExtractLaunchFn get_compact_launcher_n2(int nx, bool hash, bool ragged, bool count_only);
-ExtractLaunchFn get_compact_launcher_n3(int nx, bool hash, bool ragged, bool count_only);
-ExtractLaunchFn get_compact_launcher_n4(int nx, bool hash, bool ragged, bool count_only);
 
-#define KMC_DEFINE_FOURBIT_TABLES(FN_STRICT, FN_COMPACT, N)                                         \
+#define KMC_DEFINE_FOURBIT_TABLES(FN_STRICT, N)                                         \
     template <int NX, int MODE>                                                                     \
     static ExtractLaunchFn pick4_##N(bool hash, bool ragged)                                        \
     {                                                                                               \
@@ -612,23 +493,6 @@ ExtractLaunchFn get_compact_launcher_n4(int nx, bool hash, bool ragged, bool cou
         if (nx == NXMAX) return pick4_mode_##N<NXMAX>(mode, hash, ragged);                          \
         if (nx == NXMAX - 1) return pick4_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
         if (nx == NXMAX - 2) return pick4_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
-        return nullptr;                                                                             \
-    }                                                                                               \
-    template <int NX>                                                                               \
-    static ExtractLaunchFn pickc_##N(bool hash, bool ragged)                                        \
-    {                                                                                               \
-        if (hash)                                                                                   \
-            return ragged ? &launch_compact<N, NX, true, true, false> : &launch_compact<N, NX, true, false, false>; \
-        return ragged ? &launch_compact<N, NX, false, true, false> : &launch_compact<N, NX, false, false, false>;   \
-    }                                                                                               \
-    ExtractLaunchFn FN_COMPACT(int nx, bool hash, bool ragged, bool count_only)                     \
-    {                                                                                               \
-        constexpr int NXMAX = (64 * N + 2 * GroupOf<N>::G - 2 + 31) / 32;                           \
-        if (count_only)                                                                             \
-            return ragged ? &launch_compact<N, NXMAX, false, true, true> : &launch_compact<N, NXMAX, false, false, true>; \
-        if (nx == NXMAX) return pickc_##N<NXMAX>(hash, ragged);                                     \
-        if (nx == NXMAX - 1) return pickc_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(hash, ragged);       \
-        if (nx == NXMAX - 2) return pickc_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(hash, ragged);       \
         return nullptr;                                                                             \
     }
 

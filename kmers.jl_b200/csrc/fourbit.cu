@@ -8,6 +8,7 @@ namespace kmc {
 namespace {
 
 constexpr uint64_t kNone = ~0ull;
+constexpr int kRunLayoutG = 32; // windows per work item of the run-marking kernels (runs.cu)
 
 // ---- bit-parallel recoding of one LongSequence{<:NucleicAcidAlphabet{4}} word (16 nibbles) ------
 // 2-bit code of a one-hot nibble = trailing_zeros (A=1,C=2,G=4,T=8 -> 0,1,2,3;
@@ -54,24 +55,44 @@ __global__ void __launch_bounds__(256) recode_kernel(const uint64_t *__restrict_
 }
 
 // vstart word i: bit t set <=> no uncertain symbol in [32i + t, 32i + t + K).
+// Sliding-window OR of length K over the flag stream by doubling: A_1 = flags, A_2L = A_L | A_L >> L
+// while 2L <= K, then two windows of length L cover [P, P+K): A_L | A_L >> (K - L).  Branch-free
+// in the data (K is uniform), ~40 funnel shifts per 32 symbols.
 __global__ void __launch_bounds__(256) vstart_kernel(const uint32_t *__restrict__ bad, uint64_t n_bad, int k,
                                                      uint32_t *__restrict__ vstart, uint64_t n_out)
 {
     const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
-    const int span = (k + 30) >> 5; // extra words that windows starting in word i can reach
-    uint32_t inv = 0;
-    for (int d = 0; d <= span && inv != 0xffffffffu; ++d) {
-        uint32_t b = (i + d < n_bad) ? __ldg(bad + i + d) : 0u;
-        while (b) {
-            const int q = 32 * d + (__ffs(b) - 1); // position of an uncertain symbol relative to 32i
-            b &= b - 1;
-            const int lo = q - k + 1 > 0 ? q - k + 1 : 0;
-            const int hi = q < 31 ? q : 31;
-            if (lo <= hi) inv |= (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+    uint32_t a[6];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) a[d] = (i + d < n_bad) ? __ldg(bad + i + d) : 0u; // 31 + K - 1 <= 158 < 160 bits
+    a[5] = 0;
+    int L = 1;
+#pragma unroll
+    for (int step = 0; step < 7; ++step) {
+        const int s = 1 << step; // current window length
+        if (2 * s <= k) {
+            if (s < 32) {
+#pragma unroll
+                for (int w = 0; w < 5; ++w) a[w] |= __funnelshift_r(a[w], a[w + 1], s);
+            } else if (s == 32) {
+#pragma unroll
+                for (int w = 0; w < 5; ++w) a[w] |= a[w + 1];
+            } else {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) a[w] |= a[w + 2];
+            }
+            L = 2 * s;
         }
     }
-    vstart[i] = ~inv;
+    const int r = k - L; // 0 <= r < L, r < 64
+    uint32_t v = a[0];
+    if (r) {
+        const int b = r & 31;
+        if (r < 32) v |= __funnelshift_r(a[0], a[1], b);
+        else v |= b ? __funnelshift_r(a[1], a[2], b) : a[1];
+    }
+    vstart[i] = ~v;
 }
 
 // Turns the first offending flat window of a strict mode into what the reference throws on:
@@ -149,42 +170,31 @@ ExtractLaunchFn strict_launcher(const Geometry &ge, int mode, bool hash, bool ra
     return nullptr;
 }
 
-ExtractLaunchFn compact_launcher(const Geometry &ge, bool hash, bool ragged, bool count_only)
-{
-    switch (ge.n_limbs) {
-    case 1: return get_compact_launcher_n1(ge.nx, hash, ragged, count_only);
-    case 2: return get_compact_launcher_n2(ge.nx, hash, ragged, count_only);
-    case 3: return get_compact_launcher_n3(ge.nx, hash, ragged, count_only);
-    case 4: return get_compact_launcher_n4(ge.nx, hash, ragged, count_only);
-    }
-    return nullptr;
-}
-
-// upper bound of the number of tiles a set can need (windows <= symbols; at most two partial
-// group slots per sequence)
-uint64_t tiles_bound(const kmc_seqs *s, int g)
-{
-    const uint64_t items = s->n_words * 16 / static_cast<uint64_t>(g) + 2 * s->n_seqs + 2;
-    return (items + kTileItems - 1) / kTileItems + 1;
-}
-
 } // namespace
 
 uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
 {
-    const Geometry ge = geometry(k);
+    (void)k;
     const uint64_t nb = (s->n_words + 1) / 2;
-    const uint64_t tb = tiles_bound(s, ge.g);
+    const uint64_t tb = tiles_upper_bound(s);
     uint64_t need = 0;
-    need += round_up(8 * (nb + 2), 256);      // rec32
-    need += 2 * round_up(4 * (nb + 8), 256);  // bad, vstart
-    need += 2 * 256;                          // err_flat, err_out
+    need += round_up(8 * (nb + 2), 256);     // rec32
+    need += 2 * round_up(4 * (nb + 8), 256); // bad, vstart
+    need += 2 * 256;                         // err_flat, err_out
     need += layout_scratch_bytes(s);
     if (mode == KMC_UNAMBIG) {
-        need += round_up(8 * (tb + 1), 256) + round_up(8 * (tb + 2), 256) + round_up(8 * scan_tmp_elems(tb), 256);
+        need += 2 * round_up(8 * (tb + 1), 256) + 2 * round_up(8 * (tb + 2), 256) + round_up(8 * scan_tmp_elems(tb), 256);
         need += round_up(8 * (s->n_seqs + 1), 256) + round_up(8 * scan_tmp_elems(s->n_seqs), 256); // seq_out_offset
     }
     return need + 1024;
+}
+
+uint64_t run_scratch_bytes(uint64_t n_runs, uint64_t n_valid, int g)
+{
+    const uint64_t items = n_valid / static_cast<uint64_t>(g) + 2 * n_runs + 2;
+    const uint64_t tiles = (items + kTileItems - 1) / kTileItems + 1;
+    return 5 * round_up(8 * (n_runs + 2), 256) + round_up(8 * scan_tmp_elems(n_runs + 1), 256) +
+           round_up(8 * (tiles + 2), 256) + 1024;
 }
 
 int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,
@@ -222,7 +232,11 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     vstart_kernel<<<static_cast<unsigned>((nb + 2 + 255) / 256), 256, 0, stream>>>(bad, nb, k, vstart, nb + 2);
     CU(cudaGetLastError());
 
-    int32_t rc = plan_layout(ctx, s, k, ge, stream, known, scratch, &st->L);
+    // strict modes lay the set out for the extraction kernel's G; UnambiguousKmers lays it out in
+    // groups of 32 windows for the run-marking kernels (the extraction runs over the run list)
+    Geometry lay = ge;
+    if (st->unambig) lay.g = kRunLayoutG;
+    int32_t rc = plan_layout(ctx, s, k, lay, stream, known, scratch, &st->L);
     if (rc) return rc;
     const Layout &L = st->L;
 
@@ -251,20 +265,22 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
         return KMC_OK;
     }
 
-    // UnambiguousKmers: count pass -> per-tile offsets -> total
+    // UnambiguousKmers: survivors and run starts per tile -> scans -> totals
     const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
-    uint64_t *tile_cnt = static_cast<uint64_t *>(scratch.take(8 * (tiles + 1)));
-    uint64_t *tile_off = static_cast<uint64_t *>(scratch.take(8 * (tiles + 2)));
+    uint64_t *tile_valid = static_cast<uint64_t *>(scratch.take(8 * (tiles + 1)));
+    uint64_t *tile_runs = static_cast<uint64_t *>(scratch.take(8 * (tiles + 1)));
+    uint64_t *tile_valid_off = static_cast<uint64_t *>(scratch.take(8 * (tiles + 2)));
+    uint64_t *tile_runs_off = static_cast<uint64_t *>(scratch.take(8 * (tiles + 2)));
     uint64_t *tmp = static_cast<uint64_t *>(scratch.take(8 * scan_tmp_elems(tiles)));
-    if (!tile_cnt || !tile_off || !tmp) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
-    st->tile_off = tile_off;
-    st->p.tile_count = tile_cnt;
-    st->p.tile_out_off = tile_off;
-    ExtractLaunchFn cf = compact_launcher(ge, false, !L.uniform_len, true);
-    if (!cf) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
-    CU(cf(st->p, ctx->sm_count, stream));
-    CU(inclusive_offsets_u64(tile_cnt, tile_off, tiles, tmp, stream));
-    CU(cudaMemcpyAsync(&host_small[0], tile_off + tiles, 8, cudaMemcpyDeviceToHost, stream));
+    if (!tile_valid || !tile_runs || !tile_valid_off || !tile_runs_off || !tmp)
+        return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+    st->tile_valid_off = tile_valid_off;
+    st->tile_runs_off = tile_runs_off;
+    CU(mark_runs(st->p, !L.uniform_len, tile_valid, tile_runs, stream));
+    CU(inclusive_offsets_u64(tile_valid, tile_valid_off, tiles, tmp, stream));
+    CU(inclusive_offsets_u64(tile_runs, tile_runs_off, tiles, tmp, stream));
+    CU(cudaMemcpyAsync(&host_small[0], tile_valid_off + tiles, 8, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&host_small[2], tile_runs_off + tiles, 8, cudaMemcpyDeviceToHost, stream));
     if (out && out->seq_out_offset) {
         uint64_t *cnt = static_cast<uint64_t *>(scratch.take(8 * (s->n_seqs + 1)));
         uint64_t *tmp2 = static_cast<uint64_t *>(scratch.take(8 * scan_tmp_elems(s->n_seqs)));
@@ -277,7 +293,8 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     return KMC_OK;
 }
 
-int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, kmc_result *res)
+int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, Scratch &runs,
+                        kmc_result *res)
 {
     const Layout &L = st->L;
     if (!st->unambig) {
@@ -296,14 +313,52 @@ int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cuda
         return KMC_OK;
     }
     const uint64_t total = L.total ? st->host_small[0] : 0;
+    const uint64_t n_runs = L.total ? st->host_small[2] : 0;
     res->n_written = total;
     if (total == 0) return KMC_OK;
     if (total > out->capacity) return fail(ctx, KMC_E_OUT_TOO_SMALL, "output capacity smaller than the number of k-mers");
-    int32_t rc = bind_outputs(ctx, out, KMC_UNAMBIG, st->flags, &st->p);
+
+    // ---- run list: the surviving windows as a ragged set of "sequences" ------------------------
+    const int G = st->ge.g;
+    uint64_t *run_sym = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
+    uint64_t *run_woff = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
+    uint64_t *run_ibase = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
+    uint64_t *slots = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
+    uint64_t *run_item_off = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
+    uint64_t *tmp = static_cast<uint64_t *>(runs.take(8 * scan_tmp_elems(n_runs + 1)));
+    const uint64_t items_bound = total / static_cast<uint64_t>(G) + 2 * n_runs + 2;
+    const uint64_t tiles_bound = (items_bound + kTileItems - 1) / kTileItems;
+    uint64_t *tile_first = static_cast<uint64_t *>(runs.take(8 * (tiles_bound + 2)));
+    if (!run_sym || !run_woff || !run_ibase || !slots || !run_item_off || !tmp || !tile_first)
+        return fail(ctx, KMC_E_BAD_ARG, "internal: run scratch window too small");
+    CU(emit_runs(st->p, !L.uniform_len, st->tile_valid_off, st->tile_runs_off, run_sym, run_woff, run_ibase, stream));
+    const uint64_t tiles32 = (L.items + kTileItems - 1) / kTileItems;
+    CU(cudaMemcpyAsync(run_woff + n_runs, st->tile_valid_off + tiles32, 8, cudaMemcpyDeviceToDevice, stream)); // sentinel = total
+    CU(group_slots(run_woff, n_runs, G, slots, stream));
+    CU(inclusive_offsets_u64(slots, run_item_off, n_runs, tmp, stream));
+    CU(tile_first_reads(run_item_off, n_runs, kTileItems, tiles_bound, tile_first, stream));
+
+    // ---- the ordinary ragged extraction over the runs (MODE_FW + index) ------------------------
+    ExtractParams p = st->p;
+    p.unit_bits = 2; // run offsets are absolute SYMBOL indices of the recoded stream
+    p.unit_bias = 0;
+    p.first = 0;
+    p.n_seqs = n_runs;
+    p.items = items_bound;             // grid upper bound;
+    p.items_dev = run_item_off + n_runs; // the exact number of work items lives on the device
+    p.stride_units = 0;
+    p.wpr = 0;
+    p.gprm = 1;
+    p.seq_unit_off = run_sym;
+    p.win_off = run_woff;
+    p.item_off = run_item_off;
+    p.tile_first = tile_first;
+    p.seq_index_base = run_ibase;
+    int32_t rc = bind_outputs(ctx, out, KMC_UNAMBIG, st->flags, &p);
     if (rc) return rc;
-    ExtractLaunchFn fn = compact_launcher(st->ge, (st->flags & KMC_HASH_FX) != 0, !L.uniform_len, false);
+    ExtractLaunchFn fn = get_launcher(st->ge, MODE_FW, (st->flags & KMC_HASH_FX) != 0, true);
     if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
-    CU(fn(st->p, ctx->sm_count, stream));
+    CU(fn(p, ctx->sm_count, stream));
     return KMC_OK;
 }
 
@@ -320,7 +375,21 @@ int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t 
     rc = fourbit_phase_a(ctx, s, k, mode, flags, out, stream, KnownTotals(), 0, scratch, ctx->host_small, &st);
     if (rc) return rc;
     CU(cudaStreamSynchronize(stream));
-    rc = fourbit_phase_b(ctx, &st, out, stream, res);
+    Scratch runs;
+    if (mode == KMC_UNAMBIG && st.L.total && ctx->host_small[0]) {
+        // the run list is sized exactly, now that the counts are known (second grow-only buffer, so
+        // the recoded stream in the first one stays where it is)
+        const uint64_t need = run_scratch_bytes(ctx->host_small[2], ctx->host_small[0], st.ge.g);
+        if (need > ctx->scratch2_bytes) {
+            if (ctx->scratch2) CU(cudaFree(ctx->scratch2));
+            ctx->scratch2 = nullptr;
+            ctx->scratch2_bytes = 0;
+            CU(cudaMalloc(&ctx->scratch2, need + need / 4));
+            ctx->scratch2_bytes = need + need / 4;
+        }
+        runs = Scratch{static_cast<char *>(ctx->scratch2), ctx->scratch2_bytes, 0};
+    }
+    rc = fourbit_phase_b(ctx, &st, out, stream, runs, res);
     if (rc) return rc;
     if (mode != KMC_UNAMBIG && out->seq_out_offset) {
         if (st.L.uniform_len)

@@ -9,8 +9,10 @@
 //   strict FwKmers / FwRvIterator / CanonicalKmers (FwKmers.jl:104-115, CanonicalKmers.jl:131-144):
 //     the first window with an uncertain symbol is reported; the call fails with KMC_E_AMBIGUOUS
 //     and the position / encoding the reference's throw_uncertain (construction.jl:108-110) names;
-//   UnambiguousKmers (UnambiguousKmers.jl:134-148): windows with an uncertain symbol are skipped,
-//     the survivors are compacted in order with their 1-based start.
+//   UnambiguousKmers (UnambiguousKmers.jl:134-148): windows with an uncertain symbol are skipped.
+//     The survivors form runs of consecutive windows; a run list is built from the valid-start
+//     bits (runs.cu) and the ordinary ragged extraction kernel emits the runs in order, each
+//     k-mer with its 1-based start inside its read.
 #pragma once
 #include "plan.h"
 
@@ -26,23 +28,33 @@ struct FourBitState {
     int k = 0, mode = 0;
     uint32_t flags = 0;
     Geometry ge{};
-    Layout L{};
+    Layout L{};      // strict: layout for the kernel's G; UnambiguousKmers: the G = 32 run-marking layout
     ExtractParams p{};
     uint32_t *bad = nullptr;
-    uint64_t *tile_off = nullptr;
+    uint64_t *tile_valid_off = nullptr, *tile_runs_off = nullptr; // UnambiguousKmers: scans of the per-tile counts
     uint64_t *err_out = nullptr; // device u64[3]: seq, 1-based pos, encoding
     uint64_t *host_small = nullptr;
     uint64_t unit_bias = 0;
     bool unambig = false;
 };
 
+// bytes phase B of UnambiguousKmers needs for a run list of n_runs runs and n_valid k-mers
+uint64_t run_scratch_bytes(uint64_t n_runs, uint64_t n_valid, int g);
+
+// runs.cu
+cudaError_t mark_runs(const ExtractParams &p, bool ragged, uint64_t *tile_valid, uint64_t *tile_runs, cudaStream_t stream);
+cudaError_t emit_runs(const ExtractParams &p, bool ragged, const uint64_t *tile_valid_off, const uint64_t *tile_runs_off,
+                      uint64_t *run_sym, uint64_t *run_woff, uint64_t *run_ibase, cudaStream_t stream);
+
 uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode);
 
 int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,
                         cudaStream_t stream, const KnownTotals &known, uint64_t unit_bias, Scratch &scratch,
                         uint64_t *host_small, FourBitState *st);
-// Fills res->n_written (and err_* with KMC_E_AMBIGUOUS).  Enqueues the compaction for UnambiguousKmers.
-int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, kmc_result *res);
+// Fills res->n_written (and err_* with KMC_E_AMBIGUOUS).  For UnambiguousKmers: builds the run list in
+// `runs` (at least run_scratch_bytes(host_small[2], host_small[0], G) bytes) and enqueues the extraction.
+int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, Scratch &runs,
+                        kmc_result *res);
 
 // kmc_extract on device buffers: phase A, sync, phase B, sync.
 int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags,

@@ -54,13 +54,15 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
     result->kernel_ms = 0.f;
 
     const Geometry ge = geometry(k);
-    const uint64_t N = static_cast<uint64_t>(ge.n_limbs), G = static_cast<uint64_t>(ge.g);
+    const uint64_t N = static_cast<uint64_t>(ge.n_limbs);
     const bool four = hs->src_bits == 4;
     const uint64_t spw = four ? 16 : 32; // symbols per source word
     const bool hash = (flags & KMC_HASH_FX) != 0;
     const bool aos = (flags & KMC_AOS) != 0;
     const bool want_index = (mode == KMC_UNAMBIG);
     const bool compacting = four && mode == KMC_UNAMBIG; // variable-length output
+    // windows per work item of the layout the device planner will build (run marking uses 32)
+    const uint64_t G = compacting ? 32 : static_cast<uint64_t>(ge.g);
     const bool two = (mode == KMC_FWRV);
     const bool ragged_len = hs->seq_len != nullptr;
     const bool ragged_off = hs->seq_word_offset != nullptr;
@@ -188,7 +190,10 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
     worst.n_words = max_words;
     worst.n_seqs = single ? 1 : max_seq;
     if (single) worst.seq_len = nullptr;
-    const uint64_t scratch_per_slot = round_up(extract_scratch_bytes(&worst, k, mode), 256);
+    // UnambiguousKmers over 4 bits: the run list of a chunk is carved from the slot's window at its
+    // worst case (every other window survives)
+    const uint64_t run_bytes = compacting ? round_up(run_scratch_bytes(max_out / 2 + 1, max_out, ge.g), 256) : 0;
+    const uint64_t scratch_per_slot = round_up(extract_scratch_bytes(&worst, k, mode), 256) + run_bytes;
     st = ensure_scratch(ctx, scratch_per_slot * n_slots);
     if (st) return st;
     st = ensure_host_small(ctx);
@@ -243,7 +248,12 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         Slot &sl = slots[ci % n_slots];
         CU(cudaEventSynchronize(sl.ev_a));
         kmc_result r{};
-        int32_t rc = fourbit_phase_b(ctx, &c.fb, &c.dout, sl.stream, &r);
+        Scratch runs;
+        if (compacting) { // the tail of the slot's scratch window
+            runs.base = sl.scratch.base + (scratch_per_slot - run_bytes);
+            runs.bytes = run_bytes;
+        }
+        int32_t rc = fourbit_phase_b(ctx, &c.fb, &c.dout, sl.stream, runs, &r);
         if (rc == KMC_E_AMBIGUOUS) {
             result->n_written = 0;
             result->err_seq = single ? 0 : c.seq0 + r.err_seq;
@@ -309,6 +319,7 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         dout.capacity = c.nout;
         dout.index_base = c.index_base + ho->index_base;
         Scratch scratch = sl.scratch;
+        scratch.bytes -= run_bytes;
         scratch.used = 0;
         if (!four) {
             kmc_result r{};

@@ -157,6 +157,28 @@ def test_single_sequence_strict(kc, k):
                     assert ei.value.symbol == "-ACMGRSVTWYHKDBN"[int(bad[p])]
 
 
+@pytest.mark.parametrize("k,amb", [(1, 0.5), (3, 0.2), (31, 0.03), (64, 0.01)])
+def test_dense_ambiguity_many_runs(kc, k, amb):
+    """Lots of short runs (more runs per tile than the kernel stages in shared memory)."""
+    rng = np.random.default_rng(31 * k)
+    n = 300_000
+    codes = random_codes4(rng, n, amb)
+    w = kt.pack_codes(codes, 4)
+    rs = kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet4, w, n))
+    km, pos = ko.unambiguous(w, n, k, src_bits=4)
+    for aos in (False, True):
+        e = kc.extract(UNAMBIG, rs, k, hash=True, aos=aos)
+        N = kc.n_limbs(k)
+        assert e.n == km.shape[0]
+        if aos:
+            assert np.array_equal(e.kmers[:, :N], km) and np.array_equal(e.kmers[:, N].astype(np.int64), pos)
+        else:
+            assert np.array_equal(e.kmers, km) and np.array_equal(e.index, pos)
+        assert np.array_equal(e.hash, ko.fx_hash(km))
+    e = kc.extract(UNAMBIG, rs, k, host_path=True)
+    assert np.array_equal(e.kmers, km) and np.array_equal(e.index, pos)
+
+
 def make_ragged4(rng, lens, amb):
     codes = [random_codes4(rng, n, amb) for n in lens]
     packed = [kt.pack_codes(c, 4) if len(c) else np.zeros(0, np.uint64) for c in codes]

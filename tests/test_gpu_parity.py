@@ -151,6 +151,20 @@ def test_ragged_read_set(kc, k):
     assert np.array_equal(e.index, want_idx)
 
 
+@pytest.mark.parametrize("k", [4, 31, 63])
+def test_ragged_many_short_reads(kc, k):
+    """Thousands of reads of 0-2 work items each: a tile spans more sequences than the kernel
+    stages in shared memory, so the global-array fallback of the item search runs."""
+    rng = np.random.default_rng(900 + k)
+    lens = rng.integers(max(0, k - 2), k + 6, size=20_000).tolist()
+    seqs, words, off, ln = make_ragged(rng, lens)
+    rs = kc.ReadSet(2, words, len(lens), seq_word_offset=off, seq_len=ln)
+    a, _, h, out_off = ko.batch_iterate(words, len(lens), k, ko.CANON, word_off=off, seq_len=ln, want_hash=True)
+    e = kc.extract(MODES["canon"], rs, k, hash=True, want_seq_offsets=True)
+    assert e.n == a.shape[0] and np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+    assert np.array_equal(e.seq_out_offset, out_off)
+
+
 @pytest.mark.parametrize("k,length", [(31, 150), (31, 151), (31, 149), (21, 100), (63, 150), (63, 151), (5, 36),
                                       (31, 31), (31, 30), (32, 250), (97, 300)])
 def test_uniform_read_set(kc, k, length):
