@@ -61,6 +61,12 @@ extern "C" {
                             (out.a / out.b / out.index separate). */
 #define KMC_NO_SYNC 0x4u /* do not synchronise the stream before returning (2-bit sources,
                             fixed-count modes only; result->n_written is still exact) */
+#define KMC_OUT_DEVICE 0x8u /* kmc_extract_host only: the kmc_out buffers are DEVICE memory (the
+                            sequences still come from the host).  The streams stay in HBM for a
+                            device consumer; out.seq_out_offset must be NULL. */
+#define KMC_DIGEST 0x10u /* kmc_extract_host only: also fingerprint what was written -- xor and wrapping
+                            sum of the out.a words and of the out.hash words -> result->digest[4].
+                            Computed chunk by chunk inside the pipeline, while the chunk is L2-hot. */
 
 typedef struct kmc_ctx kmc_ctx;
 
@@ -96,6 +102,7 @@ typedef struct kmc_result {
     uint64_t err_pos;   /*   1-based symbol position within it, */
     uint32_t err_sym;   /*   and the offending 4-bit encoding (reinterpret(DNA, x)) */
     float kernel_ms;    /* device time of the launches of this call (cudaEvents), 0 with KMC_NO_SYNC */
+    uint64_t digest[4]; /* KMC_DIGEST: xor(a), sum(a), xor(hash), sum(hash) */
 } kmc_result;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
@@ -150,6 +157,11 @@ int32_t kmc_fx_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n_l
  * by the caller's collective (torch.distributed / NCCL all-reduce). */
 int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
                          uint32_t *table, kmc_result *result);
+
+/* XOR and wrapping sum of n u64 words in device memory -> out[0], out[1] (host).  A cheap
+ * fingerprint of a device-resident stream: parity checks and result read-back at sizes where
+ * downloading the stream itself would only measure PCIe.  Synchronises. */
+int32_t kmc_digest(kmc_ctx *ctx, const uint64_t *dptr, uint64_t n, uint64_t *out);
 
 /* ---- timing (cudaEvents on the context's stream) ------------------------------------ */
 int32_t kmc_timer_begin(kmc_ctx *ctx);

@@ -61,7 +61,8 @@ mutable struct KmcResult
     err_pos::UInt64
     err_sym::UInt32
     kernel_ms::Float32
-    KmcResult() = new(0, 0, 0, 0, 0.0f0)
+    digest::NTuple{4, UInt64}
+    KmcResult() = new(0, 0, 0, 0, 0.0f0, (0, 0, 0, 0))
 end
 
 mutable struct Context

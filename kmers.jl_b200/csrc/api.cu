@@ -239,6 +239,7 @@ int32_t ensure_host_small(kmc_ctx *ctx)
     if (ctx->host_small) return KMC_OK;
     CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->host_small), 4096, cudaHostAllocDefault));
     memset(ctx->host_small, 0, 4096);
+    CU(cudaMalloc(reinterpret_cast<void **>(&ctx->dev_small), 64));
     return KMC_OK;
 }
 
@@ -302,6 +303,7 @@ int32_t kmc_ctx_destroy(kmc_ctx *ctx)
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->host_small) cudaFreeHost(ctx->host_small);
+    if (ctx->dev_small) cudaFree(ctx->dev_small);
     for (int i = 0; i < 3; ++i) {
         if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
         if (ctx->pipe_streams[i]) cudaStreamDestroy(ctx->pipe_streams[i]);
@@ -525,6 +527,20 @@ int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t 
     CU(cudaEventRecord(ctx->ev_k1, stream));
     CU(cudaStreamSynchronize(stream));
     CU(cudaEventElapsedTime(&result->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+    return KMC_OK;
+}
+
+int32_t kmc_digest(kmc_ctx *ctx, const uint64_t *dptr, uint64_t n, uint64_t *out)
+{
+    if (!ctx) return KMC_E_BAD_ARG;
+    if (!out || (n && !dptr)) return fail(ctx, KMC_E_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    int32_t st = ensure_scratch(ctx, 256);
+    if (st) return st;
+    uint64_t *acc = static_cast<uint64_t *>(ctx->scratch);
+    CU(launch_digest(dptr, n, acc, ctx->sm_count, ctx->stream));
+    CU(cudaMemcpyAsync(out, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return KMC_OK;
 }
 

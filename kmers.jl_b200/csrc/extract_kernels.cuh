@@ -77,8 +77,8 @@ KMC_DEV uint32_t valid_slots(const uint32_t *__restrict__ vstart, int64_t sym0, 
     return (bits & ((1u << (jhi - jlo)) - 1u)) << jlo;
 }
 
-// G windows per thread for N limbs: G*N*8 must be a multiple of 32 bytes.
-template <int N> struct GroupOf { static constexpr int G = (N == 1) ? 4 : (N == 2) ? 2 : (N == 3) ? 4 : 1; };
+// G windows per thread for N limbs: G*N*8 must be a multiple of 32 bytes (kmer_core.cuh: group_of).
+template <int N> struct GroupOf { static constexpr int G = group_of(N); };
 
 // ---------------------------------------------------------------------------------------------
 // TileCursor: maps the work items of one tile (kTileItems consecutive group slots) to
@@ -319,80 +319,52 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             const bool full = (jlo == 0) && (jhi == G);
             const bool tuple_rv = (MODE == MODE_FWRV) && p.aos;
             const bool tuple_ix = (p.out_index != nullptr) && p.aos;
-
-            if (full && p.vec_ok) {
-                if (tuple_rv) {
-                    uint64_t buf[2 * G * N];
+            const bool fast = full && p.vec_ok;
+            // Every stream is staged as one run of words per item and written with the widest stores
+            // its alignment allows: whole 256-bit stores for a full group, and for a partial group
+            // (read / run boundary) 256- and 128-bit stores over the aligned parts of [jlo, jhi).
+            if (tuple_rv) {
+                uint64_t buf[2 * G * N];
 #pragma unroll
-                    for (int j = 0; j < G; ++j)
+                for (int j = 0; j < G; ++j)
 #pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            buf[j * 2 * N + i] = fw[j][i];
-                            buf[j * 2 * N + N + i] = rv[j][i];
-                        }
-                    store_run<2 * G * N>(p.out_a + fbase * (2 * N), buf, true);
-                } else if (tuple_ix) {
-                    // Tuple{Kmer,Int} = {u64[N]; i64} elements
-                    uint64_t buf[G * (N + 1)];
-#pragma unroll
-                    for (int j = 0; j < G; ++j) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) buf[j * (N + 1) + i] = a[j][i];
-                        buf[j * (N + 1) + N] = static_cast<uint64_t>(ibase + j);
+                    for (int i = 0; i < N; ++i) {
+                        buf[j * 2 * N + i] = fw[j][i];
+                        buf[j * 2 * N + N + i] = rv[j][i];
                     }
-                    store_run<G * (N + 1)>(p.out_a + fbase * (N + 1), buf, (G * (N + 1)) % 4 == 0);
-                } else {
-                    uint64_t buf[G * N];
-#pragma unroll
-                    for (int j = 0; j < G; ++j)
-#pragma unroll
-                        for (int i = 0; i < N; ++i) buf[j * N + i] = a[j][i];
-                    store_run<G * N>(p.out_a + fbase * N, buf, true);
-                    if (MODE == MODE_FWRV) {
-#pragma unroll
-                        for (int j = 0; j < G; ++j)
-#pragma unroll
-                            for (int i = 0; i < N; ++i) buf[j * N + i] = rv[j][i];
-                        store_run<G * N>(p.out_b + fbase * N, buf, true);
-                    }
-                    if (p.out_index) {
-                        uint64_t ib[G];
-#pragma unroll
-                        for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(ibase + j);
-                        store_run<G>(reinterpret_cast<uint64_t *>(p.out_index) + fbase, ib, G % 4 == 0);
-                    }
-                }
-                if (HASH) store_run<G>(p.out_hash + fbase, h, G % 4 == 0);
-            } else {
-                // partial group (read boundary) or unaligned output buffers: per-window stores
+                store_words<2 * G * N>(p.out_a + fbase * (2 * N), buf, jlo * 2 * N, jhi * 2 * N, fast, p.vec_ok);
+            } else if (tuple_ix) {
+                // Tuple{Kmer,Int} = {u64[N]; i64} elements
+                uint64_t buf[G * (N + 1)];
 #pragma unroll
                 for (int j = 0; j < G; ++j) {
-                    if (j < jlo || j >= jhi) continue;
-                    const uint64_t f = fbase + j;
-                    if (tuple_rv) {
 #pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            st_u64(p.out_a + f * (2 * N) + i, fw[j][i]);
-                            st_u64(p.out_a + f * (2 * N) + N + i, rv[j][i]);
-                        }
-                    } else if (tuple_ix) {
+                    for (int i = 0; i < N; ++i) buf[j * (N + 1) + i] = a[j][i];
+                    buf[j * (N + 1) + N] = static_cast<uint64_t>(ibase + j);
+                }
+                store_words<G * (N + 1)>(p.out_a + fbase * (N + 1), buf, jlo * (N + 1), jhi * (N + 1), fast, p.vec_ok);
+            } else {
+                uint64_t buf[G * N];
 #pragma unroll
-                        for (int i = 0; i < N; ++i) st_u64(p.out_a + f * (N + 1) + i, a[j][i]);
-                        st_u64(p.out_a + f * (N + 1) + N, static_cast<uint64_t>(ibase + j));
-                    } else {
+                for (int j = 0; j < G; ++j)
 #pragma unroll
-                        for (int i = 0; i < N; ++i) st_u64(p.out_a + f * N + i, a[j][i]);
-                        if (MODE == MODE_FWRV) {
+                    for (int i = 0; i < N; ++i) buf[j * N + i] = a[j][i];
+                store_words<G * N>(p.out_a + fbase * N, buf, jlo * N, jhi * N, fast, p.vec_ok);
+                if (MODE == MODE_FWRV) {
 #pragma unroll
-                            for (int i = 0; i < N; ++i) st_u64(p.out_b + f * N + i, rv[j][i]);
-                        }
-                        if (p.out_index)
-                            st_u64(reinterpret_cast<uint64_t *>(p.out_index) + f,
-                                   static_cast<uint64_t>(ibase + j));
-                    }
-                    if (HASH) st_u64(p.out_hash + f, h[j]);
+                    for (int j = 0; j < G; ++j)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) buf[j * N + i] = rv[j][i];
+                    store_words<G * N>(p.out_b + fbase * N, buf, jlo * N, jhi * N, fast, p.vec_ok);
+                }
+                if (p.out_index) {
+                    uint64_t ib[G];
+#pragma unroll
+                    for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(ibase + j);
+                    store_words<G>(reinterpret_cast<uint64_t *>(p.out_index) + fbase, ib, jlo, jhi, fast, p.vec_ok);
                 }
             }
+            if (HASH) store_words<G>(p.out_hash + fbase, h, jlo, jhi, fast, p.vec_ok);
         }
 
     next_item:

@@ -5,6 +5,7 @@
 // 4-bit source the number of k-mers of a chunk is only known after its count pass, so a chunk
 // runs in two phases (fourbit.h) and the download goes to a running host offset.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "fourbit.h"
@@ -52,6 +53,7 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
     result->err_seq = result->err_pos = 0;
     result->err_sym = 0;
     result->kernel_ms = 0.f;
+    memset(result->digest, 0, sizeof result->digest);
 
     const Geometry ge = geometry(k);
     const uint64_t N = static_cast<uint64_t>(ge.n_limbs);
@@ -59,6 +61,9 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
     const uint64_t spw = four ? 16 : 32; // symbols per source word
     const bool hash = (flags & KMC_HASH_FX) != 0;
     const bool aos = (flags & KMC_AOS) != 0;
+    const bool dev_out = (flags & KMC_OUT_DEVICE) != 0; // outputs stay in (caller-provided) device memory
+    if (dev_out && ho->seq_out_offset) return fail(ctx, KMC_E_UNSUPPORTED, "seq_out_offset is not available with KMC_OUT_DEVICE");
+    const bool want_digest = (flags & KMC_DIGEST) != 0;
     const bool want_index = (mode == KMC_UNAMBIG);
     const bool compacting = four && mode == KMC_UNAMBIG; // variable-length output
     // windows per work item of the layout the device planner will build (run marking uses 32)
@@ -72,7 +77,9 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
 
     // ---- chunk plan (host side; lengths are host arrays here) --------------------------------
     std::vector<Chunk> chunks;
-    const uint64_t target = 4ull << 20; // windows per chunk (64-128 MB of output at 16-32 B / window)
+    // windows per chunk: 64-128 MB of staged output at 16-32 B / window; with KMC_OUT_DEVICE nothing is
+    // staged, so larger chunks (fewer, larger H2D transfers) are free
+    const uint64_t target = dev_out ? (32ull << 20) : (4ull << 20);
     uint64_t total = 0;
     const bool single = (hs->n_seqs == 1);
     if (single) {
@@ -106,17 +113,20 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
             c.first = hs->first_symbol_offset;
             if (!ragged_len) {
                 uint64_t take = wpr_u ? std::max<uint64_t>(1, target / wpr_u) : n;
+                if (take > 4) take &= ~3ull; // chunk outputs start on a 32-byte boundary (vector stores, KMC_OUT_DEVICE)
                 take = std::min(take, n - r);
                 c.nseq = take;
                 c.nout = take * wpr_u;
                 r += take;
             } else {
                 uint64_t acc = 0, items = 0;
-                while (r < n && (acc < target || c.nseq == 0)) {
+                uint64_t extra = 0;
+                while (r < n && (acc < target || c.nseq == 0 || ((acc & 3) && extra < 64))) {
                     uint64_t len = hs->seq_len[r];
                     acc += len >= K ? len - K + 1 : 0;
                     ++r;
                     ++c.nseq;
+                    if (acc >= target) ++extra; // a few more reads so that the next chunk starts 32-byte aligned
                 }
                 // group slots are relative to the chunk's own flat origin (0); the host only needs
                 // their total so that the device planner does not have to be read back
@@ -178,10 +188,10 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
     const bool want_seq_out = compacting && ho->seq_out_offset && !single;
     const uint64_t b_words = round_up((max_words + 4) * 8, 256);
     const uint64_t b_meta = round_up((max_seq + 1) * 8, 256);
-    const uint64_t b_a = round_up(max_out * a_elems * 8, 256);
-    const uint64_t b_b = (two && !aos) ? round_up(max_out * N * 8, 256) : 0;
-    const uint64_t b_h = hash ? round_up(max_out * 8, 256) : 0;
-    const uint64_t b_i = (want_index && !aos) ? round_up(max_out * 8, 256) : 0;
+    const uint64_t b_a = dev_out ? 0 : round_up(max_out * a_elems * 8, 256);
+    const uint64_t b_b = (two && !aos && !dev_out) ? round_up(max_out * N * 8, 256) : 0;
+    const uint64_t b_h = (hash && !dev_out) ? round_up(max_out * 8, 256) : 0;
+    const uint64_t b_i = (want_index && !aos && !dev_out) ? round_up(max_out * 8, 256) : 0;
     const uint64_t b_so = want_seq_out ? b_meta : 0;
     const uint64_t per_slot = b_words + 2 * b_meta + b_so + b_a + b_b + b_h + b_i;
     const int n_slots = chunks.size() >= 3 ? 3 : static_cast<int>(chunks.size());
@@ -198,6 +208,13 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
     if (st) return st;
     st = ensure_host_small(ctx);
     if (st) return st;
+    if (want_digest) {
+        // the three slot streams accumulate into it with atomics; ordered after this memset by an event
+        CU(cudaMemsetAsync(ctx->dev_small, 0, 32, ctx->pipe_streams[0]));
+        if (!ctx->ev_k0) return KMC_E_BAD_ARG;
+        CU(cudaEventRecord(ctx->ev_k0, ctx->pipe_streams[0]));
+        for (int i = 1; i < 3; ++i) CU(cudaStreamWaitEvent(ctx->pipe_streams[i], ctx->ev_k0, 0));
+    }
 
     Slot slots[3];
     for (int i = 0; i < n_slots; ++i) {
@@ -218,7 +235,7 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         sl.off = reinterpret_cast<uint64_t *>(base); base += b_meta;
         sl.len = reinterpret_cast<uint64_t *>(base); base += b_meta;
         sl.seq_out = b_so ? reinterpret_cast<uint64_t *>(base) : nullptr; base += b_so;
-        sl.a = reinterpret_cast<uint64_t *>(base); base += b_a;
+        sl.a = b_a ? reinterpret_cast<uint64_t *>(base) : nullptr; base += b_a;
         sl.b = b_b ? reinterpret_cast<uint64_t *>(base) : nullptr; base += b_b;
         sl.hash = b_h ? reinterpret_cast<uint64_t *>(base) : nullptr; base += b_h;
         sl.index = b_i ? reinterpret_cast<int64_t *>(base) : nullptr;
@@ -233,12 +250,38 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
     std::vector<Fixup> fixups;
 
     auto download = [&](Slot &sl, uint64_t host_elem0, uint64_t n) -> int32_t {
-        if (!n) return KMC_OK;
+        if (!n || dev_out) return KMC_OK;
         cudaStream_t sm = sl.stream;
         CU(cudaMemcpyAsync(ho->a + host_elem0 * a_elems, sl.a, n * a_elems * 8, cudaMemcpyDeviceToHost, sm));
         if (sl.b) CU(cudaMemcpyAsync(ho->b + host_elem0 * N, sl.b, n * N * 8, cudaMemcpyDeviceToHost, sm));
         if (sl.hash) CU(cudaMemcpyAsync(ho->hash + host_elem0, sl.hash, n * 8, cudaMemcpyDeviceToHost, sm));
         if (sl.index) CU(cudaMemcpyAsync(ho->index + host_elem0, sl.index, n * 8, cudaMemcpyDeviceToHost, sm));
+        return KMC_OK;
+    };
+
+    // where a chunk's k-mers go: the slot's staging buffers, or (KMC_OUT_DEVICE) the caller's device
+    // buffers at the chunk's element offset
+    auto bind_chunk_out = [&](Chunk &c, Slot &sl, uint64_t elem0, uint64_t cap) {
+        kmc_out &d = c.dout;
+        if (dev_out) {
+            d.a = ho->a + elem0 * a_elems;
+            d.b = (two && !aos) ? ho->b + elem0 * N : nullptr;
+            d.hash = hash ? ho->hash + elem0 : nullptr;
+            d.index = (want_index && !aos) ? ho->index + elem0 : nullptr;
+        } else {
+            d.a = sl.a;
+            d.b = sl.b;
+            d.hash = sl.hash;
+            d.index = sl.index;
+        }
+        d.capacity = cap;
+    };
+
+    // KMC_DIGEST: fingerprint the chunk's k-mers and hashes right behind the kernel that wrote them
+    auto digest_chunk = [&](Chunk &c, Slot &sl, uint64_t n) -> int32_t {
+        if (!want_digest || !n) return KMC_OK;
+        CU(launch_digest(c.dout.a, n * a_elems, ctx->dev_small, ctx->sm_count, sl.stream, false));
+        if (hash) CU(launch_digest(c.dout.hash, n, ctx->dev_small + 2, ctx->sm_count, sl.stream, false));
         return KMC_OK;
     };
 
@@ -248,6 +291,7 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         Slot &sl = slots[ci % n_slots];
         CU(cudaEventSynchronize(sl.ev_a));
         kmc_result r{};
+        if (compacting) bind_chunk_out(c, sl, emitted, dev_out ? ho->capacity - emitted : c.nout);
         Scratch runs;
         if (compacting) { // the tail of the slot's scratch window
             runs.base = sl.scratch.base + (scratch_per_slot - run_bytes);
@@ -266,6 +310,8 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         if (compacting) {
             if (emitted + r.n_written > ho->capacity)
                 return fail(ctx, KMC_E_OUT_TOO_SMALL, "output capacity smaller than the number of k-mers");
+            rc = digest_chunk(c, sl, r.n_written);
+            if (rc) return rc;
             rc = download(sl, emitted, r.n_written);
             if (rc) return rc;
             if (want_seq_out) {
@@ -311,12 +357,8 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         }
         kmc_out &dout = c.dout;
         dout = kmc_out{};
-        dout.a = sl.a;
-        dout.b = sl.b;
-        dout.hash = sl.hash;
-        dout.index = sl.index;
+        bind_chunk_out(c, sl, c.out0, c.nout);
         dout.seq_out_offset = want_seq_out ? sl.seq_out : nullptr;
-        dout.capacity = c.nout;
         dout.index_base = c.index_base + ho->index_base;
         Scratch scratch = sl.scratch;
         scratch.bytes -= run_bytes;
@@ -325,12 +367,16 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
             kmc_result r{};
             st = extract_device(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch);
             if (st) return st;
+            st = digest_chunk(c, sl, c.nout);
+            if (st) return st;
             st = download(sl, c.out0, c.nout);
             if (st) return st;
         } else {
             st = fourbit_phase_a(ctx, &ds, k, mode, flags, &dout, sm, known, bias, scratch, sl.host_small, &c.fb);
             if (st) return st;
             if (!compacting) {
+                st = digest_chunk(c, sl, c.nout);
+                if (st) return st;
                 st = download(sl, c.out0, c.nout);
                 if (st) return st;
             }
@@ -346,6 +392,7 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         if (st) return st;
     }
     for (int i = 0; i < n_slots; ++i) CU(cudaStreamSynchronize(slots[i].stream));
+    if (want_digest) CU(cudaMemcpy(result->digest, ctx->dev_small, 32, cudaMemcpyDeviceToHost));
     if (compacting) {
         result->n_written = emitted;
         if (ho->seq_out_offset) {

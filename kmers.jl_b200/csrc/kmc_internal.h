@@ -26,6 +26,7 @@ struct kmc_ctx {
     // small pinned host block for device->host read-backs of counts and error records:
     // 16 u64 per pipeline slot, slot 3 = the context's own stream
     uint64_t *host_small = nullptr;
+    uint64_t *dev_small = nullptr; // 64 bytes of device memory: KMC_DIGEST accumulators
     std::string last_error;
 };
 
@@ -52,6 +53,8 @@ cudaError_t tile_first_reads(const uint64_t *item_off, uint64_t n_seqs, uint64_t
 // misc_kernels.cu -----------------------------------------------------------------------------
 cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,
                            cudaStream_t stream);
+// acc[0] ^= xor of the words, acc[1] += their sum (zero = clear acc first)
+cudaError_t launch_digest(const uint64_t *p, uint64_t n, uint64_t *acc, int sm_count, cudaStream_t stream, bool zero = true);
 cudaError_t launch_store_probe(void *dptr, uint64_t bytes, int sm_count, cudaStream_t stream);
 
 } // namespace kmc

@@ -28,6 +28,17 @@ namespace kmc {
 
 constexpr uint64_t FX_CONSTANT = 0x517cc1b727220a95ull; // src/kmer.jl:218
 
+// Windows per work item (= per thread) for k-mers of n limbs.  G*n*8 bytes is a multiple of 32, so
+// a full group goes out as whole 256-bit stores; 64-96 bytes per thread and stream amortise the
+// per-item address arithmetic over more windows (profiles/: G = 4 -> 8 for one limb).
+#ifndef KMC_GROUP_1
+#define KMC_GROUP_1 8
+#define KMC_GROUP_2 4
+#define KMC_GROUP_3 4
+#define KMC_GROUP_4 2
+#endif
+constexpr int group_of(int n) { return n == 1 ? KMC_GROUP_1 : n == 2 ? KMC_GROUP_2 : n == 3 ? KMC_GROUP_3 : KMC_GROUP_4; }
+
 // reversebits(x, BitsPerSymbol{2}) on a 32-bit word: reverse the order of the 16 two-bit groups.
 KMC_DEV uint32_t rev2_32(uint32_t x)
 {
@@ -107,6 +118,36 @@ KMC_DEV void store_run(uint64_t *p, const uint64_t (&v)[CNT], bool aligned32)
     } else {
 #pragma unroll
         for (int i = 0; i < CNT; ++i) st_u64(p + i, v[i]);
+    }
+}
+
+// CNT words staged for the address p; only the words [lo, hi) are to be written.
+//   fast     all of them, and p is 32-byte aligned (whole 256-bit stores when CNT % 4 == 0)
+//   base_ok  the stream's base pointer is 32-byte aligned, so p is aligned to CNT*8 bytes (mod 32):
+//            aligned quads / pairs that lie inside [lo, hi) still go out as 256- / 128-bit stores
+template <int CNT>
+KMC_DEV void store_words(uint64_t *p, const uint64_t (&v)[CNT], int lo, int hi, bool fast, bool base_ok)
+{
+    if (fast) {
+        store_run<CNT>(p, v, CNT % 4 == 0);
+        return;
+    }
+    const bool quad_ok = base_ok && (CNT % 4 == 0), pair_ok = base_ok && (CNT % 2 == 0);
+#pragma unroll
+    for (int i = 0; i < CNT; i += 4) {
+        if (i + 4 <= CNT && quad_ok && lo <= i && hi >= i + 4) {
+            st_v4(p + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            continue;
+        }
+#pragma unroll
+        for (int j = i; j < i + 4 && j < CNT; j += 2) {
+            if (j + 2 <= CNT && pair_ok && lo <= j && hi >= j + 2) {
+                st_v2(p + j, v[j], v[j + 1]);
+            } else {
+                if (j >= lo && j < hi) st_u64(p + j, v[j]);
+                if (j + 1 < CNT && j + 1 >= lo && j + 1 < hi) st_u64(p + j + 1, v[j + 1]);
+            }
+        }
     }
 }
 

@@ -41,6 +41,64 @@ cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint6
     return cudaGetLastError();
 }
 
+// XOR / wrapping-sum fingerprint of a u64 stream (kmc_digest): 128-bit loads, warp shuffle +
+// shared-memory reduction, one pair of atomics per block.
+__global__ void __launch_bounds__(256) digest_kernel(const uint64_t *__restrict__ p, uint64_t n,
+                                                     unsigned long long *__restrict__ acc)
+{
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    uint64_t x = 0, s = 0;
+    const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) / 8 % 2; // words before 16-byte alignment
+    const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tid < head && tid < n) {
+        x ^= p[tid];
+        s += p[tid];
+    }
+    const uint64_t n2 = n > head ? (n - head) / 2 : 0;
+    const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(p + head);
+    for (uint64_t i = tid; i < n2; i += stride) {
+        const ulonglong2 v = __ldg(p2 + i);
+        x ^= v.x ^ v.y;
+        s += v.x + v.y;
+    }
+    const uint64_t tail = head + 2 * n2;
+    if (tid == 0 && tail < n) {
+        x ^= p[tail];
+        s += p[tail];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, d);
+        s += __shfl_xor_sync(0xffffffffu, s, d);
+    }
+    // one pair of atomics per BLOCK: same-address atomics serialise in L2
+    __shared__ uint64_t sx[8], ss[8];
+    if ((threadIdx.x & 31) == 0) {
+        sx[threadIdx.x >> 5] = x;
+        ss[threadIdx.x >> 5] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+            x ^= sx[w];
+            s += ss[w];
+        }
+        atomicXor(acc, static_cast<unsigned long long>(x));
+        atomicAdd(acc + 1, static_cast<unsigned long long>(s));
+    }
+}
+
+cudaError_t launch_digest(const uint64_t *p, uint64_t n, uint64_t *acc, int sm_count, cudaStream_t stream, bool zero)
+{
+    cudaError_t e = zero ? cudaMemsetAsync(acc, 0, 16, stream) : cudaSuccess;
+    if (e != cudaSuccess || n == 0) return e;
+    const uint64_t want = (n / 2 + 255) / 256 + 1;
+    const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 8 ? want : static_cast<uint64_t>(sm_count) * 8);
+    digest_kernel<<<grid, 256, 0, stream>>>(p, n, reinterpret_cast<unsigned long long *>(acc));
+    return cudaGetLastError();
+}
+
 // Every thread writes 32 bytes per step with one 256-bit store; nothing is read.  Same launch shape
 // as the extraction kernels (one tile of 8 x 256 stores per block, hardware-scheduled), so it is the
 // write ceiling for exactly that store pattern.

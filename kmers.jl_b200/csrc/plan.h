@@ -29,7 +29,7 @@ inline Geometry geometry(int k)
 {
     Geometry ge;
     ge.n_limbs = (2 * k + 63) / 64;
-    ge.g = ge.n_limbs == 1 ? 4 : ge.n_limbs == 2 ? 2 : ge.n_limbs == 3 ? 4 : 1;
+    ge.g = group_of(ge.n_limbs);
     ge.nx = (2 * k + 2 * ge.g - 2 + 31) / 32;
     ge.s0 = static_cast<uint32_t>(32 * ge.nx - 2 * k - 2 * (ge.g - 1));
     int used = 2 * k - 64 * (ge.n_limbs - 1); // bits used in the head limb, 2..64

@@ -14,4 +14,4 @@ from .api import (  # noqa: E402
     UnambiguousDNAMers, UnambiguousKmers, UnambiguousRNAMers, bucket_count, default_context, extract, fx_hash,
     n_limbs)
 from ._abi import (KMC_AOS, KMC_CANON, KMC_FW, KMC_FWRV, KMC_HASH_FX, KMC_MAX_K, KMC_NO_SYNC,  # noqa: E402
-                   KMC_UNAMBIG)
+                   KMC_OUT_DEVICE, KMC_UNAMBIG)

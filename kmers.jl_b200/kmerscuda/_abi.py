@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libkmerscuda.so")
+# the in-tree build; KMERSCUDA_LIB selects another build of the same library (A/B measurements)
+LIB_PATH = os.environ.get("KMERSCUDA_LIB") or os.path.join(os.path.dirname(_HERE), "libkmerscuda.so")
 
 KMC_OK = 0
 KMC_E_BAD_K = 1
@@ -21,7 +22,7 @@ KMC_E_NO_DEVICE = 5
 KMC_E_UNSUPPORTED = 6
 
 KMC_FW, KMC_FWRV, KMC_CANON, KMC_UNAMBIG = 0, 1, 2, 3
-KMC_HASH_FX, KMC_AOS, KMC_NO_SYNC = 0x1, 0x2, 0x4
+KMC_HASH_FX, KMC_AOS, KMC_NO_SYNC, KMC_OUT_DEVICE, KMC_DIGEST = 0x1, 0x2, 0x4, 0x8, 0x10
 KMC_MAX_K = 128
 
 
@@ -58,6 +59,7 @@ class kmc_result(C.Structure):
         ("err_pos", C.c_uint64),
         ("err_sym", C.c_uint32),
         ("kernel_ms", C.c_float),
+        ("digest", C.c_uint64 * 4),
     ]
 
 
@@ -89,6 +91,7 @@ SIGNATURES = {
     "kmc_fx_hash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]),
     "kmc_bucket_count": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p,
                                      C.POINTER(kmc_result)]),
+    "kmc_digest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "kmc_timer_begin": (C.c_int32, [C.c_void_p]),
     "kmc_timer_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "kmc_store_probe": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),

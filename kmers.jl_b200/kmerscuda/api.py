@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import (KMC_AOS, KMC_CANON, KMC_E_AMBIGUOUS, KMC_E_BAD_K, KMC_FW, KMC_FWRV, KMC_HASH_FX, KMC_MAX_K,
-                   KMC_NO_SYNC, KMC_OK, KMC_UNAMBIG, kmc_out, kmc_result, kmc_seqs)
+                   KMC_NO_SYNC, KMC_OK, KMC_OUT_DEVICE, KMC_UNAMBIG, kmc_out, kmc_result, kmc_seqs)
 
 # ----------------------------------------------------------------------------------------------
 # alphabets (only what the path needs: the 2- and 4-bit nucleic acid alphabets)
@@ -254,6 +254,12 @@ class Context:
         _PINNED[arr.ctypes.data] = (self, p.value)
         return arr
 
+    def digest(self, dptr: int, n_words: int):
+        """(xor, wrapping sum) of n_words u64 in device memory (kmc_digest)."""
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.kmc_digest(self.handle, dptr, n_words, out))
+        return int(out[0]), int(out[1])
+
     def timer_begin(self):
         self._check(self.lib.kmc_timer_begin(self.handle))
 
@@ -326,12 +332,14 @@ def _upper_bound(ctx: Context, desc: kmc_seqs, rs: ReadSet, K: int, mode: int) -
 
 def extract(mode: int, rs, K: int, *, A: Alphabet = DNAAlphabet2, hash: bool = False, aos: bool = False,
             want_seq_offsets: bool = False, ctx: Optional[Context] = None, host_path: bool = False,
-            index_base: int = 0) -> Extracted:
+            index_base: int = 0, device_out: bool = False) -> Extracted:
     """Batched `collect` of one iterator type over a ReadSet / DeviceReadSet.
 
     host_path=False: descriptors are uploaded (or already resident), kmc_extract runs on device
     buffers and the outputs are downloaded.  host_path=True: one kmc_extract_host call on host
-    buffers (the pipelined entry point a Julia `collect` replacement uses).
+    buffers (the pipelined entry point a Julia `collect` replacement uses); with device_out=True the
+    sequences come from the host but the outputs are written to device buffers (KMC_OUT_DEVICE) and
+    only downloaded afterwards.
     """
     _check_K(K)
     if K > KMC_MAX_K:
@@ -352,7 +360,18 @@ def extract(mode: int, rs, K: int, *, A: Alphabet = DNAAlphabet2, hash: bool = F
     flags = (KMC_HASH_FX if hash else 0) | (KMC_AOS if aos else 0)
     res = kmc_result()
 
-    if host_path:
+    if host_path and device_out:
+        da = ctx.alloc(max(cap, 1) * a_elems * 8)
+        db = ctx.alloc(max(cap, 1) * N * 8) if (two and not aos) else None
+        dh = ctx.alloc(max(cap, 1) * 8) if hash else None
+        di = ctx.alloc(max(cap, 1) * 8) if (want_index and not aos) else None
+        dso = None
+        out = kmc_out(da.ptr, db.ptr if db else None, dh.ptr if dh else None, di.ptr if di else None, None, cap,
+                      index_base)
+        desc = _host_desc(hrs)
+        st = lib.kmc_extract_host(ctx.handle, C.byref(desc), K, mode, flags | KMC_OUT_DEVICE, C.byref(out), C.byref(res))
+        host_path = False  # results are on the device: take the download branch below
+    elif host_path:
         a = np.zeros(max(cap, 1) * a_elems, dtype=np.uint64)
         b = np.zeros(max(cap, 1) * N, dtype=np.uint64) if (two and not aos) else None
         h = np.zeros(max(cap, 1), dtype=np.uint64) if hash else None

@@ -287,6 +287,52 @@ def test_host_path_ragged_reads_chunked(kc):
     assert np.array_equal(e2.kmers, a) and np.array_equal(e2.hash, h)
 
 
+def test_host_sequences_device_outputs_and_digest(kc, ctx):
+    """KMC_OUT_DEVICE: sequences from the host, streams left in device memory; kmc_digest is the
+    fingerprint a caller reads back instead of the streams."""
+    k, length, stride, n_reads = 31, 150, 5, 90_000
+    words = kt.splitmix64(np.arange(n_reads * stride, dtype=np.uint64) + np.uint64(99))
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    a, _, h, _ = ko.batch_iterate(words, n_reads, k, ko.CANON, uniform_len=length, uniform_stride=stride, want_hash=True)
+    e = kc.extract(MODES["canon"], rs, k, hash=True, host_path=True, device_out=True)
+    assert np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+    # ragged + single long sequence + 4-bit unambiguous through the same flag
+    rng = np.random.default_rng(4)
+    lens = rng.integers(0, 400, size=60_000).tolist()
+    seqs, w2, off, ln = make_ragged(rng, [int(x) for x in lens])
+    rs2 = kc.ReadSet(2, w2, len(lens), seq_word_offset=off, seq_len=ln)
+    a2, b2, h2, _ = ko.batch_iterate(w2, len(lens), k, ko.FWRV, word_off=off, seq_len=ln, want_hash=True)
+    e = kc.extract(MODES["fwrv"], rs2, k, hash=True, host_path=True, device_out=True)
+    assert np.array_equal(e.kmers, a2) and np.array_equal(e.rv, b2) and np.array_equal(e.hash, h2)
+    n = 9_000_011
+    codes = np.where(kt.splitmix64(np.arange(n, dtype=np.uint64)) % np.uint64(100) == 0, np.uint64(15),
+                     np.uint64(1) << (kt.splitmix64(np.arange(n, dtype=np.uint64) + np.uint64(5)) & np.uint64(3)))
+    w4 = kt.pack_codes(codes, 4)
+    km, pos = ko.unambiguous(w4, n, k, src_bits=4)
+    e = kc.extract(MODES["unambig"], kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet4, w4, n)), k, hash=True,
+                   host_path=True, device_out=True)
+    assert np.array_equal(e.kmers, km) and np.array_equal(e.index, pos) and np.array_equal(e.hash, ko.fx_hash(km))
+    # KMC_DIGEST fused into the pipeline == fingerprint of what the call wrote
+    from kmerscuda import _abi
+    cap = a.shape[0]
+    da, dh = ctx.alloc(cap * 8), ctx.alloc(cap * 8)
+    desc = _abi.kmc_seqs(words.ctypes.data, words.size, n_reads, None, None, length, stride, 2, 0)
+    out = _abi.kmc_out(da.ptr, None, dh.ptr, None, None, cap, 0)
+    res = _abi.kmc_result()
+    ctx._check(ctx.lib.kmc_extract_host(ctx.handle, C.byref(desc), k, MODES["canon"],
+                                        _abi.KMC_HASH_FX | _abi.KMC_OUT_DEVICE | _abi.KMC_DIGEST, C.byref(out), C.byref(res)))
+    assert list(res.digest) == [int(np.bitwise_xor.reduce(a.reshape(-1))), int(a.sum(dtype=np.uint64)),
+                                int(np.bitwise_xor.reduce(h)), int(h.sum(dtype=np.uint64))]
+    assert np.array_equal(da.download(np.uint64, cap), a[:, 0])
+    # digest == numpy xor / wrapping sum, at odd offsets and lengths
+    d = ctx.to_device(a)
+    for o, m in ((0, a.size), (1, a.size - 1), (3, 1001), (0, 0), (2, 1)):
+        x, s = ctx.digest(d.ptr + 8 * o, m)
+        sl = a.reshape(-1)[o:o + m]
+        assert x == int(np.bitwise_xor.reduce(sl)) if m else x == 0
+        assert s == int(sl.sum(dtype=np.uint64)) if m else s == 0
+
+
 # ---------------------------------------------------------------------- bucket count table
 @pytest.mark.parametrize("k,bits", [(31, 20), (63, 12), (15, 28)])
 def test_bucket_count(kc, k, bits):
