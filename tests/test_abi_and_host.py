@@ -38,7 +38,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_abi.kmc_seqs) == 64
     assert _abi.kmc_seqs.src_bits.offset == 56 and _abi.kmc_seqs.first_symbol_offset.offset == 60
     assert C.sizeof(_abi.kmc_out) == 56
-    assert C.sizeof(_abi.kmc_result) == 32
+    assert C.sizeof(_abi.kmc_result) == 64 and _abi.kmc_result.digest.offset == 32
     assert _abi.kmc_result.err_sym.offset == 24 and _abi.kmc_result.kernel_ms.offset == 28
 
 
