@@ -382,7 +382,7 @@ def run_ours(args, rank, local_rank, world):
                        "parallelism": f"reads sharded over {world} GPU(s), no data-path collective",
                        "l2": "no explicit flush: each step streams 0.4 GB in + 19.2 GB out, far larger than the 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "extract_kernel<N=1,NX=3,CANON,HASH,uniform>",
+                         "traffic": traffic, "kernel": "extract_kernel<N=1,NX=3,CANON,HASH,uniform,G=8>",
                          "kernel_ms": k_ms, "bytes_per_kmer": BYTES_PER_KMER, "peak_source": peak_src},
             "gpu_launches": args.steps,
             "clocks": clocks,
