@@ -40,8 +40,10 @@ extern "C" {
 #define KMC_OK 0
 #define KMC_E_BAD_K 1         /* K < 1 ("K must be at least 1", FwKmers.jl:32-33) or K > KMC_MAX_K */
 #define KMC_E_BAD_ARG 2       /* null / inconsistent descriptor */
-#define KMC_E_AMBIGUOUS 3     /* strict 4->2 recoding hit an uncertain symbol: the caller throws
-                                 BioSequences.EncodeError as construction.jl:108-110 does */
+#define KMC_E_AMBIGUOUS 3     /* a symbol cannot be encoded in the 2-bit alphabet: strict 4->2 recoding hit an
+                                 uncertain symbol (construction.jl:108-110), or an ASCII source holds a byte
+                                 that is not a valid letter (FwKmers.jl:124-126, UnambiguousKmers.jl:123-124).
+                                 The caller throws BioSequences.EncodeError; result->err_* say where / what */
 #define KMC_E_OUT_TOO_SMALL 4 /* kmc_out.capacity < number of elements to write */
 #define KMC_E_NO_DEVICE 5
 #define KMC_E_UNSUPPORTED 6
@@ -64,6 +66,9 @@ extern "C" {
 #define KMC_OUT_DEVICE 0x8u /* kmc_extract_host only: the kmc_out buffers are DEVICE memory (the
                             sequences still come from the host).  The streams stay in HBM for a
                             device consumer; out.seq_out_offset must be NULL. */
+#define KMC_RNA 0x20u    /* the k-mer alphabet is RNAAlphabet{2} (default DNAAlphabet{2}).  The limbs are
+                            bit-identical; it only matters for strict iteration over ASCII sources,
+                            where U (not T) is the fourth valid letter. */
 #define KMC_DIGEST 0x10u /* kmc_extract_host only: also fingerprint what was written -- xor and wrapping
                             sum of the out.a words and of the out.hash words -> result->digest[4].
                             Computed chunk by chunk inside the pipeline, while the chunk is L2-hot. */
@@ -72,7 +77,10 @@ typedef struct kmc_ctx kmc_ctx;
 
 /* A set of sequences resident in device memory.  n_seqs == 1 is a single LongSequence.
  * Ragged sets give word-aligned CSR offsets; uniform sets (every read the same length,
- * fixed word stride) leave seq_word_offset / seq_len NULL. */
+ * fixed word stride) leave seq_word_offset / seq_len NULL.
+ * src_bits == 8 describes ASCII sources (String / codeunits / Vector{UInt8}: the AsciiEncode scheme,
+ * construction.jl:95-96): `words` then points at BYTES (no alignment required) and every "word"
+ * quantity below -- n_words, seq_word_offset, uniform_stride_words -- counts bytes. */
 typedef struct kmc_seqs {
     const uint64_t *words;           /* device: concatenated LongSequence.data */
     uint64_t n_words;                /* number of u64 words addressable at `words` */
@@ -81,7 +89,8 @@ typedef struct kmc_seqs {
     const uint64_t *seq_len;         /* device u64[n_seqs] symbols per sequence, or NULL */
     uint64_t uniform_len;            /* used when seq_len == NULL */
     uint64_t uniform_stride_words;   /* used when seq_word_offset == NULL */
-    uint32_t src_bits;               /* 2 (Copyable, construction.jl:75-80) or 4 (FourToTwo, :85-86) */
+    uint32_t src_bits;               /* 2 (Copyable, construction.jl:75-80), 4 (FourToTwo, :85-86) or
+                                        8 (ASCII bytes, AsciiEncode, :95-96) */
     uint32_t first_symbol_offset;    /* symbols skipped at the start of every sequence (LongSubSeq view) */
 } kmc_seqs;
 
@@ -100,7 +109,7 @@ typedef struct kmc_result {
     uint64_t n_written; /* elements produced (== length(iterator) summed over sequences) */
     uint64_t err_seq;   /* KMC_E_AMBIGUOUS: 0-based sequence, */
     uint64_t err_pos;   /*   1-based symbol position within it, */
-    uint32_t err_sym;   /*   and the offending 4-bit encoding (reinterpret(DNA, x)) */
+    uint32_t err_sym;   /*   and the offending 4-bit encoding (reinterpret(DNA, x)) or ASCII byte */
     float kernel_ms;    /* device time of the launches of this call (cudaEvents), 0 with KMC_NO_SYNC */
     uint64_t digest[4]; /* KMC_DIGEST: xor(a), sum(a), xor(hash), sum(hash) */
 } kmc_result;

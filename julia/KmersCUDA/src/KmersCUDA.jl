@@ -134,7 +134,8 @@ device writes the Julia element layout directly into the vector (KMC_AOS).
 function collect(it::Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, K}, UnambiguousKmers{A, K}};
         ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
     seq = source(it)
-    seq isa LongSequence || throw(ArgumentError("KmersCUDA accelerates LongSequence sources"))
+    seq isa AsciiSource && return collect_ascii(it, seq; ctx)
+    seq isa LongSequence || throw(ArgumentError("KmersCUDA accelerates LongSequence and ASCII sources"))
     T = derive_type(Kmer{A, K})
     mode = mode_of(it)
     len = length(seq)
@@ -154,6 +155,36 @@ function collect(it::Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, 
         st = ccall((:kmc_extract_host, LIB[]), Int32,
             (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
             ctx.handle, s, K, mode, KMC_AOS, o, pointer_from_objref(res))
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    resize!(out, res.n_written)
+    return out
+end
+
+# ASCII sources (the AsciiEncode scheme, src/construction.jl:95-96): String, SubString{String},
+# codeunits and byte vectors go to the device as they are (src_bits = 8); nothing is packed on the host.
+const AsciiSource = Union{String, SubString{String}, Base.CodeUnits{UInt8, String}, Vector{UInt8}}
+ascii_bytes(s::Union{String, SubString{String}}) = codeunits(s)
+ascii_bytes(s) = s
+
+function collect_ascii(it::AnyIter{A, K}, src::AsciiSource; ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
+    T = derive_type(Kmer{A, K})
+    mode = mode_of(it)
+    bytes = ascii_bytes(src)
+    len = length(bytes)
+    ET = mode == KMC_FWRV ? Tuple{T, T} : mode == KMC_UNAMBIG ? Tuple{T, Int} : T
+    out = Vector{ET}(undef, max(0, len - K + 1))     # upper bound; UnambiguousKmers may return fewer
+    res = KmcResult()
+    flags = KMC_AOS | (A <: RNAAlphabet ? UInt32(0x20) : UInt32(0))   # KMC_RNA: U, not T, is the fourth letter
+    GC.@preserve src out begin
+        s = Ref(KmcSeqs(Ptr{UInt64}(pointer(bytes)), len, 1, C_NULL, C_NULL, len, max(len, 1), UInt32(8), 0))
+        o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, C_NULL, C_NULL, C_NULL, length(out), 0))
+        st = ccall((:kmc_extract_host, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
+            ctx.handle, s, K, mode, flags, o, pointer_from_objref(res))
+        if st == KMC_E_AMBIGUOUS   # FwKmers.jl:124-126 / UnambiguousKmers.jl:123-124
+            throw(BioSequences.EncodeError(A(), repr(UInt8(res.err_sym))))
+        end
         st == KMC_OK || throw_status(ctx, st, res, A)
     end
     resize!(out, res.n_written)

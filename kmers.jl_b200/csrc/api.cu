@@ -66,7 +66,8 @@ int32_t check_common(kmc_ctx *ctx, const kmc_seqs *s, int32_t k)
     if (!s) return fail(ctx, KMC_E_BAD_ARG, "kmc_seqs is NULL");
     if (k < 1) return fail(ctx, KMC_E_BAD_K, "K must be at least 1");
     if (k > KMC_MAX_K) return fail(ctx, KMC_E_BAD_K, "K exceeds KMC_MAX_K (128)");
-    if (s->src_bits != 2 && s->src_bits != 4) return fail(ctx, KMC_E_BAD_ARG, "src_bits must be 2 or 4");
+    if (s->src_bits != 2 && s->src_bits != 4 && s->src_bits != 8)
+        return fail(ctx, KMC_E_BAD_ARG, "src_bits must be 2, 4 (LongSequence words) or 8 (ASCII bytes)");
     if (s->n_seqs > 0 && s->words == nullptr && s->n_words > 0) return fail(ctx, KMC_E_BAD_ARG, "words is NULL");
     return KMC_OK;
 }
@@ -177,7 +178,7 @@ int32_t bind_outputs(kmc_ctx *ctx, const kmc_out *out, int mode, uint32_t flags,
 
 uint64_t extract_scratch_bytes(const kmc_seqs *s, int k, int mode)
 {
-    if (s->src_bits == 4) return fourbit_scratch_bytes(s, k, mode);
+    if (s->src_bits != 2) return fourbit_scratch_bytes(s, k, mode);
     return layout_scratch_bytes(s) + 256;
 }
 
@@ -452,7 +453,7 @@ int32_t kmc_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, u
     if (!n_out) return fail(ctx, KMC_E_BAD_ARG, "n_out is NULL");
     if (mode < KMC_FW || mode > KMC_UNAMBIG) return fail(ctx, KMC_E_BAD_ARG, "unknown mode");
     CU(cudaSetDevice(ctx->device));
-    if (mode == KMC_UNAMBIG && seqs->src_bits == 4) return count_unambiguous_4bit(ctx, seqs, k, n_out, ctx->stream);
+    if (mode == KMC_UNAMBIG && seqs->src_bits != 2) return count_unambiguous_4bit(ctx, seqs, k, n_out, ctx->stream);
     const Geometry ge = geometry(k);
     st = ensure_scratch(ctx, layout_scratch_bytes(seqs) + 256);
     if (st) return st;
@@ -476,7 +477,7 @@ int32_t kmc_extract(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode,
     result->err_seq = result->err_pos = 0;
     result->err_sym = 0;
     result->kernel_ms = 0.f;
-    if (seqs->src_bits == 4) return extract_device_4bit(ctx, seqs, k, mode, flags, out, result, ctx->stream);
+    if (seqs->src_bits != 2) return extract_device_4bit(ctx, seqs, k, mode, flags, out, result, ctx->stream);
     st = ensure_scratch(ctx, extract_scratch_bytes(seqs, k, mode));
     if (st) return st;
     Scratch scratch{static_cast<char *>(ctx->scratch), ctx->scratch_bytes, 0};

@@ -1,0 +1,206 @@
+// ascii.cu -- ASCII sources (the AsciiEncode recoding scheme, src/construction.jl:95-96): byte
+// strings (String, SubString, codeunits, Vector{UInt8}, StringView -- what FASTA/FASTQ parsers hand
+// over) are recoded ON THE DEVICE into the same three streams a 4-bit source produces (2-bit codes,
+// "cannot be part of a k-mer" flags, hard-error flags), so the bytes cross PCIe once and the host
+// never packs anything.
+//
+//   strict FwKmers / FwRvIterator / CanonicalKmers (FwKmers.jl:117-129, CanonicalKmers.jl:146-174,
+//     construction_utils.jl:71-88): BioSequences.ascii_encode(A, byte) > 0x7f is an EncodeError.
+//     For a 2-bit alphabet the valid bytes are the alphabet's own four symbols in either case:
+//     ACGT/acgt for DNAAlphabet{2}, ACGU/acgu for RNAAlphabet{2} (BioSequences v3 builds the table
+//     from symbols(A) and their lowercase forms; restated, BioSequences is not vendored).
+//   UnambiguousKmers (UnambiguousKmers.jl:109-132): ASCII_SKIPPING_LUT (iterators/common.jl:22-32):
+//     Aa Cc Gg TtUu -> 0..3 for both alphabets, "-MRSVWYHKDBN" in either case -> skip and
+//     restart, every other byte -> EncodeError.
+#include "fourbit.h"
+
+namespace kmc {
+
+namespace {
+
+// LUT entry: bits 0-1 = 2-bit code, bit 6 = skip (ambiguity code / gap), bit 7 = error
+constexpr uint8_t kSkip = 0x40, kErr = 0x80;
+
+struct AsciiLuts {
+    uint8_t strict_dna[256], strict_rna[256], skipping[256];
+};
+
+AsciiLuts make_luts()
+{
+    AsciiLuts l;
+    for (int i = 0; i < 256; ++i) l.strict_dna[i] = l.strict_rna[i] = l.skipping[i] = kErr;
+    const char *dna = "ACGT", *rna = "ACGU";
+    for (int c = 0; c < 4; ++c) {
+        l.strict_dna[static_cast<uint8_t>(dna[c])] = l.strict_dna[static_cast<uint8_t>(dna[c] | 0x20)] = static_cast<uint8_t>(c);
+        l.strict_rna[static_cast<uint8_t>(rna[c])] = l.strict_rna[static_cast<uint8_t>(rna[c] | 0x20)] = static_cast<uint8_t>(c);
+    }
+    // iterators/common.jl:22-32
+    const char *codes[4] = {"Aa", "cC", "gG", "TtUu"};
+    for (int c = 0; c < 4; ++c)
+        for (const char *q = codes[c]; *q; ++q) l.skipping[static_cast<uint8_t>(*q)] = static_cast<uint8_t>(c);
+    for (const char *q = "-MRSVWYHKDBN"; *q; ++q) {
+        l.skipping[static_cast<uint8_t>(*q)] = kSkip;
+        const char lower = (*q >= 'A' && *q <= 'Z') ? static_cast<char>(*q | 0x20) : *q; // lowercase('-') == '-'
+        l.skipping[static_cast<uint8_t>(lower)] = kSkip;
+    }
+    return l;
+}
+
+__constant__ uint8_t c_luts[3][256];
+
+// One thread per 32 bytes: 2 x u32 of 2-bit codes, 1 x u32 of "not a base" flags, 1 x u32 of error flags.
+__global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut,
+                                                           uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
+                                                           uint32_t *__restrict__ err, uint64_t n_groups)
+{
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = c_luts[lut][threadIdx.x];
+    __syncthreads();
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_groups) return;
+    const uint64_t b0 = 32 * i;
+    uint32_t v[8];
+    if (b0 + 32 <= n_bytes && ((reinterpret_cast<uintptr_t>(bytes) & 15) == 0)) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(bytes + b0);
+        const uint4 x = __ldg(p), y = __ldg(p + 1);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint64_t b = b0 + 4 * w + c;
+                t |= static_cast<uint32_t>(b < n_bytes ? bytes[b] : 'A') << (8 * c); // past the end: never part of a window
+            }
+            v[w] = t;
+        }
+    }
+    uint64_t codes = 0;
+    uint32_t fb = 0, fe = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t e = s_lut[(v[w] >> (8 * c)) & 0xffu];
+            const int sym = 4 * w + c;
+            codes |= static_cast<uint64_t>(e & 3u) << (2 * sym);
+            fb |= ((e >> 6) ? 1u : 0u) << sym; // skip or error: the symbol cannot be part of a k-mer
+            fe |= (e >> 7) << sym;
+        }
+    }
+    reinterpret_cast<uint2 *>(rec)[i] = make_uint2(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32));
+    bad[i] = fb;
+    if (err) err[i] = fe;
+}
+
+// UnambiguousKmers over ASCII reads EVERY byte of every sequence (even sequences shorter than K),
+// so any error byte fails the call: the first sequence that holds one.  One warp per sequence.
+__global__ void __launch_bounds__(256) seq_first_error_kernel(ExtractParams p, const uint32_t *__restrict__ err,
+                                                              const uint64_t *__restrict__ seq_len, uint64_t uniform_len,
+                                                              unsigned long long *__restrict__ err_seq)
+{
+    const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p.n_seqs == 1) { // one long sequence: the whole grid strides over its flag words
+        const uint64_t len = seq_len ? seq_len[0] : uniform_len;
+        if (len == 0) return;
+        const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[0] - p.unit_bias : 0;
+        const uint64_t a = unit_off * (p.unit_bits >> 1) + p.first, b = a + len;
+        const uint64_t threads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+        for (uint64_t w = (a >> 5) + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; w <= ((b - 1) >> 5); w += threads) {
+            uint32_t v = __ldg(err + w);
+            if (w == (a >> 5)) v &= 0xffffffffu << (a & 31);
+            if (w == ((b - 1) >> 5)) v &= 0xffffffffu >> (31 - ((b - 1) & 31));
+            if (v) {
+                atomicMin(err_seq, 0ull);
+                return;
+            }
+        }
+        return;
+    }
+    for (uint64_t r = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < p.n_seqs; r += warps) {
+        const uint64_t len = seq_len ? seq_len[r] : uniform_len;
+        if (len == 0) continue;
+        const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[r] - p.unit_bias : r * p.stride_units;
+        const uint64_t a = unit_off * (p.unit_bits >> 1) + p.first, b = a + len; // error bits [a, b)
+        bool found = false;
+        for (uint64_t w = (a >> 5) + lane; w <= ((b - 1) >> 5) && !found; w += 32) {
+            uint32_t v = __ldg(err + w);
+            if (w == (a >> 5)) v &= 0xffffffffu << (a & 31);
+            if (w == ((b - 1) >> 5)) v &= 0xffffffffu >> (31 - ((b - 1) & 31));
+            found = v != 0;
+        }
+        if (__any_sync(0xffffffffu, found)) {
+            if (lane == 0) atomicMin(err_seq, static_cast<unsigned long long>(r));
+            return; // later sequences of this warp cannot lower the minimum
+        }
+    }
+}
+
+// position (1-based) and byte of the first error byte of sequence r.  One block.
+__global__ void __launch_bounds__(256) resolve_ascii_error_kernel(ExtractParams p, const uint8_t *__restrict__ bytes,
+                                                                  const uint32_t *__restrict__ err,
+                                                                  const uint64_t *__restrict__ seq_len, uint64_t uniform_len,
+                                                                  uint64_t r, uint64_t *__restrict__ err_out)
+{
+    __shared__ unsigned long long s_min;
+    if (threadIdx.x == 0) s_min = ~0ull;
+    __syncthreads();
+    const uint64_t len = seq_len ? seq_len[r] : uniform_len;
+    const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[r] - p.unit_bias : r * p.stride_units;
+    const uint64_t a = unit_off * (p.unit_bits >> 1) + p.first;
+    for (uint64_t j = threadIdx.x; j < len; j += blockDim.x) {
+        const uint64_t s = a + j;
+        if ((err[s >> 5] >> (s & 31)) & 1u) {
+            atomicMin(&s_min, static_cast<unsigned long long>(j));
+            break;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        err_out[0] = r;
+        err_out[1] = s_min + 1;
+        err_out[2] = bytes[a + s_min];
+    }
+}
+
+} // namespace
+
+cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, uint32_t *rec, uint32_t *bad, uint32_t *err,
+                         uint64_t n_groups, cudaStream_t stream)
+{
+    static bool uploaded[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !uploaded[dev]) {
+        const AsciiLuts l = make_luts();
+        e = cudaMemcpyToSymbol(c_luts, &l, sizeof l);
+        if (e != cudaSuccess) return e;
+        uploaded[dev] = true;
+    }
+    if (n_groups == 0) return cudaSuccess;
+    ascii_recode_kernel<<<static_cast<unsigned>((n_groups + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, lut, rec, bad, err, n_groups);
+    return cudaGetLastError();
+}
+
+cudaError_t ascii_first_error_seq(const ExtractParams &p, const uint32_t *err, const uint64_t *seq_len, uint64_t uniform_len,
+                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream)
+{
+    if (p.n_seqs == 0) return cudaSuccess;
+    const uint64_t want = p.n_seqs == 1 ? static_cast<uint64_t>(sm_count) * 32 : (p.n_seqs * 32 + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 32 ? want : static_cast<uint64_t>(sm_count) * 32);
+    seq_first_error_kernel<<<grid, 256, 0, stream>>>(p, err, seq_len, uniform_len, err_seq);
+    return cudaGetLastError();
+}
+
+cudaError_t ascii_resolve_error(const ExtractParams &p, const uint8_t *bytes, const uint32_t *err, const uint64_t *seq_len,
+                                uint64_t uniform_len, uint64_t r, uint64_t *err_out, cudaStream_t stream)
+{
+    resolve_ascii_error_kernel<<<1, 256, 0, stream>>>(p, bytes, err, seq_len, uniform_len, r, err_out);
+    return cudaGetLastError();
+}
+
+} // namespace kmc

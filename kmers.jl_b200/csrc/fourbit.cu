@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) vstart_kernel(const uint32_t *__restrict_
 // Turns the first offending flat window of a strict mode into what the reference throws on:
 // the first symbol with count_ones != 1 of that sequence (its 0-based sequence, 1-based position
 // and 4-bit encoding).  One thread.
-__global__ void resolve_error_kernel(ExtractParams p, int g, const uint64_t *__restrict__ words4,
+__global__ void resolve_error_kernel(ExtractParams p, int src_bits, const uint64_t *__restrict__ words4,
                                      const uint32_t *__restrict__ bad, uint64_t flat, uint64_t *__restrict__ err_out)
 {
     uint64_t r, f0;
@@ -117,7 +117,7 @@ __global__ void resolve_error_kernel(ExtractParams p, int g, const uint64_t *__r
     }
     const uint64_t w = flat - f0;
     const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[r] - p.unit_bias : r * p.stride_units;
-    const uint64_t s0 = unit_off * 16 + p.first; // absolute symbol index of the sequence's first symbol
+    const uint64_t s0 = unit_off * (p.unit_bits >> 1) + p.first; // absolute symbol index of the sequence's first symbol
     uint64_t pos0 = w + static_cast<uint64_t>(p.k) - 1; // windows before w were clean => only the last symbol can be new
     if (w == 0) {
         for (uint64_t j = 0; j < static_cast<uint64_t>(p.k); ++j) {
@@ -131,7 +131,7 @@ __global__ void resolve_error_kernel(ExtractParams p, int g, const uint64_t *__r
     const uint64_t a = s0 + pos0;
     err_out[0] = r;
     err_out[1] = pos0 + 1;
-    err_out[2] = (words4[a >> 4] >> (4 * (a & 15))) & 15u;
+    err_out[2] = src_bits == 8 ? reinterpret_cast<const uint8_t *>(words4)[a] : (words4[a >> 4] >> (4 * (a & 15))) & 15u;
 }
 
 // Emitted k-mers per sequence (UnambiguousKmers): popcount of the valid-start bits over the
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) seq_valid_counts_kernel(ExtractParams p, 
     uint64_t wcount;
     if (p.win_off) wcount = p.win_off[r + 1] - p.win_off[r]; else wcount = p.wpr;
     const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[r] - p.unit_bias : r * p.stride_units;
-    const uint64_t a = unit_off * 16 + p.first, b = a + wcount; // valid-start bits [a, b)
+    const uint64_t a = unit_off * (p.unit_bits >> 1) + p.first, b = a + wcount; // valid-start bits [a, b)
     uint64_t c = 0;
     if (wcount) {
         for (uint64_t w = (a >> 5) + lane; w <= ((b - 1) >> 5); w += 32) {
@@ -175,11 +175,11 @@ ExtractLaunchFn strict_launcher(const Geometry &ge, int mode, bool hash, bool ra
 uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
 {
     (void)k;
-    const uint64_t nb = (s->n_words + 1) / 2;
+    const uint64_t nb = s->src_bits == 8 ? (s->n_words + 31) / 32 : (s->n_words + 1) / 2; // groups of 32 symbols
     const uint64_t tb = tiles_upper_bound(s);
     uint64_t need = 0;
     need += round_up(8 * (nb + 2), 256);     // rec32
-    need += 2 * round_up(4 * (nb + 8), 256); // bad, vstart
+    need += 3 * round_up(4 * (nb + 8), 256); // bad, vstart, err
     need += 2 * 256;                         // err_flat, err_out
     need += layout_scratch_bytes(s);
     if (mode == KMC_UNAMBIG) {
@@ -215,17 +215,25 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     const Geometry &ge = st->ge;
     const bool hash = (flags & KMC_HASH_FX) != 0;
 
-    const uint64_t nb = (s->n_words + 1) / 2; // pairs of source words = u32 words of flag bits
+    const bool ascii = s->src_bits == 8;
+    // groups of 32 symbols = u32 words of flag bits (4-bit: pairs of source words; ASCII: 32 bytes)
+    const uint64_t nb = ascii ? (s->n_words + 31) / 32 : (s->n_words + 1) / 2;
     uint32_t *rec = static_cast<uint32_t *>(scratch.take(8 * (nb + 2)));
     uint32_t *bad = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
     uint32_t *vstart = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
+    uint32_t *err = (ascii && st->unambig) ? static_cast<uint32_t *>(scratch.take(4 * (nb + 8))) : nullptr;
+    if (ascii && st->unambig && !err) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+    st->err = err;
     unsigned long long *err_flat = static_cast<unsigned long long *>(scratch.take(8));
     uint64_t *err_out = static_cast<uint64_t *>(scratch.take(24));
     if (!rec || !bad || !vstart || !err_flat || !err_out) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
     st->bad = bad;
     st->err_out = err_out;
 
-    if (nb) {
+    if (ascii) {
+        const int lut = st->unambig ? 2 : ((flags & KMC_RNA) ? 1 : 0);
+        CU(ascii_recode(reinterpret_cast<const uint8_t *>(s->words), s->n_words, lut, rec, bad, err, nb, stream));
+    } else if (nb) {
         recode_kernel<<<static_cast<unsigned>((nb + 255) / 256), 256, 0, stream>>>(s->words, s->n_words, rec, bad, nb);
         CU(cudaGetLastError());
     }
@@ -242,11 +250,17 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
 
     ExtractParams p = base_params(s, k, ge, L, unit_bias);
     p.w32 = rec;
-    p.nw32 = static_cast<int64_t>(s->n_words);
-    p.unit_bits = 32;
+    p.nw32 = static_cast<int64_t>(2 * nb);
+    p.unit_bits = ascii ? 2 : 32; // offsets are in bytes = symbols (ASCII) or in source words = 16 symbols
     p.vstart = vstart;
     p.err_flat = err_flat;
     st->p = p;
+    if (ascii && st->unambig) {
+        // every byte of every sequence is read (UnambiguousKmers.jl:109-132), whatever its length
+        CU(cudaMemsetAsync(err_flat, 0xff, 8, stream));
+        CU(ascii_first_error_seq(st->p, err, s->seq_len, s->uniform_len, err_flat, ctx->sm_count, stream));
+        CU(cudaMemcpyAsync(&host_small[1], err_flat, 8, cudaMemcpyDeviceToHost, stream));
+    }
     if (L.total == 0) {
         if (st->unambig && out && out->seq_out_offset)
             CU(cudaMemsetAsync(out->seq_out_offset, 0, (s->n_seqs + 1) * sizeof(uint64_t), stream));
@@ -299,7 +313,8 @@ int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cuda
     const Layout &L = st->L;
     if (!st->unambig) {
         if (st->host_small[1] != kNone) {
-            resolve_error_kernel<<<1, 1, 0, stream>>>(st->p, st->ge.g, st->words4, st->bad, st->host_small[1], st->err_out);
+            resolve_error_kernel<<<1, 1, 0, stream>>>(st->p, static_cast<int>(st->seqs->src_bits), st->words4, st->bad,
+                                                      st->host_small[1], st->err_out);
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(&st->host_small[2], st->err_out, 24, cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
@@ -311,6 +326,17 @@ int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cuda
         }
         res->n_written = L.total;
         return KMC_OK;
+    }
+    if (st->err && st->host_small[1] != kNone) { // ASCII: a byte outside the skipping table
+        CU(ascii_resolve_error(st->p, reinterpret_cast<const uint8_t *>(st->words4), st->err, st->seqs->seq_len,
+                               st->seqs->uniform_len, st->host_small[1], st->err_out, stream));
+        CU(cudaMemcpyAsync(&st->host_small[4], st->err_out, 24, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        res->n_written = 0;
+        res->err_seq = st->host_small[4];
+        res->err_pos = st->host_small[5];
+        res->err_sym = static_cast<uint32_t>(st->host_small[6]);
+        return fail(ctx, KMC_E_AMBIGUOUS, "cannot encode this byte in a 2-bit alphabet");
     }
     const uint64_t total = L.total ? st->host_small[0] : 0;
     const uint64_t n_runs = L.total ? st->host_small[2] : 0;
@@ -414,6 +440,11 @@ int32_t count_unambiguous_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, uint6
     rc = fourbit_phase_a(ctx, s, k, KMC_UNAMBIG, 0, nullptr, stream, KnownTotals(), 0, scratch, ctx->host_small, &st);
     if (rc) return rc;
     CU(cudaStreamSynchronize(stream));
+    if (st.err && ctx->host_small[1] != kNone) { // ASCII: the iteration would throw before finishing
+        kmc_result r{};
+        Scratch none;
+        return fourbit_phase_b(ctx, &st, nullptr, stream, none, &r);
+    }
     *n_out = st.L.total ? ctx->host_small[0] : 0;
     return KMC_OK;
 }

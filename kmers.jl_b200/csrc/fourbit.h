@@ -1,5 +1,6 @@
-// fourbit.h -- 4-bit (DNAAlphabet{4} / RNAAlphabet{4}) sources: the FourToTwo recoding scheme
-// (src/construction.jl:85-86).
+// fourbit.h -- sources that are recoded on the device before extraction: 4-bit (DNAAlphabet{4} /
+// RNAAlphabet{4}) LongSequences, the FourToTwo scheme (src/construction.jl:85-86), and ASCII byte
+// strings, the AsciiEncode scheme (construction.jl:95-96, ascii.cu).
 //
 // A 4-bit source is first recoded on the device into (i) a 2-bit stream (trailing_zeros of each
 // one-hot nibble, construction_utils.jl:41-54) and (ii) a bit stream that flags every uncertain
@@ -31,6 +32,7 @@ struct FourBitState {
     Layout L{};      // strict: layout for the kernel's G; UnambiguousKmers: the G = 32 run-marking layout
     ExtractParams p{};
     uint32_t *bad = nullptr;
+    uint32_t *err = nullptr; // ASCII UnambiguousKmers: hard-error flags (bytes outside the skipping table)
     uint64_t *tile_valid_off = nullptr, *tile_runs_off = nullptr; // UnambiguousKmers: scans of the per-tile counts
     uint64_t *err_out = nullptr; // device u64[3]: seq, 1-based pos, encoding
     uint64_t *host_small = nullptr;
@@ -45,6 +47,15 @@ uint64_t run_scratch_bytes(uint64_t n_runs, uint64_t n_valid, int g);
 cudaError_t mark_runs(const ExtractParams &p, bool ragged, uint64_t *tile_valid, uint64_t *tile_runs, cudaStream_t stream);
 cudaError_t emit_runs(const ExtractParams &p, bool ragged, const uint64_t *tile_valid_off, const uint64_t *tile_runs_off,
                       uint64_t *run_sym, uint64_t *run_woff, uint64_t *run_ibase, cudaStream_t stream);
+
+// ascii.cu: byte sources (AsciiEncode).  lut: 0 = strict DNAAlphabet{2}, 1 = strict RNAAlphabet{2},
+// 2 = the UnambiguousKmers skipping table.  n_groups = groups of 32 bytes.
+cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, uint32_t *rec, uint32_t *bad, uint32_t *err,
+                         uint64_t n_groups, cudaStream_t stream);
+cudaError_t ascii_first_error_seq(const ExtractParams &p, const uint32_t *err, const uint64_t *seq_len, uint64_t uniform_len,
+                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream);
+cudaError_t ascii_resolve_error(const ExtractParams &p, const uint8_t *bytes, const uint32_t *err, const uint64_t *seq_len,
+                                uint64_t uniform_len, uint64_t r, uint64_t *err_out, cudaStream_t stream);
 
 uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode);
 

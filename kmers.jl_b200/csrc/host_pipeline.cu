@@ -57,8 +57,10 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
 
     const Geometry ge = geometry(k);
     const uint64_t N = static_cast<uint64_t>(ge.n_limbs);
-    const bool four = hs->src_bits == 4;
-    const uint64_t spw = four ? 16 : 32; // symbols per source word
+    const bool four = hs->src_bits != 2; // recoded on the device first: 4-bit words or ASCII bytes (fourbit.h)
+    const bool ascii = hs->src_bits == 8;
+    const uint64_t spw = ascii ? 1 : hs->src_bits == 4 ? 16 : 32; // symbols per source unit (word, or byte for ASCII)
+    const uint64_t unit_bytes = ascii ? 1 : 8;
     const bool hash = (flags & KMC_HASH_FX) != 0;
     const bool aos = (flags & KMC_AOS) != 0;
     const bool dev_out = (flags & KMC_OUT_DEVICE) != 0; // outputs stay in (caller-provided) device memory
@@ -186,7 +188,7 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         max_seq = std::max(max_seq, c.nseq);
     }
     const bool want_seq_out = compacting && ho->seq_out_offset && !single;
-    const uint64_t b_words = round_up((max_words + 4) * 8, 256);
+    const uint64_t b_words = round_up((max_words + 32) * unit_bytes, 256);
     const uint64_t b_meta = round_up((max_seq + 1) * 8, 256);
     const uint64_t b_a = dev_out ? 0 : round_up(max_out * a_elems * 8, 256);
     const uint64_t b_b = (two && !aos && !dev_out) ? round_up(max_out * N * 8, 256) : 0;
@@ -327,7 +329,9 @@ extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k,
         Chunk &c = chunks[ci];
         Slot &sl = slots[ci % n_slots];
         cudaStream_t sm = sl.stream;
-        if (c.nwords) CU(cudaMemcpyAsync(sl.words, hs->words + c.word0, c.nwords * 8, cudaMemcpyHostToDevice, sm));
+        if (c.nwords)
+            CU(cudaMemcpyAsync(sl.words, reinterpret_cast<const char *>(hs->words) + c.word0 * unit_bytes, c.nwords * unit_bytes,
+                               cudaMemcpyHostToDevice, sm));
         kmc_seqs &ds = c.ds;
         ds = *hs;
         ds.words = sl.words;

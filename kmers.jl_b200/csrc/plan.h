@@ -76,8 +76,8 @@ struct Layout {
 // partial group slots per sequence), for scratch sizing before the exact totals are known
 inline uint64_t tiles_upper_bound(const kmc_seqs *s)
 {
-    const uint64_t spw = s->src_bits == 4 ? 16 : 32;
-    return (s->n_words * spw + 2 * s->n_seqs) / kTileItems + 2;
+    const uint64_t spu = s->src_bits == 8 ? 1 : s->src_bits == 4 ? 16 : 32; // symbols per unit of n_words
+    return (s->n_words * spu + 2 * s->n_seqs) / kTileItems + 2;
 }
 
 int32_t check_common(kmc_ctx *ctx, const kmc_seqs *s, int32_t k);

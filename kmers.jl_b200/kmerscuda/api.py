@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import (KMC_AOS, KMC_CANON, KMC_E_AMBIGUOUS, KMC_E_BAD_K, KMC_FW, KMC_FWRV, KMC_HASH_FX, KMC_MAX_K,
-                   KMC_NO_SYNC, KMC_OK, KMC_OUT_DEVICE, KMC_UNAMBIG, kmc_out, kmc_result, kmc_seqs)
+                   KMC_NO_SYNC, KMC_OK, KMC_OUT_DEVICE, KMC_RNA, KMC_UNAMBIG, kmc_out, kmc_result, kmc_seqs)
 
 # ----------------------------------------------------------------------------------------------
 # alphabets (only what the path needs: the 2- and 4-bit nucleic acid alphabets)
@@ -120,12 +120,14 @@ class ReadSet:
     """A batch of LongSequences in one word-aligned CSR buffer (what `Vector{LongDNA{2}}` becomes).
 
     Either ragged (`seq_word_offset`, `seq_len` arrays) or uniform (`uniform_len`, `uniform_stride_words`).
+    bits = 8 is a set of ASCII sources (`Vector{String}`): `words` are the concatenated BYTES and the
+    offsets / strides count bytes.
     """
 
     def __init__(self, bits: int, words: np.ndarray, n_seqs: int, *, seq_word_offset=None, seq_len=None,
                  uniform_len: int = 0, uniform_stride_words: int = 0, first_symbol_offset: int = 0):
         self.bits = bits
-        self.words = np.ascontiguousarray(words, dtype=np.uint64)
+        self.words = np.ascontiguousarray(words, dtype=np.uint8 if bits == 8 else np.uint64)
         self.n_seqs = int(n_seqs)
         self.seq_word_offset = None if seq_word_offset is None else np.ascontiguousarray(seq_word_offset, np.uint64)
         self.seq_len = None if seq_len is None else np.ascontiguousarray(seq_len, np.uint64)
@@ -144,6 +146,27 @@ class ReadSet:
             words[int(o): int(o) + n] = s.data[:n]
         return cls(bits, words, len(seqs), seq_word_offset=off[:-1].copy(),
                    seq_len=np.array([len(s) for s in seqs], dtype=np.uint64))
+
+    @classmethod
+    def from_strings(cls, strs) -> "ReadSet":
+        """ASCII sources (str / bytes), concatenated without separators."""
+        raw = [x.encode("latin-1") if isinstance(x, str) else bytes(x) for x in strs]
+        lens = np.array([len(r) for r in raw], dtype=np.uint64)
+        off = np.zeros(len(raw) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        data = np.frombuffer(b"".join(raw) + b"\0", dtype=np.uint8).copy()
+        return cls(8, data, len(raw), seq_word_offset=off[:-1].copy(), seq_len=lens)
+
+    @classmethod
+    def ascii(cls, src, first_symbol_offset: int = 0, length: Optional[int] = None) -> "ReadSet":
+        """One ASCII source (String, SubString, codeunits, Vector{UInt8})."""
+        if isinstance(src, str):
+            src = src.encode("latin-1")
+        data = np.frombuffer(bytes(src), dtype=np.uint8) if not isinstance(src, np.ndarray) else np.ascontiguousarray(src, np.uint8)
+        n = int(data.size) - first_symbol_offset if length is None else length
+        if data.size == 0:
+            data = np.zeros(1, np.uint8)
+        return cls(8, data, 1, uniform_len=n, uniform_stride_words=int(data.size), first_symbol_offset=first_symbol_offset)
 
     @classmethod
     def single(cls, seq: LongSequence, first_symbol_offset: int = 0, length: Optional[int] = None) -> "ReadSet":
@@ -320,6 +343,8 @@ _MODE_NAMES = {KMC_FW: "FwKmers", KMC_FWRV: "FwRvIterator", KMC_CANON: "Canonica
 
 
 def _raise_ambiguous(rs_bits: int, A: Alphabet, res: kmc_result):
+    if rs_bits == 8:  # ASCII source: the offending byte
+        raise EncodeError(A, chr(res.err_sym & 0xFF), int(res.err_seq), int(res.err_pos))
     sym = _SYM4_DNA[res.err_sym & 15]
     if A.name.startswith("RNA") and sym == "T":
         sym = "U"
@@ -357,7 +382,7 @@ def extract(mode: int, rs, K: int, *, A: Alphabet = DNAAlphabet2, hash: bool = F
     two = mode == KMC_FWRV
     want_index = mode == KMC_UNAMBIG
     a_elems = (2 * N if two else N + 1 if want_index else N) if aos else N
-    flags = (KMC_HASH_FX if hash else 0) | (KMC_AOS if aos else 0)
+    flags = (KMC_HASH_FX if hash else 0) | (KMC_AOS if aos else 0) | (KMC_RNA if A.name.startswith("RNA") else 0)
     res = kmc_result()
 
     if host_path and device_out:
@@ -425,18 +450,22 @@ def extract(mode: int, rs, K: int, *, A: Alphabet = DNAAlphabet2, hash: bool = F
 class _KmerIterator:
     mode = KMC_FW
 
-    def __init__(self, A: Alphabet, K: int, seq: LongSequence):
+    def __init__(self, A: Alphabet, K: int, seq):
         _check_K(K)
-        if not isinstance(seq, LongSequence):
-            raise TypeError("the accelerated path takes LongSequence sources (ASCII sources are the next row)")
+        # RecodingScheme(A, S) (construction.jl:75-100): LongSequence -> Copyable / FourToTwo,
+        # str / bytes / uint8 arrays -> AsciiEncode
+        if not isinstance(seq, (LongSequence, str, bytes, bytearray, np.ndarray)):
+            raise TypeError("sources are LongSequence (2- or 4-bit) or ASCII (str, bytes, uint8 array)")
         self.A, self.K, self.seq = A, K, seq
+        self.is_ascii = not isinstance(seq, LongSequence)
 
     def __len__(self):
         # FwKmers.jl:40-43
         return max(0, len(self.seq) - self.K + 1)
 
     def _extract(self, **kw) -> Extracted:
-        return extract(self.mode, ReadSet.single(self.seq), self.K, A=self.A, **kw)
+        rs = ReadSet.ascii(self.seq) if self.is_ascii else ReadSet.single(self.seq)
+        return extract(self.mode, rs, self.K, A=self.A, **kw)
 
 
 class FwKmers(_KmerIterator):
@@ -469,8 +498,8 @@ class UnambiguousKmers(_KmerIterator):
 
     def __len__(self):
         # IteratorSize is SizeUnknown unless the source is 2-bit (UnambiguousKmers.jl:33-37)
-        if self.seq.alphabet.bits != 2:
-            raise TypeError("length is unknown for a 4-bit source (Base.SizeUnknown)")
+        if self.is_ascii or self.seq.alphabet.bits != 2:
+            raise TypeError("length is unknown unless the source is a 2-bit sequence (Base.SizeUnknown)")
         return super().__len__()
 
     def collect(self, **kw):

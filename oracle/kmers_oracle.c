@@ -509,3 +509,118 @@ int ko_max_threads(void)
     return 1;
 #endif
 }
+
+/* ======================================================================
+ * ASCII sources (the AsciiEncode recoding scheme, src/construction.jl:95-96).
+ *
+ * BioSequences.ascii_encode(A, byte) is not in the reference tree; restated from
+ * BioSequences v3 (src/alphabet.jl): a 256-entry table filled with 0x80, then for
+ * every symbol of the alphabet its character and its lowercase character map to
+ * the symbol's encoding.  For DNAAlphabet{2}: ACGT/acgt -> 0..3; for
+ * RNAAlphabet{2}: ACGU/acgu -> 0..3; everything else >= 0x80 (EncodeError).
+ * Pinned by the reference's tests only as far as: lowercase is accepted
+ * (test/runtests.jl:713-719) and 'P' is rejected (:722-724, :844-846).
+ * ====================================================================== */
+INL unsigned ascii_encode2(int rna, unsigned b)
+{
+    switch (b) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return rna ? 0x80u : 3;
+    case 'U': case 'u': return rna ? 3 : 0x80u;
+    default: return 0x80u;
+    }
+}
+
+/* src/iterators/common.jl:22-32  ASCII_SKIPPING_LUT */
+INL unsigned ascii_skipping_lut(unsigned b)
+{
+    switch (b) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': case 'U': case 'u': return 3;
+    case '-':
+    case 'M': case 'R': case 'S': case 'V': case 'W': case 'Y': case 'H': case 'K': case 'D': case 'B': case 'N':
+    case 'm': case 'r': case 's': case 'v': case 'w': case 'y': case 'h': case 'k': case 'd': case 'b': case 'n':
+        return 0xf0;
+    default: return 0xff;
+    }
+}
+
+/* FwKmers.jl:69-78,117-129 ; CanonicalKmers.jl:69-79,146-174,220-225 ; construction_utils.jl:71-88 */
+static int ascii_iterate_n(const uint8_t *src, u64 len, int rna, int K, const int N, int mode,
+                           u64 *out_a, u64 *out_b, u64 *out_hash, u64 *n_out, u64 *err_pos, u64 *err_byte)
+{
+    u64 fw[KO_MAX_LIMBS], rv[KO_MAX_LIMBS];
+    u64 n = 0;
+    *n_out = 0;
+    if (len < (u64)K) return KO_OK;
+    for (int i = 0; i < N; ++i) fw[i] = 0;
+    for (u64 i = 1; i <= (u64)K; ++i) { /* unsafe_extract(::AsciiEncode) */
+        unsigned enc = ascii_encode2(rna, src[i - 1]);
+        if (enc > 0x7f) { *err_pos = i; *err_byte = src[i - 1]; return KO_E_AMBIGUOUS; }
+        leftshift_carry(fw, N, 2, enc);
+    }
+    if (mode != KO_FW) {
+        for (int i = 0; i < N; ++i) rv[i] = fw[i];
+        reverse_complement2(rv, K, N);
+    }
+    u64 i = (u64)K + 1;
+    for (;;) {
+        const u64 *a = fw;
+        if (mode == KO_CANON) a = (cmp_limbs(fw, rv, N) == -1) ? fw : rv;
+        for (int j = 0; j < N; ++j) out_a[n * (u64)N + j] = a[j];
+        if (mode == KO_FWRV)
+            for (int j = 0; j < N; ++j) out_b[n * (u64)N + j] = rv[j];
+        if (out_hash) out_hash[n] = fx_hash_limbs(a, N, 0);
+        ++n;
+        if (i > len) break;
+        unsigned enc = ascii_encode2(rna, src[i - 1]);
+        if (enc > 0x7f) { *n_out = n; *err_pos = i; *err_byte = src[i - 1]; return KO_E_AMBIGUOUS; }
+        shift_encoding(fw, K, N, enc);
+        if (mode != KO_FW) shift_first_encoding(rv, K, N, enc ^ 3u);
+        ++i;
+    }
+    *n_out = n;
+    return KO_OK;
+}
+
+int ko_ascii_iterate(const uint8_t *src, uint64_t len, int rna, int K, int mode,
+                     uint64_t *out_a, uint64_t *out_b, uint64_t *out_hash,
+                     uint64_t *n_out, uint64_t *err_pos, uint64_t *err_byte)
+{
+    int st = check_k(K);
+    if (st) return st;
+    return ascii_iterate_n(src, len, rna, K, n_limbs(K, 2), mode, out_a, out_b, out_hash, n_out, err_pos, err_byte);
+}
+
+/* UnambiguousKmers.jl:79-86 (initial state) and :109-132 (the ASCII loop).  out_kmer may be NULL (count only). */
+int ko_ascii_unambiguous(const uint8_t *src, uint64_t len, int K, uint64_t *out_kmer, int64_t *out_pos,
+                         uint64_t *n_out, uint64_t *err_pos, uint64_t *err_byte)
+{
+    int st = check_k(K);
+    if (st) return st;
+    const int N = n_limbs(K, 2);
+    u64 kmer[KO_MAX_LIMBS];
+    for (int j = 0; j < N; ++j) kmer[j] = 0;
+    u64 n = 0, remaining = (u64)K, index = 1;
+    for (;;) {
+        while (remaining != 0) {
+            if (index > len) { *n_out = n; return KO_OK; }
+            unsigned byte = src[index - 1];
+            index += 1;
+            unsigned enc = ascii_skipping_lut(byte);
+            if (enc == 0xff) { *n_out = n; *err_pos = index - 1; *err_byte = byte; return KO_E_AMBIGUOUS; }
+            else if (enc == 0xf0) remaining = (u64)K;
+            else { remaining -= 1; shift_encoding(kmer, K, N, enc); }
+        }
+        if (out_kmer) {
+            for (int j = 0; j < N; ++j) out_kmer[n * (u64)N + j] = kmer[j];
+            out_pos[n] = (int64_t)(index - (u64)K);
+        }
+        ++n;
+        remaining = 1;
+    }
+}

@@ -66,6 +66,11 @@ def lib():
         L.ko_batch_unambiguous.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                            C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int]
+        L.ko_ascii_iterate.restype = C.c_int
+        L.ko_ascii_iterate.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, _u64p, _u64p, _u64p]
+        L.ko_ascii_unambiguous.restype = C.c_int
+        L.ko_ascii_unambiguous.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, _u64p, _u64p, _u64p]
         L.ko_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -128,6 +133,51 @@ def unambiguous(words, length, k, src_bits=4, first=0):
     pos = np.zeros(max(n, 1), dtype=np.int64)
     n_out = C.c_uint64(0)
     st = L.ko_unambiguous(_ptr(w), first, length, src_bits, k, _ptr(km), _ptr(pos), C.byref(n_out))
+    if st != KO_OK:
+        raise ValueError(f"oracle status {st}")
+    return km[: n_out.value].copy(), pos[: n_out.value].copy()
+
+
+def _bytes(src):
+    if isinstance(src, str):
+        src = src.encode("latin-1")
+    b = np.frombuffer(bytes(src), dtype=np.uint8) if not isinstance(src, np.ndarray) else np.ascontiguousarray(src, np.uint8)
+    return b if b.size else np.zeros(1, np.uint8), (len(src) if not isinstance(src, np.ndarray) else int(src.size))
+
+
+def ascii_iterate(src, k, mode, rna=False, want_hash=False):
+    """FwKmers / FwRvIterator / CanonicalKmers over an ASCII source (String, codeunits, ...).
+    Raises AmbiguousError(pos = 1-based byte index, enc = the byte) on an invalid byte."""
+    L = lib()
+    if k < 1:
+        raise ValueError("K must be at least 1")
+    b, length = _bytes(src)
+    N = n_limbs(k)
+    n = max(0, length - k + 1)
+    a = np.zeros((n, N), dtype=np.uint64)
+    bb = np.zeros((n, N), dtype=np.uint64) if mode == FWRV else None
+    h = np.zeros(n, dtype=np.uint64) if want_hash else None
+    n_out, ep, ee = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    st = L.ko_ascii_iterate(_ptr(b), length, int(rna), k, mode, _ptr(a), _ptr(bb), _ptr(h), C.byref(n_out), C.byref(ep), C.byref(ee))
+    if st == KO_E_AMBIGUOUS:
+        raise AmbiguousError(0, ep.value, ee.value, n_out.value)
+    if st != KO_OK:
+        raise ValueError(f"oracle status {st}")
+    return a, bb, h
+
+
+def ascii_unambiguous(src, k):
+    """UnambiguousKmers over an ASCII source: (kmers, 1-based starts)."""
+    L = lib()
+    b, length = _bytes(src)
+    N = n_limbs(k)
+    n = max(0, length - k + 1)
+    km = np.zeros((max(n, 1), N), dtype=np.uint64)
+    pos = np.zeros(max(n, 1), dtype=np.int64)
+    n_out, ep, ee = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    st = L.ko_ascii_unambiguous(_ptr(b), length, k, _ptr(km), _ptr(pos), C.byref(n_out), C.byref(ep), C.byref(ee))
+    if st == KO_E_AMBIGUOUS:
+        raise AmbiguousError(0, ep.value, ee.value, n_out.value)
     if st != KO_OK:
         raise ValueError(f"oracle status {st}")
     return km[: n_out.value].copy(), pos[: n_out.value].copy()

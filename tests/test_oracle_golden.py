@@ -273,3 +273,40 @@ def test_batch_unambiguous_and_errors():
     assert ei.value.seq == bad[0]
     s = seqs[bad[0]]
     assert ei.value.pos == 1 + min(i for i, c in enumerate(s) if not kt.is_certain(c))
+
+
+# ------------------------------------------------------------------ ASCII sources (AsciiEncode)
+def test_ascii_oracle_against_reference_examples_and_naive():
+    """The ASCII restatement against the reference's own examples and the string-level naive
+    definitions (/root/reference/test/runtests.jl:713-725, 754, 779, 812-821, 844-846, 892-899)."""
+    import kmertools as kt
+    from oracle import oracle as ko
+    a, _, _ = ko.ascii_iterate("AGCGA", 3, ko.CANON, rna=True)
+    assert [tuple(r) for r in a.tolist()] == [kt.kmer_limbs(x) for x in ("AGC", "CGC", "CGA")]
+    km, pos = ko.ascii_unambiguous("TGAGCWKCATC", 4)  # UnambiguousKmers.jl:18-27 given as a String
+    assert pos.tolist() == [1, 2, 8] and [tuple(r) for r in km.tolist()] == [kt.kmer_limbs(x) for x in ("TGAG", "GAGC", "CATC")]
+    rng = np.random.default_rng(5)
+    for k in (1, 3, 31, 33, 64):
+        for n in (0, k - 1, k, 200):
+            s = kt.random_dna(rng, n)
+            mixed = "".join(c.lower() if rng.random() < 0.4 else c for c in s)
+            a, b, h = ko.ascii_iterate(mixed, k, ko.FWRV, want_hash=True)
+            want = kt.naive_fwrv(s, k)
+            assert [tuple(r) for r in a.tolist()] == [w[0] for w in want]
+            assert [tuple(r) for r in b.tolist()] == [w[1] for w in want]
+            assert h.tolist() == [kt.fx_hash(w[0]) for w in want]
+            c, _, _ = ko.ascii_iterate(mixed.replace("T", "U").replace("t", "u"), k, ko.CANON, rna=True)
+            assert [tuple(r) for r in c.tolist()] == kt.naive_canonical(s, k)
+            amb = kt.random_dna(rng, n, ambiguous=0.1)
+            km, pos = ko.ascii_unambiguous(amb.lower(), k)
+            wantu = kt.naive_unambiguous(amb, k)
+            assert [tuple(r) for r in km.tolist()] == [w[0] for w in wantu] and pos.tolist() == [w[1] for w in wantu]
+    for fn in (lambda: ko.ascii_iterate("TAGTCGTAGPATGC", 3, ko.FW), lambda: ko.ascii_unambiguous("TAGTCGTAGPATGC", 3)):
+        with pytest.raises(ko.AmbiguousError) as ei:
+            fn()
+        assert ei.value.pos == 10 and ei.value.enc == ord("P")
+    with pytest.raises(ko.AmbiguousError):
+        ko.ascii_iterate("ACGU", 2, ko.FW)            # U is not a DNAAlphabet{2} letter
+    with pytest.raises(ko.AmbiguousError):
+        ko.ascii_iterate("ACGT", 2, ko.FW, rna=True)  # T is not an RNAAlphabet{2} letter
+    assert ko.ascii_unambiguous("ACGTUacgtu", 2)[0].shape[0] == 9  # the skipping table takes both

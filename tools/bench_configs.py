@@ -210,6 +210,31 @@ def case_ragged(ctx, steps, scale):
         del words, a, h
 
 
+def case_ascii(ctx, steps, scale):
+    """C2 workload from ASCII bytes (what a FASTQ parser hands over): 150 bytes per read, recoded on the device."""
+    n_reads, length, k = int(10_000_000 * scale), 150, 31
+    wpr = length - k + 1
+    n = n_reads * wpr
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
+    data = lut[torch.randint(0, 4, (n_reads * length,), device="cuda", generator=g)]
+    a = torch.empty(n, dtype=torch.int64, device="cuda")
+    h = torch.empty(n, dtype=torch.int64, device="cuda")
+    desc = _abi.kmc_seqs(data.data_ptr(), data.numel(), n_reads, None, None, length, length, 8, 0)
+    out = _abi.kmc_out(a.data_ptr(), None, h.data_ptr(), None, None, n, 0)
+    res = _abi.kmc_result()
+    torch.cuda.synchronize()
+    med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, CANON, _abi.KMC_HASH_FX, out, res), steps)
+    emit("ASCII source: CanonicalDNAMers{31}+fx_hash, %d x 150-byte reads (strict, recoded on device)" % n_reads, n,
+         1.0 * n_reads * length + 16 * n, med, mn)
+    data[torch.rand(data.numel(), device="cuda", generator=g) < 0.01] = 78  # 'N'
+    idx = torch.empty(n, dtype=torch.int64, device="cuda")
+    out = _abi.kmc_out(a.data_ptr(), None, None, idx.data_ptr(), None, n, 0)
+    med, mn = timed(ctx, lambda: run_extract(ctx, desc, k, UNAMBIG, 0, out, res), steps)
+    nw = int(res.n_written)
+    emit("ASCII source: UnambiguousDNAMers{31}, 1%% N, %d x 150-byte reads" % n_reads, nw, 1.0 * n_reads * length + 16 * nw, med, mn)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="c3,c3long,c4,c5,modes")
@@ -221,7 +246,7 @@ def main():
     WARMUP = args.warmup
     torch.cuda.set_device(0)
     ctx = kc.Context(0)
-    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged}
+    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii}
     for c in args.cases.split(","):
         table[c](ctx, args.steps, args.scale)
         torch.cuda.empty_cache()
