@@ -167,6 +167,17 @@ int32_t kmc_fx_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n_l
 int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
                          uint32_t *table, kmc_result *result);
 
+/* Minimizers: "the minimum of W consecutive kmers, as ordered by some ordering O"
+ * (docs/src/replacements.md:28-30) with fx_hash as the ordering (replacements.md:32-58,
+ * test/benchmark.jl:96-119).  For every window start i = 1, 1+step, 1+2*step, ... that has W
+ * k-mers available, out.a gets the k-mer with the smallest fx_hash among the k-mers starting at
+ * i .. i+W-1 (ties: the first), out.hash (KMC_HASH_FX) its hash and out.index (optional) its
+ * 1-based start.  mode KMC_FW orders forward k-mers as the reference example does, KMC_CANON
+ * canonical k-mers.  Device buffers; 2-bit sources; K <= 32 and K + W - 1 <= 64.  The full
+ * k-mer stream is never written. */
+int32_t kmc_minimizers(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t w, int32_t step, int32_t mode,
+                       uint32_t flags, const kmc_out *out, kmc_result *result);
+
 /* XOR and wrapping sum of n u64 words in device memory -> out[0], out[1] (host).  A cheap
  * fingerprint of a device-resident stream: parity checks and result read-back at sizes where
  * downloading the stream itself would only measure PCIe.  Synchronises. */

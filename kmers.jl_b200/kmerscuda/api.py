@@ -552,6 +552,34 @@ def fx_hash(kmers: np.ndarray, h: int = 0, ctx: Optional[Context] = None) -> np.
     return out
 
 
+def minimizers(rs, K: int, W: int, step: int = 1, *, canonical: bool = False, hash: bool = False,
+               ctx: Optional[Context] = None):
+    """Minimizers under the fx_hash ordering (docs/src/replacements.md:28-58): for every window start
+    1, 1+step, ... the k-mer with the smallest fx_hash among W consecutive k-mers.
+    Returns (kmers u64[n], index i64[n] 1-based start of each minimizer, hash u64[n] or None, seq_out_offset)."""
+    _check_K(K)
+    ctx = ctx or default_context()
+    drs = rs if isinstance(rs, DeviceReadSet) else DeviceReadSet(ctx, rs)
+    h = drs.host
+    span = K + W - 1
+    lens = np.full(h.n_seqs, h.uniform_len, dtype=np.int64) if h.seq_len is None else h.seq_len.astype(np.int64)
+    cap = int(np.where(lens >= span, (lens - span) // step + 1, 0).sum())
+    da, di = ctx.alloc(max(cap, 1) * 8), ctx.alloc(max(cap, 1) * 8)
+    dh = ctx.alloc(max(cap, 1) * 8) if hash else None
+    dso = ctx.alloc((h.n_seqs + 1) * 8)
+    out = kmc_out(da.ptr, None, dh.ptr if dh else None, di.ptr, dso.ptr, cap, 0)
+    res = kmc_result()
+    ctx._check(ctx.lib.kmc_minimizers(ctx.handle, C.byref(drs.desc), K, W, step, KMC_CANON if canonical else KMC_FW,
+                                      KMC_HASH_FX if hash else 0, C.byref(out), C.byref(res)))
+    n = int(res.n_written)
+    r = (da.download(np.uint64, n), di.download(np.int64, n), dh.download(np.uint64, n) if dh else None,
+         dso.download(np.uint64, h.n_seqs + 1))
+    for d in (da, di, dh, dso):
+        if d:
+            d.free()
+    return r
+
+
 def bucket_count(rs, K: int, bucket_bits: int, ctx: Optional[Context] = None, table: Optional[DeviceBuffer] = None):
     """Histogram of fx_hash(canonical k-mer) >> (64 - bucket_bits) (north_star extension).
     Returns (table u32[2^bucket_bits] on the host, n_kmers, kernel_ms)."""

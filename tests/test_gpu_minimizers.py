@@ -1,0 +1,83 @@
+"""Minimizers on the device (kmc_minimizers) against the prose definition of the reference
+("the minimum of W consecutive kmers" under the fx_hash ordering,
+/root/reference/docs/src/replacements.md:28-58, test/benchmark.jl:96-119), evaluated naively per
+window from the string."""
+import numpy as np
+import pytest
+
+import kmertools as kt
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kc():
+    import kmerscuda
+    return kmerscuda
+
+
+def naive_minimizers(s, k, w, step, canonical):
+    out = []
+    span = k + w - 1
+    for i in range(0, len(s) - span + 1, step):
+        best = None
+        for j in range(w):
+            sub = s[i + j:i + j + k]
+            km = kt.kmer_int(sub)
+            if canonical:
+                km = min(km, kt.kmer_int(kt.revcomp(sub)))
+            h = kt.fx_hash((km,))
+            if best is None or h < best[0]:
+                best = (h, km, i + j + 1)
+        out.append(best)
+    return out
+
+
+@pytest.mark.parametrize("k,w", [(8, 20), (5, 9), (31, 10), (32, 33), (15, 10), (1, 1), (1, 64), (21, 1)])
+def test_single_sequence(kc, k, w):
+    rng = np.random.default_rng(k * 100 + w)
+    for length in sorted({0, k + w - 2, k + w - 1, k + w, 333, 2000}):
+        s = kt.random_dna(rng, max(length, 0))
+        rs = kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet2, kt.pack2(s), len(s)))
+        for step in sorted({1, w, 7}):
+            for canonical in (False, True):
+                want = naive_minimizers(s, k, w, step, canonical)
+                km, idx, h, off = kc.minimizers(rs, k, w, step, canonical=canonical, hash=True)
+                assert km.tolist() == [x[1] for x in want], (k, w, length, step, canonical)
+                assert idx.tolist() == [x[2] for x in want]
+                assert h.tolist() == [x[0] for x in want]
+                assert off.tolist() == [0, len(want)]
+
+
+def test_read_sets(kc):
+    rng = np.random.default_rng(8)
+    k, w = 15, 10
+    lens = [0, 5, k + w - 2, k + w - 1, k + w, 150, 151] + rng.integers(0, 300, size=400).tolist()
+    seqs = [kt.random_dna(rng, int(n)) for n in lens]
+    packed = [kt.pack2(s) for s in seqs]
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(p) for p in packed])
+    words = np.concatenate([p for p in packed if len(p)] + [np.zeros(1, np.uint64)])
+    rs = kc.ReadSet(2, words, len(seqs), seq_word_offset=off[:-1].copy(), seq_len=np.array(lens, dtype=np.uint64))
+    for step in (1, 10):
+        want = [naive_minimizers(s, k, w, step, True) for s in seqs]
+        km, idx, h, so = kc.minimizers(rs, k, w, step, canonical=True, hash=True)
+        flat = [x for ws in want for x in ws]
+        assert km.tolist() == [x[1] for x in flat] and idx.tolist() == [x[2] for x in flat]
+        assert so.tolist() == np.concatenate([[0], np.cumsum([len(ws) for ws in want])]).tolist()
+    # uniform read set (the C2 shape), benchmark.jl's K = 8, W = 20, step 20
+    n_reads, length, stride = 500, 150, 5
+    seqs = [kt.random_dna(rng, length) for _ in range(n_reads)]
+    words = np.concatenate([kt.pack2(s) for s in seqs])
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    km, idx, h, so = kc.minimizers(rs, 8, 20, 20)
+    flat = [x for s in seqs for x in naive_minimizers(s, 8, 20, 20, False)]
+    assert km.tolist() == [x[1] for x in flat] and idx.tolist() == [x[2] for x in flat] and h is None
+
+
+def test_argument_checks(kc):
+    rs = kc.ReadSet.single(kc.LongDNA2("ACGT" * 50))
+    with pytest.raises(kc.KmersCUDAError):
+        kc.minimizers(rs, 33, 5)
+    with pytest.raises(kc.KmersCUDAError):
+        kc.minimizers(rs, 31, 40)
