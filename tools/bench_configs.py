@@ -235,6 +235,30 @@ def case_ascii(ctx, steps, scale):
     emit("ASCII source: UnambiguousDNAMers{31}, 1%% N, %d x 150-byte reads" % n_reads, nw, 1.0 * n_reads * length + 16 * nw, med, mn)
 
 
+def case_minimizers(ctx, steps, scale):
+    """Minimizers over one 1 Gbp 2-bit sequence: benchmark.jl's (K=8, W=20, step 20) and dense canonical (K=31, W=10, step 1)."""
+    length = int(1_000_000_000 * scale)
+    words = rand_words_2bit((length + 31) // 32, 19)
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), 1, None, None, length, words.numel(), 2, 0)
+    res = _abi.kmc_result()
+    for k, w, step, mode, name in ((8, 20, 20, FW, "forward, non-overlapping windows (test/benchmark.jl:96-119)"),
+                                   (31, 10, 1, CANON, "canonical, every window start")):
+        n = (length - (k + w - 1)) // step + 1
+        a = torch.empty(n, dtype=torch.int64, device="cuda")
+        idx = torch.empty(n, dtype=torch.int64, device="cuda")
+        out = _abi.kmc_out(a.data_ptr(), None, None, idx.data_ptr(), None, n, 0)
+        torch.cuda.synchronize()
+
+        def stepf():
+            st = ctx.lib.kmc_minimizers(ctx.handle, C.byref(desc), k, w, step, mode, 0, C.byref(out), C.byref(res))
+            if st != 0:
+                raise RuntimeError(ctx.lib.kmc_last_error(ctx.handle).decode())
+        med, mn = timed(ctx, stepf, steps)
+        emit("minimizers K=%d W=%d step=%d, %s, one %d bp sequence" % (k, w, step, name, length), n,
+             0.25 * length + 16 * n, med, mn, {"kmers_ordered_per_s": n * w / (med / 1e3)})
+        del a, idx
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="c3,c3long,c4,c5,modes")
@@ -246,7 +270,7 @@ def main():
     WARMUP = args.warmup
     torch.cuda.set_device(0)
     ctx = kc.Context(0)
-    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii}
+    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii, "minimizers": case_minimizers}
     for c in args.cases.split(","):
         table[c](ctx, args.steps, args.scale)
         torch.cuda.empty_cache()
