@@ -48,19 +48,13 @@ AsciiLuts make_luts()
 
 __constant__ uint8_t c_luts[3][256];
 
-// One thread per 32 bytes: 2 x u32 of 2-bit codes, 1 x u32 of "not a base" flags, 1 x u32 of error flags.
-__global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut,
-                                                           uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
-                                                           uint32_t *__restrict__ err, uint64_t n_groups)
+// 32 bytes -> 64 bits of 2-bit codes, 32 "not a base" flags, 32 error flags
+__device__ __forceinline__ void ascii_group(const uint8_t *__restrict__ bytes, uint64_t n_bytes, bool aligned, uint64_t g,
+                                            const uint8_t *s_lut, uint64_t &codes, uint32_t &fb, uint32_t &fe)
 {
-    __shared__ uint8_t s_lut[256];
-    s_lut[threadIdx.x] = c_luts[lut][threadIdx.x];
-    __syncthreads();
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_groups) return;
-    const uint64_t b0 = 32 * i;
+    const uint64_t b0 = 32 * g;
     uint32_t v[8];
-    if (b0 + 32 <= n_bytes && ((reinterpret_cast<uintptr_t>(bytes) & 15) == 0)) {
+    if (b0 + 32 <= n_bytes && aligned) {
         const uint4 *p = reinterpret_cast<const uint4 *>(bytes + b0);
         const uint4 x = __ldg(p), y = __ldg(p + 1);
         v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
@@ -77,8 +71,8 @@ __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__rest
             v[w] = t;
         }
     }
-    uint64_t codes = 0;
-    uint32_t fb = 0, fe = 0;
+    codes = 0;
+    fb = fe = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
 #pragma unroll
@@ -90,9 +84,49 @@ __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__rest
             fe |= (e >> 7) << sym;
         }
     }
-    reinterpret_cast<uint2 *>(rec)[i] = make_uint2(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32));
-    bad[i] = fb;
-    if (err) err[i] = fe;
+}
+
+// One thread per group of 32 bytes: 2 x u32 of 2-bit codes, 1 x u32 of "not a base" flags, 1 x u32 of
+// error flags and, fused through shared memory (+ a recomputed 5-group halo), the valid-start word.
+__global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut, int k,
+                                                           uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
+                                                           uint32_t *__restrict__ err, uint32_t *__restrict__ vstart,
+                                                           uint64_t n_groups, uint64_t n_vstart)
+{
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_bad[256 + 8];
+    s_lut[threadIdx.x] = c_luts[lut][threadIdx.x];
+    __syncthreads();
+    const bool aligned = (reinterpret_cast<uintptr_t>(bytes) & 15) == 0;
+    const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * 256;
+    {
+        const uint64_t g = g0 + threadIdx.x;
+        uint32_t fb = 0, fe = 0;
+        if (g < n_groups) {
+            uint64_t codes;
+            ascii_group(bytes, n_bytes, aligned, g, s_lut, codes, fb, fe);
+            reinterpret_cast<uint2 *>(rec)[g] = make_uint2(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32));
+            bad[g] = fb;
+            if (err) err[g] = fe;
+        }
+        s_bad[threadIdx.x] = fb;
+    }
+    if (threadIdx.x < kRecodeHalo) {
+        const uint64_t g = g0 + 256 + threadIdx.x;
+        uint32_t fb = 0, fe = 0;
+        uint64_t codes;
+        if (g < n_groups) ascii_group(bytes, n_bytes, aligned, g, s_lut, codes, fb, fe);
+        s_bad[256 + threadIdx.x] = fb;
+    }
+    __syncthreads();
+    const uint64_t g = g0 + threadIdx.x;
+    if (g < n_vstart) {
+        uint32_t a[6];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) a[d] = s_bad[threadIdx.x + d];
+        a[5] = 0;
+        vstart[g] = valid_start_word(a, k);
+    }
 }
 
 // UnambiguousKmers over ASCII reads EVERY byte of every sequence (even sequences shorter than K),
@@ -168,8 +202,8 @@ __global__ void __launch_bounds__(256) resolve_ascii_error_kernel(ExtractParams 
 
 } // namespace
 
-cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, uint32_t *rec, uint32_t *bad, uint32_t *err,
-                         uint64_t n_groups, cudaStream_t stream)
+cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k, uint32_t *rec, uint32_t *bad, uint32_t *err,
+                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream)
 {
     static bool uploaded[64] = {};
     int dev = 0;
@@ -181,8 +215,8 @@ cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, uint32
         if (e != cudaSuccess) return e;
         uploaded[dev] = true;
     }
-    if (n_groups == 0) return cudaSuccess;
-    ascii_recode_kernel<<<static_cast<unsigned>((n_groups + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, lut, rec, bad, err, n_groups);
+    ascii_recode_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, lut, k, rec, bad, err,
+                                                                                          vstart, n_groups, n_vstart);
     return cudaGetLastError();
 }
 

@@ -41,58 +41,42 @@ __device__ __forceinline__ uint32_t uncertain_word(uint64_t w)
     return static_cast<uint32_t>(n);
 }
 
-// One thread per PAIR of source words: 2 x u32 of 2-bit codes, 1 x u32 of uncertainty flags.
-__global__ void __launch_bounds__(256) recode_kernel(const uint64_t *__restrict__ words, uint64_t n_words,
-                                                     uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
-                                                     uint64_t n_pairs_padded)
+// One thread per PAIR of source words (= one group of 32 symbols): 2 x u32 of 2-bit codes, 1 x u32 of
+// uncertainty flags -- and, fused, the group's valid-start word: the block keeps its 256 flag words
+// (+ a 5-word halo recomputed from the neighbouring block's source words) in shared memory, so the
+// flags are never re-read from global memory and no second pass is launched.
+__global__ void __launch_bounds__(256) recode_vstart_kernel(const uint64_t *__restrict__ words, uint64_t n_words, int k,
+                                                            uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
+                                                            uint32_t *__restrict__ vstart, uint64_t n_groups,
+                                                            uint64_t n_vstart)
 {
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_pairs_padded) return;
-    const uint64_t w0 = (2 * i < n_words) ? __ldg(words + 2 * i) : 0x1111111111111111ull;
-    const uint64_t w1 = (2 * i + 1 < n_words) ? __ldg(words + 2 * i + 1) : 0x1111111111111111ull;
-    reinterpret_cast<uint2 *>(rec)[i] = make_uint2(recode_word(w0), recode_word(w1));
-    bad[i] = uncertain_word(w0) | (uncertain_word(w1) << 16);
-}
-
-// vstart word i: bit t set <=> no uncertain symbol in [32i + t, 32i + t + K).
-// Sliding-window OR of length K over the flag stream by doubling: A_1 = flags, A_2L = A_L | A_L >> L
-// while 2L <= K, then two windows of length L cover [P, P+K): A_L | A_L >> (K - L).  Branch-free
-// in the data (K is uniform), ~40 funnel shifts per 32 symbols.
-__global__ void __launch_bounds__(256) vstart_kernel(const uint32_t *__restrict__ bad, uint64_t n_bad, int k,
-                                                     uint32_t *__restrict__ vstart, uint64_t n_out)
-{
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
-    uint32_t a[6];
-#pragma unroll
-    for (int d = 0; d < 5; ++d) a[d] = (i + d < n_bad) ? __ldg(bad + i + d) : 0u; // 31 + K - 1 <= 158 < 160 bits
-    a[5] = 0;
-    int L = 1;
-#pragma unroll
-    for (int step = 0; step < 7; ++step) {
-        const int s = 1 << step; // current window length
-        if (2 * s <= k) {
-            if (s < 32) {
-#pragma unroll
-                for (int w = 0; w < 5; ++w) a[w] |= __funnelshift_r(a[w], a[w + 1], s);
-            } else if (s == 32) {
-#pragma unroll
-                for (int w = 0; w < 5; ++w) a[w] |= a[w + 1];
-            } else {
-#pragma unroll
-                for (int w = 0; w < 4; ++w) a[w] |= a[w + 2];
-            }
-            L = 2 * s;
+    __shared__ uint32_t s_bad[256 + 8];
+    const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * 256;
+    auto load = [&](uint64_t i) -> uint64_t { return i < n_words ? __ldg(words + i) : 0x1111111111111111ull; };
+    {
+        const uint64_t g = g0 + threadIdx.x;
+        uint32_t f = 0;
+        if (g < n_groups) {
+            const uint64_t w0 = load(2 * g), w1 = load(2 * g + 1);
+            reinterpret_cast<uint2 *>(rec)[g] = make_uint2(recode_word(w0), recode_word(w1));
+            f = uncertain_word(w0) | (uncertain_word(w1) << 16);
+            bad[g] = f;
         }
+        s_bad[threadIdx.x] = f;
     }
-    const int r = k - L; // 0 <= r < L, r < 64
-    uint32_t v = a[0];
-    if (r) {
-        const int b = r & 31;
-        if (r < 32) v |= __funnelshift_r(a[0], a[1], b);
-        else v |= b ? __funnelshift_r(a[1], a[2], b) : a[1];
+    if (threadIdx.x < kRecodeHalo) {
+        const uint64_t g = g0 + 256 + threadIdx.x;
+        s_bad[256 + threadIdx.x] = g < n_groups ? (uncertain_word(load(2 * g)) | (uncertain_word(load(2 * g + 1)) << 16)) : 0u;
     }
-    vstart[i] = ~v;
+    __syncthreads();
+    const uint64_t g = g0 + threadIdx.x;
+    if (g < n_vstart) {
+        uint32_t a[6];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) a[d] = s_bad[threadIdx.x + d];
+        a[5] = 0;
+        vstart[g] = valid_start_word(a, k);
+    }
 }
 
 // Turns the first offending flat window of a strict mode into what the reference throws on:
@@ -232,13 +216,12 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
 
     if (ascii) {
         const int lut = st->unambig ? 2 : ((flags & KMC_RNA) ? 1 : 0);
-        CU(ascii_recode(reinterpret_cast<const uint8_t *>(s->words), s->n_words, lut, rec, bad, err, nb, stream));
-    } else if (nb) {
-        recode_kernel<<<static_cast<unsigned>((nb + 255) / 256), 256, 0, stream>>>(s->words, s->n_words, rec, bad, nb);
+        CU(ascii_recode(reinterpret_cast<const uint8_t *>(s->words), s->n_words, lut, k, rec, bad, err, vstart, nb, nb + 2, stream));
+    } else {
+        recode_vstart_kernel<<<static_cast<unsigned>((nb + 2 + 255) / 256), 256, 0, stream>>>(s->words, s->n_words, k, rec, bad,
+                                                                                             vstart, nb, nb + 2);
         CU(cudaGetLastError());
     }
-    vstart_kernel<<<static_cast<unsigned>((nb + 2 + 255) / 256), 256, 0, stream>>>(bad, nb, k, vstart, nb + 2);
-    CU(cudaGetLastError());
 
     // strict modes lay the set out for the extraction kernel's G; UnambiguousKmers lays it out in
     // groups of 32 windows for the run-marking kernels (the extraction runs over the run list)

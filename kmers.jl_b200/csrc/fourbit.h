@@ -48,10 +48,46 @@ cudaError_t mark_runs(const ExtractParams &p, bool ragged, uint64_t *tile_valid,
 cudaError_t emit_runs(const ExtractParams &p, bool ragged, const uint64_t *tile_valid_off, const uint64_t *tile_runs_off,
                       uint64_t *run_sym, uint64_t *run_woff, uint64_t *run_ibase, cudaStream_t stream);
 
+// Valid-start bits of one group of 32 symbols from the flag words a[0..4] of this and the next four
+// groups (a[5] = 0): bit t set <=> no flagged symbol in [t, t + K).  Sliding-window OR of length K by
+// doubling -- A_1 = flags, A_2L = A_L | A_L >> L while 2L <= K, then two windows of length L cover
+// [P, P+K): A_L | A_L >> (K - L).  Branch-free in the data (K is uniform), ~40 funnel shifts.
+__device__ __forceinline__ uint32_t valid_start_word(uint32_t (&a)[6], int k)
+{
+    int L = 1;
+#pragma unroll
+    for (int step = 0; step < 7; ++step) {
+        const int s = 1 << step; // current window length
+        if (2 * s <= k) {
+            if (s < 32) {
+#pragma unroll
+                for (int w = 0; w < 5; ++w) a[w] |= __funnelshift_r(a[w], a[w + 1], s);
+            } else if (s == 32) {
+#pragma unroll
+                for (int w = 0; w < 5; ++w) a[w] |= a[w + 1];
+            } else {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) a[w] |= a[w + 2];
+            }
+            L = 2 * s;
+        }
+    }
+    const int r = k - L; // 0 <= r < L, r < 64
+    uint32_t v = a[0];
+    if (r) {
+        const int b = r & 31;
+        if (r < 32) v |= __funnelshift_r(a[0], a[1], b);
+        else v |= b ? __funnelshift_r(a[1], a[2], b) : a[1];
+    }
+    return ~v;
+}
+constexpr int kRecodeHalo = 5; // flag words beyond a group that its windows can reach (31 + K - 1 <= 158 bits)
+
 // ascii.cu: byte sources (AsciiEncode).  lut: 0 = strict DNAAlphabet{2}, 1 = strict RNAAlphabet{2},
 // 2 = the UnambiguousKmers skipping table.  n_groups = groups of 32 bytes.
-cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, uint32_t *rec, uint32_t *bad, uint32_t *err,
-                         uint64_t n_groups, cudaStream_t stream);
+// Writes rec / bad / err for the groups [0, n_groups) and the valid-start words [0, n_vstart).
+cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k, uint32_t *rec, uint32_t *bad, uint32_t *err,
+                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream);
 cudaError_t ascii_first_error_seq(const ExtractParams &p, const uint32_t *err, const uint64_t *seq_len, uint64_t uniform_len,
                                   unsigned long long *err_seq, int sm_count, cudaStream_t stream);
 cudaError_t ascii_resolve_error(const ExtractParams &p, const uint8_t *bytes, const uint32_t *err, const uint64_t *seq_len,

@@ -41,8 +41,25 @@ struct Chunk {
 
 } // namespace
 
+static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t mode, uint32_t flags, const kmc_out *ho,
+                            kmc_result *result);
+
 extern "C" int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t mode, uint32_t flags,
                                     const kmc_out *ho, kmc_result *result)
+{
+    const int32_t st = run_pipeline(ctx, hs, k, mode, flags, ho, result);
+    if (st != KMC_OK && ctx) {
+        // never return while copies into the caller's buffers are still in flight
+        const std::string keep = ctx->last_error;
+        for (int i = 0; i < 3; ++i)
+            if (ctx->pipe_streams[i]) cudaStreamSynchronize(ctx->pipe_streams[i]);
+        ctx->last_error = keep;
+    }
+    return st;
+}
+
+static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t mode, uint32_t flags, const kmc_out *ho,
+                            kmc_result *result)
 {
     int32_t st = check_common(ctx, hs, k);
     if (st) return st;

@@ -507,6 +507,45 @@ class UnambiguousKmers(_KmerIterator):
         return e.kmers, e.index
 
 
+class SpacedKmers(_KmerIterator):
+    """Every J-th k-mer: SpacedKmers{A,K,J} (src/iterators/SpacedKmers.jl:23-44), positions 1, 1+J, ...
+    On the device this is kmc_minimizers with a window of ONE k-mer and step J (the closed form makes
+    the stride free).  2-bit LongSequence sources, K <= 32.  collect() -> u64[n, 1]."""
+    mode = KMC_FW
+
+    def __init__(self, A: Alphabet, K: int, J: int, seq: LongSequence):
+        super().__init__(A, K, seq)
+        if not isinstance(J, (int, np.integer)) or isinstance(J, bool):
+            raise TypeError("J must be an Int")
+        if J < 1:
+            raise ValueError("J must be at least 1")
+        if self.is_ascii or seq.alphabet.bits != 2:
+            raise NotImplementedError("SpacedKmers is accelerated for 2-bit LongSequence sources")
+        self.J = J
+
+    def __len__(self):
+        # SpacedKmers.jl:40-44
+        L = len(self.seq)
+        return 0 if L < self.K else (L - self.K) // self.J + 1
+
+    def collect(self, **kw) -> np.ndarray:
+        km, _, _, _ = minimizers(ReadSet.single(self.seq), self.K, 1, self.J, **kw)
+        return km.reshape(-1, 1)
+
+
+def SpacedDNAMers(K, J, seq):
+    return SpacedKmers(DNAAlphabet2, K, J, seq)
+
+
+def SpacedRNAMers(K, J, seq):
+    return SpacedKmers(RNAAlphabet2, K, J, seq)
+
+
+def each_codon(seq: LongSequence):
+    """each_codon(s) = SpacedKmers{A,3,3}(s) (SpacedKmers.jl:57-81)."""
+    return SpacedKmers(seq.alphabet if seq.alphabet.bits == 2 else DNAAlphabet2, 3, 3, seq)
+
+
 def FwDNAMers(K, seq):
     return FwKmers(DNAAlphabet2, K, seq)
 

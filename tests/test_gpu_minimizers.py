@@ -81,3 +81,17 @@ def test_argument_checks(kc):
         kc.minimizers(rs, 33, 5)
     with pytest.raises(kc.KmersCUDAError):
         kc.minimizers(rs, 31, 40)
+
+
+def test_spaced_kmers(kc):
+    """SpacedKmers{A,K,J} (/root/reference/src/iterators/SpacedKmers.jl:13-21, 57-81) = windows of one k-mer, step J."""
+    rows = lambda a: [tuple(int(v) for v in r) for r in a]
+    assert rows(kc.SpacedDNAMers(3, 2, kc.LongDNA2("AGCGTATA")).collect()) == [kt.kmer_limbs(x) for x in ("AGC", "CGT", "TAT")]
+    assert rows(kc.each_codon(kc.LongDNA2("TGACGATCGAC")).collect()) == [kt.kmer_limbs(x) for x in ("TGA", "CGA", "TCG")]
+    rng = np.random.default_rng(2)
+    for k, j in ((7, 7), (31, 5), (32, 1), (3, 3), (1, 4)):
+        for n in (0, k - 1, k, k + j - 1, k + j, 1000):
+            s = kt.random_dna(rng, max(n, 0))
+            it = kc.SpacedDNAMers(k, j, kc.LongDNA2(s))
+            want = [kt.kmer_limbs(s[i:i + k]) for i in range(0, len(s) - k + 1, j)]
+            assert rows(it.collect()) == want and len(it) == len(want)
