@@ -281,6 +281,15 @@ int32_t kmc_ctx_create(int32_t device, kmc_ctx **out)
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) {
+        // temporaries of the binned bucket count come from the stream-ordered pool: keep them cached
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&ctx->pipe_streams[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_begin);
@@ -520,11 +529,50 @@ int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t 
     result->n_written = L.total;
     if (L.total == 0) return KMC_OK;
     ExtractParams p = base_params(seqs, k, ge, L, 0);
-    p.bucket_table = table;
     p.bucket_shift = static_cast<uint32_t>(64 - bucket_bits);
-    ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKETS, true, !L.uniform_len);
-    if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
-    CU(fn(p, ctx->sm_count, stream));
+    // Tables beyond L2 (B = 28 is 1 GiB): write the bucket ids out, bin them by their high bits, apply
+    // bin after bin (buckets.cu).  Needs 8 bytes per k-mer of temporary memory; without it (or for
+    // L2-sized tables) the kernel increments the table directly.
+    const uint64_t table_bytes = 4ull << bucket_bits;
+    bool binned = table_bytes > (96ull << 20) && bucket_bits <= 32;
+    uint32_t *ids = nullptr, *tmp_ids = nullptr;
+    uint64_t *matrix = nullptr, *offs = nullptr, *scan_tmp = nullptr;
+    const uint64_t n_ids = (L.items + 1) * static_cast<uint64_t>(ge.g); // flat windows, rounded up to whole groups
+    if (binned) {
+        const uint64_t cells = (static_cast<uint64_t>(1) << binned_count_bin_bits(bucket_bits)) * binned_count_blocks(n_ids);
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ids), round_up(n_ids * 4, 256), stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&tmp_ids), round_up(n_ids * 4, 256), stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&matrix), (cells + 1) * 8, stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&offs), (cells + 2) * 8, stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&scan_tmp), (scan_tmp_elems(cells) + 1) * 8, stream);
+        if (e != cudaSuccess) { // not enough memory for the binned path: fall back to direct increments
+            (void)cudaGetLastError();
+            for (void *q : {static_cast<void *>(ids), static_cast<void *>(tmp_ids), static_cast<void *>(matrix),
+                            static_cast<void *>(offs), static_cast<void *>(scan_tmp)})
+                if (q) cudaFreeAsync(q, stream);
+            binned = false;
+        }
+    }
+    if (binned) {
+        // the flat id array is exactly the flat window array: every flat index < L.total is written
+        // once (slots of partial groups that are not windows are not written and not binned)
+        p.out_a = reinterpret_cast<uint64_t *>(ids);
+        p.vec_ok = 1;
+        ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKET_IDS, true, !L.uniform_len);
+        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+        CU(fn(p, ctx->sm_count, stream));
+        CU(binned_count(ids, L.total, bucket_bits, table, tmp_ids, matrix, offs, scan_tmp, ctx->sm_count, stream));
+        for (void *q : {static_cast<void *>(ids), static_cast<void *>(tmp_ids), static_cast<void *>(matrix),
+                        static_cast<void *>(offs), static_cast<void *>(scan_tmp)})
+            CU(cudaFreeAsync(q, stream));
+    } else {
+        // a table that fits L2 is pulled into it first: increments that miss L2 serialise at DRAM latency
+        if (table_bytes <= (96ull << 20)) CU(warm_table(table, 1ull << bucket_bits, ctx->sm_count, stream));
+        p.bucket_table = table;
+        ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKETS, true, !L.uniform_len);
+        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+        CU(fn(p, ctx->sm_count, stream));
+    }
     CU(cudaEventRecord(ctx->ev_k1, stream));
     CU(cudaStreamSynchronize(stream));
     CU(cudaEventElapsedTime(&result->kernel_ms, ctx->ev_k0, ctx->ev_k1));

@@ -20,7 +20,9 @@ namespace kmc {
 
 enum : int { MODE_FW = 0, MODE_FWRV = 1, MODE_CANON = 2 };
 // where the k-mers go: the output streams, or (north_star extension) a hash-bucket count table
-enum : int { SINK_STREAMS = 0, SINK_BUCKETS = 1 };
+// SINK_BUCKETS increments table[bucket] directly; SINK_IDS writes the 32-bit bucket id of every window
+// to a flat array instead (first pass of the binned count for tables that do not fit L2, buckets.cu)
+enum : int { SINK_STREAMS = 0, SINK_BUCKETS = 1, SINK_IDS = 2 };
 
 constexpr int kBlockThreads = 256;
 constexpr int kTileIters = 8;                                // work items per thread per tile
@@ -304,6 +306,21 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
                 if (HASH) h[j] = fx_hash<N>(a[j], 0);
             }
 
+            if (SINK == SINK_IDS) {
+                uint32_t *ids = reinterpret_cast<uint32_t *>(p.out_a) + q * G;
+                if (G == 8 && jlo == 0 && jhi == G && p.vec_ok) {
+                    uint64_t w[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        w[t] = (h[(2 * t) % G] >> p.bucket_shift) | ((h[(2 * t + 1) % G] >> p.bucket_shift) << 32);
+                    st_v4(reinterpret_cast<uint64_t *>(ids), w[0], w[1], w[2], w[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+                        if (j >= jlo && j < jhi) ids[j] = static_cast<uint32_t>(h[j] >> p.bucket_shift);
+                }
+                goto next_item;
+            }
             if (SINK == SINK_BUCKETS) {
                 // canonical k-mer -> fx_hash -> bucket -> counter (no k-mer stream is written)
 #pragma unroll
@@ -396,6 +413,7 @@ ExtractLaunchFn get_extract_launcher_n3(int nx, int mode, bool hash, bool ragged
 ExtractLaunchFn get_extract_launcher_n4(int nx, int mode, bool hash, bool ragged);
 // mode == -1 selects the bucket-count sink (canonical + fx_hash -> table)
 constexpr int MODE_BUCKETS = -1;
+constexpr int MODE_BUCKET_IDS = -2; // canonical + fx_hash -> flat array of 32-bit bucket ids
 
 // One translation unit per N instantiates its 3 NX variants x 3 modes x hash x locator.
 #define KMC_DEFINE_LAUNCHER_TABLE(FN, N)                                                            \
@@ -416,6 +434,9 @@ constexpr int MODE_BUCKETS = -1;
         case MODE_BUCKETS:                                                                          \
             return ragged ? &launch_extract<N, NX, MODE_CANON, true, true, SINK_BUCKETS>            \
                           : &launch_extract<N, NX, MODE_CANON, true, false, SINK_BUCKETS>;          \
+        case MODE_BUCKET_IDS:                                                                       \
+            return ragged ? &launch_extract<N, NX, MODE_CANON, true, true, SINK_IDS>                \
+                          : &launch_extract<N, NX, MODE_CANON, true, false, SINK_IDS>;              \
         case MODE_FW: return pick_hash_##N<NX, MODE_FW>(hash, ragged);                              \
         case MODE_FWRV: return pick_hash_##N<NX, MODE_FWRV>(hash, ragged);                          \
         case MODE_CANON: return pick_hash_##N<NX, MODE_CANON>(hash, ragged);                        \

@@ -50,6 +50,13 @@ cudaError_t group_slots(const uint64_t *win_off, uint64_t n, int g, uint64_t *sl
 cudaError_t tile_first_reads(const uint64_t *item_off, uint64_t n_seqs, uint64_t tile_items, uint64_t n_tiles,
                              uint64_t *tile_first, cudaStream_t stream);
 
+// buckets.cu: histogram of n bucket ids into a table too large for L2, by binning the ids first
+int binned_count_bin_bits(int bucket_bits);
+uint64_t binned_count_blocks(uint64_t n);
+cudaError_t warm_table(const uint32_t *table, uint64_t n_counters, int sm_count, cudaStream_t stream);
+cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint32_t *table, uint32_t *binned, uint64_t *matrix,
+                         uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream);
+
 // misc_kernels.cu -----------------------------------------------------------------------------
 cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,
                            cudaStream_t stream);

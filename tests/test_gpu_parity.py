@@ -334,6 +334,21 @@ def test_host_sequences_device_outputs_and_digest(kc, ctx):
 
 
 # ---------------------------------------------------------------------- bucket count table
+def test_bucket_count_binned_ragged(kc):
+    """Tables beyond L2 take the binned path (ids -> bins -> apply); ragged set, one- and two-limb k-mers."""
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 300, size=30_000).tolist()
+    seqs, words, off, ln = make_ragged(rng, [int(x) for x in lens])
+    rs = kc.ReadSet(2, words, len(lens), seq_word_offset=off, seq_len=ln)
+    for k, bits in ((31, 26), (63, 27), (5, 30), (100, 25)):
+        _, _, h, _ = ko.batch_iterate(words, len(lens), k, ko.CANON, word_off=off, seq_len=ln, want_hash=True)
+        table, n, _ = kc.bucket_count(rs, k, bits)
+        assert n == h.size
+        idx, cnt = np.unique((h >> np.uint64(64 - bits)).astype(np.int64), return_counts=True)
+        assert int(table.sum(dtype=np.int64)) == h.size
+        assert np.array_equal(np.nonzero(table)[0], idx) and np.array_equal(table[idx], cnt.astype(np.uint32))
+
+
 @pytest.mark.parametrize("k,bits", [(31, 20), (63, 12), (15, 28)])
 def test_bucket_count(kc, k, bits):
     rng = np.random.default_rng(k)
