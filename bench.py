@@ -327,12 +327,14 @@ def run_ours(args, rank, local_rank, world):
         # -- the same call with both streams written to pinned host memory
         del d_canon, d_hash
         torch.cuda.empty_cache()
+        # 16 bytes of pinned host memory per k-mer: the full 19.2 GB on one GPU, a 1/world share per rank
+        # otherwise (all ranks share one host's memory and one root complex; the number is PCIe-bound anyway)
+        e2e_reads = max(1, n_reads // world)
         try:
-            h_canon = ctx.pinned(n_kmers * 8, np.uint64)
-            h_hash = ctx.pinned(n_kmers * 8, np.uint64)
-            e2e_reads = n_reads
+            h_canon = ctx.pinned(e2e_reads * WPR * 8, np.uint64)
+            h_hash = ctx.pinned(e2e_reads * WPR * 8, np.uint64)
         except kc.KmersCUDAError:
-            e2e_reads = max(1, n_reads // 10)
+            e2e_reads = max(1, e2e_reads // 10)
             h_canon = ctx.pinned(e2e_reads * WPR * 8, np.uint64)
             h_hash = ctx.pinned(e2e_reads * WPR * 8, np.uint64)
         hdesc2 = _abi.kmc_seqs(pinned_in.ctypes.data, e2e_reads * STRIDE, e2e_reads, None, None, READ_LEN, STRIDE, 2, 0)
