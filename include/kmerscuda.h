@@ -160,6 +160,14 @@ int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *host_seqs, int32_t k, int
 int32_t kmc_fx_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n_limbs, uint64_t h0,
                     uint64_t *out);
 
+/* Base.hash.(v, h0) (src/kmer.jl:206: hash(x.data, h ⊻ K)) over n k-mers of K symbols and n_limbs limbs
+ * in device memory, with the tuple / UInt64 hashing of Julia 1.10 and 1.11 (hash_64_64).  Pinned by
+ * the reference's documented hash(mer"UGCUGUAC"r) == 0xe5057d38c8907b22 (docs/src/hashing.md:18-20);
+ * the reference warns that values change between Julia minors (hashing.md:10-13), so a binding must
+ * check that value against its own Julia before using this entry point. */
+int32_t kmc_base_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n_limbs, int32_t k, uint64_t h0,
+                      uint64_t *out);
+
 /* north_star extension (not in the reference): histogram of
  * fx_hash(canonical k-mer) >> (64 - bucket_bits) over the set, accumulated into
  * table[2^bucket_bits] (u32, device, caller-zeroed).  Tables of several GPUs are summed

@@ -18,7 +18,7 @@ using Kmers
 using Kmers: FwKmers, FwRvIterator, CanonicalKmers, UnambiguousKmers, Kmer, derive_type
 using Libdl
 
-export fx_hash_device, extract, set_library!
+export fx_hash_device, hash_device, extract, set_library!
 
 # ---------------------------------------------------------------------------------------------
 # library handle
@@ -280,6 +280,39 @@ function fx_hash_device(v::Vector{Kmer{A, K, N}}, h::UInt64 = UInt64(0); ctx::Co
 end
 
 # Base.hash(kmer, h) = hash(kmer.data, h ⊻ K) (src/kmer.jl:206) depends on the Julia version's tuple
-# hash and is deliberately NOT reimplemented on the device: call Base.hash on the returned k-mers.
+# and integer hashing.  libkmerscuda implements the Julia 1.10 / 1.11 definition (kmc_base_hash); it
+# reproduces the reference's documented hash(mer"UGCUGUAC"r) == 0xe5057d38c8907b22
+# (docs/src/hashing.md:18-20).  Whether THIS Julia agrees is checked once, on the host, before the
+# device path is trusted; otherwise Base.hash is evaluated on the returned k-mers by Julia itself.
+const BASE_HASH_ON_DEVICE = Ref{Union{Nothing, Bool}}(nothing)
+function base_hash_matches()
+    if BASE_HASH_ON_DEVICE[] === nothing
+        probe = [mer"UGCUGUAC"r, mer"TAGCTAGGACATTTTAAACCCGGGTAGCTAGGACATTTTAAACC"d]
+        BASE_HASH_ON_DEVICE[] = _hash_device(probe, UInt(0)) == hash.(probe)
+    end
+    return BASE_HASH_ON_DEVICE[]::Bool
+end
+
+function _hash_device(v::Vector{Kmer{A, K, N}}, h::UInt; ctx::Context = default_context()) where {A, K, N}
+    out = Vector{UInt64}(undef, length(v))
+    isempty(v) && return out
+    GC.@preserve v out begin
+        dk, dout = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(v), dk)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(out), dout)
+        ccall((:kmc_upload, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, dk[], v, sizeof(v))
+        st = ccall((:kmc_base_hash, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Int32, Int32, UInt64, Ptr{Cvoid}),
+            ctx.handle, dk[], length(v), N, K, h, dout[])
+        ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, out, dout[], sizeof(out))
+        ccall((:kmc_free, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, dk[])
+        ccall((:kmc_free, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, dout[])
+        st == KMC_OK || error("libkmerscuda status $st: $(last_error(ctx))")
+    end
+    return out
+end
+
+"`hash.(v, h)` (Base.hash of k-mers): on the device when this Julia's hashing matches, else on the host."
+hash_device(v::Vector{<:Kmer}, h::UInt = UInt(0); ctx::Context = default_context()) =
+    base_hash_matches() ? _hash_device(v, h; ctx) : hash.(v, h)
 
 end # module

@@ -504,6 +504,17 @@ int32_t kmc_fx_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n_l
     return KMC_OK;
 }
 
+int32_t kmc_base_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n_limbs, int32_t k, uint64_t h0, uint64_t *out)
+{
+    if (!ctx) return KMC_E_BAD_ARG;
+    if (n_limbs < 0 || n_limbs > 4) return fail(ctx, KMC_E_BAD_ARG, "n_limbs must be in 0..4");
+    if (k < 0) return fail(ctx, KMC_E_BAD_K, "K must not be negative");
+    if (n && (!out || (n_limbs && !kmers))) return fail(ctx, KMC_E_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_base_hash(kmers, n, n_limbs, h0 ^ static_cast<uint64_t>(k), out, ctx->sm_count, ctx->stream));
+    return KMC_OK;
+}
+
 int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits, uint32_t *table,
                          kmc_result *result)
 {

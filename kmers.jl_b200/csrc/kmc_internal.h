@@ -62,6 +62,8 @@ cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint6
                            cudaStream_t stream);
 // acc[0] ^= xor of the words, acc[1] += their sum (zero = clear acc first)
 cudaError_t launch_digest(const uint64_t *p, uint64_t n, uint64_t *acc, int sm_count, cudaStream_t stream, bool zero = true);
+cudaError_t launch_base_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h, uint64_t *out, int sm_count,
+                             cudaStream_t stream);
 cudaError_t launch_store_probe(void *dptr, uint64_t bytes, int sm_count, cudaStream_t stream);
 
 } // namespace kmc

@@ -41,6 +41,54 @@ cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint6
     return cudaGetLastError();
 }
 
+// Base.hash(x::Kmer, h) = hash(x.data, h ⊻ K) (src/kmer.jl:206) with Julia 1.10 / 1.11's Base:
+//   hash(::Tuple{}, h) = h + 0x77cfa1eef01bca90 ; hash(t::Tuple, h) = hash(t[1], hash(tail(t), h))   (tuple.jl)
+//   hash(x::UInt64, h) = hash_64_64(x) - 3h                                                          (hashing.jl)
+// Pinned by the reference's documented value hash(mer"UGCUGUAC"r) == 0xe5057d38c8907b22
+// (docs/src/hashing.md:18-20).  Julia >= 1.12 hashes integers differently; the Julia binding checks
+// that value at load time before it trusts this kernel.
+__device__ __forceinline__ uint64_t hash_64_64(uint64_t a)
+{
+    a = ~a + (a << 21);
+    a = a ^ (a >> 24);
+    a = a + (a << 3) + (a << 8);
+    a = a ^ (a >> 14);
+    a = a + (a << 2) + (a << 4);
+    a = a ^ (a >> 28);
+    a = a + (a << 31);
+    return a;
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) base_hash_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t h,
+                                                        uint64_t *__restrict__ out)
+{
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t acc = h + 0x77cfa1eef01bca90ull; // the empty tail
+#pragma unroll
+        for (int j = N - 1; j >= 0; --j) acc = hash_64_64(__ldg(kmers + i * N + j)) - 3 * acc;
+        st_u64(out + i, acc);
+    }
+}
+
+cudaError_t launch_base_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h, uint64_t *out, int sm_count,
+                             cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    uint64_t want = (n + 255) / 256;
+    unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 16 ? want : static_cast<uint64_t>(sm_count) * 16);
+    switch (n_limbs) {
+    case 0: base_hash_kernel<0><<<grid, 256, 0, stream>>>(kmers, n, h, out); break;
+    case 1: base_hash_kernel<1><<<grid, 256, 0, stream>>>(kmers, n, h, out); break;
+    case 2: base_hash_kernel<2><<<grid, 256, 0, stream>>>(kmers, n, h, out); break;
+    case 3: base_hash_kernel<3><<<grid, 256, 0, stream>>>(kmers, n, h, out); break;
+    case 4: base_hash_kernel<4><<<grid, 256, 0, stream>>>(kmers, n, h, out); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 // XOR / wrapping-sum fingerprint of a u64 stream (kmc_digest): 128-bit loads, warp shuffle +
 // shared-memory reduction, one pair of atomics per block.
 __global__ void __launch_bounds__(256) digest_kernel(const uint64_t *__restrict__ p, uint64_t n,

@@ -11,7 +11,7 @@ from .api import (  # noqa: E402
     Alphabet, CanonicalDNAMers, CanonicalKmers, CanonicalRNAMers, Context, DeviceBuffer, DeviceReadSet,
     DNAAlphabet2, DNAAlphabet4, EncodeError, Extracted, FwDNAMers, FwKmers, FwRNAMers, FwRvDNAIterator,
     FwRvIterator, KmersCUDAError, LongDNA2, LongDNA4, LongSequence, ReadSet, RNAAlphabet2, RNAAlphabet4,
-    UnambiguousDNAMers, UnambiguousKmers, UnambiguousRNAMers, bucket_count, default_context, extract, fx_hash,
+    UnambiguousDNAMers, UnambiguousKmers, UnambiguousRNAMers, base_hash, bucket_count, default_context, extract, fx_hash,
     SpacedDNAMers, SpacedKmers, SpacedRNAMers, each_codon, minimizers, n_limbs)
 from ._abi import (KMC_AOS, KMC_CANON, KMC_FW, KMC_FWRV, KMC_HASH_FX, KMC_MAX_K, KMC_NO_SYNC,  # noqa: E402
                    KMC_OUT_DEVICE, KMC_UNAMBIG)

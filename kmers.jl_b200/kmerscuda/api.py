@@ -591,6 +591,23 @@ def fx_hash(kmers: np.ndarray, h: int = 0, ctx: Optional[Context] = None) -> np.
     return out
 
 
+def base_hash(kmers: np.ndarray, K: int, h: int = 0, ctx: Optional[Context] = None) -> np.ndarray:
+    """Base.hash.(kmers, h) of Kmer{A,K,N} values (src/kmer.jl:206), Julia 1.10 / 1.11 hashing; `kmers` is u64[n, N]."""
+    ctx = ctx or default_context()
+    km = np.ascontiguousarray(kmers, dtype=np.uint64)
+    if km.ndim == 1:
+        km = km.reshape(-1, 1)
+    n, N = km.shape
+    dk = ctx.to_device(km) if km.size else None
+    do = ctx.alloc(max(n, 1) * 8)
+    ctx._check(ctx.lib.kmc_base_hash(ctx.handle, dk.ptr if dk else None, n, N, K, h, do.ptr))
+    out = do.download(np.uint64, n)
+    if dk:
+        dk.free()
+    do.free()
+    return out
+
+
 def minimizers(rs, K: int, W: int, step: int = 1, *, canonical: bool = False, hash: bool = False,
                ctx: Optional[Context] = None):
     """Minimizers under the fx_hash ordering (docs/src/replacements.md:28-58): for every window start

@@ -624,3 +624,35 @@ int ko_ascii_unambiguous(const uint8_t *src, uint64_t len, int K, uint64_t *out_
         remaining = 1;
     }
 }
+
+
+/* ======================================================================
+ * Base.hash(x::Kmer, h::UInt) = hash(x.data, h ⊻ (ksize(typeof(x)) % UInt))   -- src/kmer.jl:206.
+ * hash(::NTuple{N,UInt64}, ::UInt) is Julia Base, not the reference; restated for Julia 1.10 / 1.11:
+ *   tuple.jl     hash(::Tuple{}, h) = h + tuplehash_seed (0x77cfa1eef01bca90 on 64-bit)
+ *                hash(t::Tuple, h)  = hash(t[1], hash(tail(t), h))
+ *   hashing.jl   hash(x::UInt64, h) = hash_uint64(x) - 3h ; hash_uint64 = hash_64_64 (below)
+ * Pinned by the value the reference documents: hash(mer"UGCUGUAC"r) == 0xe5057d38c8907b22
+ * (docs/src/hashing.md:18-20).  Julia >= 1.12 changed integer hashing (the reference warns,
+ * hashing.md:10-13): those versions are NOT covered.
+ * ====================================================================== */
+INL u64 jl_hash_64_64(u64 a)
+{
+    a = ~a + (a << 21);
+    a = a ^ (a >> 24);
+    a = a + (a << 3) + (a << 8);
+    a = a ^ (a >> 14);
+    a = a + (a << 2) + (a << 4);
+    a = a ^ (a >> 28);
+    a = a + (a << 31);
+    return a;
+}
+
+void ko_base_hash(const uint64_t *kmers, uint64_t n, int N, int K, uint64_t h0, uint64_t *out)
+{
+    for (u64 i = 0; i < n; ++i) {
+        u64 acc = (h0 ^ (u64)K) + 0x77cfa1eef01bca90ull;
+        for (int j = N - 1; j >= 0; --j) acc = jl_hash_64_64(kmers[i * (u64)N + j]) - 3 * acc;
+        out[i] = acc;
+    }
+}

@@ -71,6 +71,8 @@ def lib():
                                        C.c_void_p, _u64p, _u64p, _u64p]
         L.ko_ascii_unambiguous.restype = C.c_int
         L.ko_ascii_unambiguous.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, _u64p, _u64p, _u64p]
+        L.ko_base_hash.restype = None
+        L.ko_base_hash.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
         L.ko_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -189,6 +191,16 @@ def fx_hash(kmers, h0=0):
         km = km.reshape(-1, 1)
     out = np.zeros(km.shape[0], dtype=np.uint64)
     lib().ko_fx_hash(_ptr(km), km.shape[0], km.shape[1], h0, _ptr(out))
+    return out
+
+
+def base_hash(kmers, k, h0=0):
+    """Base.hash.(kmers, h0) (src/kmer.jl:206), Julia 1.10 / 1.11 tuple + UInt64 hashing."""
+    km = np.ascontiguousarray(kmers, dtype=np.uint64)
+    if km.ndim == 1:
+        km = km.reshape(-1, 1)
+    out = np.zeros(km.shape[0], dtype=np.uint64)
+    lib().ko_base_hash(_ptr(km) if km.size else None, km.shape[0], km.shape[1], k, h0, _ptr(out))
     return out
 
 

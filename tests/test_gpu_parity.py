@@ -241,6 +241,19 @@ def test_standalone_fx_hash(kc):
             assert np.array_equal(kc.fx_hash(km, h0), ko.fx_hash(km, h0))
 
 
+def test_base_hash(kc):
+    """Base.hash.(v) (src/kmer.jl:206, Julia 1.10 / 1.11 hashing): the documented value and the oracle."""
+    for e in KATS["base_hash"]:
+        s = dna(e["kmer"])
+        got = kc.base_hash(np.array([kt.kmer_limbs(s)], dtype=np.uint64), len(s))
+        assert int(got[0]) == int(e["hash"], 16)
+    rng = np.random.default_rng(10)
+    for N, K in ((1, 1), (1, 31), (2, 63), (3, 96), (4, 128)):
+        km = rng.integers(0, 2**64, size=(10_000, N), dtype=np.uint64)
+        for h0 in (0, 7, 0xDEADBEEF12345678):
+            assert np.array_equal(kc.base_hash(km, K, h0), ko.base_hash(km, K, h0))
+
+
 # --------------------------------------------------------------------- pipelined host path
 @pytest.mark.parametrize("k", [31, 63])
 def test_host_path_single_sequence_chunked(kc, k):

@@ -310,3 +310,41 @@ def test_ascii_oracle_against_reference_examples_and_naive():
     with pytest.raises(ko.AmbiguousError):
         ko.ascii_iterate("ACGT", 2, ko.FW, rna=True)  # T is not an RNAAlphabet{2} letter
     assert ko.ascii_unambiguous("ACGTUacgtu", 2)[0].shape[0] == 9  # the skipping table takes both
+
+
+def test_base_hash_documented_value_and_invariants():
+    """Base.hash (src/kmer.jl:206) restated for Julia 1.10 / 1.11, pinned by the reference's documented
+    value (docs/src/hashing.md:18-20) and its invariants (test/runtests.jl:214-238, hashing.md:25-40)."""
+    import kmertools as kt
+    from oracle import oracle as ko
+    for e in KATS["base_hash"]:
+        s = e["kmer"].replace("U", "T")
+        got = ko.base_hash(np.array([kt.kmer_limbs(s)], dtype=np.uint64), len(s))
+        assert int(got[0]) == int(e["hash"], 16)
+    # same bit pattern, different K -> different hash (mer"TAG"d vs mer"AAAAAAATAG"d, hashing.md:27-36)
+    a = ko.base_hash(np.array([kt.kmer_limbs("TAG")], dtype=np.uint64), 3)
+    b = ko.base_hash(np.array([kt.kmer_limbs("AAAAAAATAG")], dtype=np.uint64), 10)
+    assert kt.kmer_limbs("TAG") == kt.kmer_limbs("AAAAAAATAG") and int(a[0]) != int(b[0])
+    # independent python evaluation of the recursion for multi-limb k-mers
+    M = (1 << 64) - 1
+
+    def h64(x):
+        x = (~x + (x << 21)) & M
+        x ^= x >> 24
+        x = (x + (x << 3) + (x << 8)) & M
+        x ^= x >> 14
+        x = (x + (x << 2) + (x << 4)) & M
+        x ^= x >> 28
+        return (x + (x << 31)) & M
+
+    rng = np.random.default_rng(1)
+    for N, K in ((1, 31), (2, 63), (3, 70), (4, 128)):
+        km = rng.integers(0, 2**64, size=(50, N), dtype=np.uint64)
+        for h0 in (0, 12345):
+            want = []
+            for row in km.tolist():
+                acc = ((h0 ^ K) + 0x77CFA1EEF01BCA90) & M
+                for x in reversed(row):
+                    acc = (h64(x) - 3 * acc) & M
+                want.append(acc)
+            assert ko.base_hash(km, K, h0).tolist() == want
