@@ -311,7 +311,6 @@ int32_t kmc_ctx_destroy(kmc_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->host_small) cudaFreeHost(ctx->host_small);
     if (ctx->dev_small) cudaFree(ctx->dev_small);
     for (int i = 0; i < 3; ++i) {

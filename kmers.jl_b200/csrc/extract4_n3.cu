@@ -1,6 +1,7 @@
-// 4-bit source (FourToTwo) instantiations for N = 3 limbs: strict Fw/FwRv/Canonical with the
-// uncertain-symbol check.
-#include "extract_kernels.cuh"
+// 4-bit / ASCII source (FourToTwo, AsciiEncode) instantiations for N = 3 limbs: strict
+// Fw/FwRv/Canonical with the uncertain-symbol check, and the ordered compaction of UnambiguousKmers.
+#include "compact_kernels.cuh"
 namespace kmc {
 KMC_DEFINE_FOURBIT_TABLES(get_strict4_launcher_n3, 3)
+KMC_DEFINE_COMPACT_TABLE(get_compact_launcher_n3, 3)
 }

@@ -45,6 +45,9 @@ struct ExtractParams {
     uint64_t wpr;        // windows per read
     uint64_t gprm;       // group slots per read
     uint64_t it_dq, it_dr; // divmod(kBlockThreads, gprm): per-iteration advance of (r, gi)
+    uint64_t it_df0;       // it_dq * wpr: per-iteration advance of the read's first flat window
+    uint64_t read_bits;    // stride_units * unit_bits: stream bits from one read to the next (uniform offsets)
+    uint64_t it_dbits;     // it_dq * read_bits
     // ragged locator
     const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
     const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
@@ -112,7 +115,8 @@ struct TileCursor {
     uint64_t r_first;     // ragged: read owning the tile's first item
     // derived for the current item
     uint64_t f0, wcount;  // flat index of the read's first window, its window count
-    uint64_t unit_off;    // where the read starts in the stream (units of p.unit_bits)
+    uint64_t unit_off;    // ragged: where the read starts in the stream (units of p.unit_bits)
+    uint64_t ubit;        // the same in bits; uniform offsets: kept incrementally (no multiplies per item)
     uint64_t seq_ibase;   // p.seq_index_base[r] (0 without it)
     uint64_t q;           // aligned flat group of this item
     int64_t wbase;        // window (within the read) of slot 0, in (-G, wcount)
@@ -146,6 +150,8 @@ struct TileCursor {
                 gi -= static_cast<uint64_t>(d) * p.gprm;
                 r += d;
             }
+            f0 = r * p.wpr;
+            ubit = r * p.read_bits;
         } else {
             r_first = __ldg(p.tile_first + blockIdx.x);
             const uint64_t r_last = __ldg(p.tile_first + blockIdx.x + 1);
@@ -209,10 +215,10 @@ struct TileCursor {
                 unit_off = unit_off_of(p, r);
                 seq_ibase = p.seq_index_base ? __ldg(p.seq_index_base + r) : 0ull;
             }
+            ubit = unit_off * p.unit_bits;
         } else {
-            f0 = r * p.wpr;
-            wcount = p.wpr;
-            unit_off = unit_off_of(p, r);
+            wcount = p.wpr; // f0 and ubit follow r incrementally (init / advance)
+            if (p.seq_unit_off) ubit = (__ldg(p.seq_unit_off + r) - p.unit_bias) * p.unit_bits;
         }
         q = f0 / G + gi;
         wbase = static_cast<int64_t>(q * G - f0);
@@ -224,7 +230,7 @@ struct TileCursor {
     // bit offset in the stream of slot 0's first symbol
     KMC_DEV int64_t bit(const ExtractParams &p) const
     {
-        return static_cast<int64_t>(unit_off) * p.unit_bits + 2 * (static_cast<int64_t>(p.first) + wbase);
+        return static_cast<int64_t>(ubit) + 2 * (static_cast<int64_t>(p.first) + wbase);
     }
 
     // to the item kBlockThreads further on
@@ -233,24 +239,27 @@ struct TileCursor {
         if (!RAGGED) {
             r += p.it_dq;
             gi += p.it_dr;
+            f0 += p.it_df0;
+            ubit += p.it_dbits;
             if (gi >= p.gprm) {
                 gi -= p.gprm;
                 ++r;
-            }
-        }
-    }
-
-    // to the next item
-    KMC_DEV void advance1(const ExtractParams &p)
-    {
-        if (!RAGGED) {
-            if (++gi >= p.gprm) {
-                gi = 0;
-                ++r;
+                f0 += p.wpr;
+                ubit += p.read_bits;
             }
         }
     }
 };
+
+// per-iteration strides of the uniform locator (every launcher calls this before the launch)
+inline void set_iteration_strides(ExtractParams &p)
+{
+    p.it_dq = kBlockThreads / p.gprm;
+    p.it_dr = kBlockThreads % p.gprm;
+    p.it_df0 = p.it_dq * p.wpr;
+    p.read_bits = p.stride_units * p.unit_bits;
+    p.it_dbits = p.it_dq * p.read_bits;
+}
 
 
 
@@ -399,8 +408,7 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
     const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
     if (tiles == 0) return cudaSuccess;
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    p.it_dq = kBlockThreads / p.gprm;
-    p.it_dr = kBlockThreads % p.gprm;
+    set_iteration_strides(p);
     extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4>
         <<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
     return cudaGetLastError();

@@ -1,6 +1,7 @@
 // fourbit.cu -- 4-bit sources (FourToTwo, src/construction.jl:85-86): device recoding, the
 // valid-start bit stream, the strict-mode error resolution and the two-phase orchestration of
 // UnambiguousKmers' ordered compaction.  See fourbit.h for the scheme.
+#include "compact_kernels.cuh"
 #include "fourbit.h"
 
 namespace kmc {
@@ -8,37 +9,40 @@ namespace kmc {
 namespace {
 
 constexpr uint64_t kNone = ~0ull;
-constexpr int kRunLayoutG = 32; // windows per work item of the run-marking kernels (runs.cu)
+constexpr int kCountLayoutG = 32; // windows per work item when the survivors are only counted (valid_count.cu)
 
 // ---- bit-parallel recoding of one LongSequence{<:NucleicAcidAlphabet{4}} word (16 nibbles) ------
-// 2-bit code of a one-hot nibble = trailing_zeros (A=1,C=2,G=4,T=8 -> 0,1,2,3;
-// construction_utils.jl:51): bit0 = x1|x3, bit1 = x2|x3.
-__device__ __forceinline__ uint32_t recode_word(uint64_t w)
+// Everything is done on 32-bit halves (8 nibbles): the integer pipe is 32 bits wide, a 64-bit
+// formulation costs two instructions per operation.
+//   2-bit code of a one-hot nibble = trailing_zeros (A=1,C=2,G=4,T=8 -> 0,1,2,3;
+//   construction_utils.jl:51): bit0 = x1|x3, bit1 = x2|x3.
+//   flag <=> the nibble is not one-hot (count_ones(enc) != 1: the reference's uncertainty test,
+//   FwKmers.jl:112, UnambiguousKmers.jl:145; covers IUPAC ambiguity codes, N and gap): with the four
+//   bit planes a..d aligned at bit 0 of each nibble, exactly one is set iff
+//   ((a^b) ^ (c^d)) & ~(a&b) & ~(c&d).
+__device__ __forceinline__ void recode_half(uint32_t x, uint32_t &codes16, uint32_t &flags8)
 {
-    const uint64_t ones = 0x1111111111111111ull;
-    const uint64_t b0 = ((w >> 1) | (w >> 3)) & ones;
-    const uint64_t b1 = ((w >> 2) | (w >> 3)) & ones;
-    uint64_t c = b0 | (b1 << 1); // nibble i holds the code in its low 2 bits
-    c = (c | (c >> 2)) & 0x0f0f0f0f0f0f0f0full;
-    c = (c | (c >> 4)) & 0x00ff00ff00ff00ffull;
-    c = (c | (c >> 8)) & 0x0000ffff0000ffffull;
-    c = (c | (c >> 16)) & 0x00000000ffffffffull;
-    return static_cast<uint32_t>(c);
+    const uint32_t M = 0x11111111u;
+    const uint32_t t1 = x >> 1, t2 = x >> 2, t3 = x >> 3;
+    uint32_t c = ((t1 | t3) & M) | (((t2 | t3) & M) << 1); // nibble i holds its code in its low 2 bits
+    c = (c | (c >> 2)) & 0x0f0f0f0fu;
+    c = (c | (c >> 4)) & 0x00ff00ffu;
+    codes16 = __byte_perm(c, 0u, 0x4420); // bytes 0 and 2
+    const uint32_t one = ((x ^ t1) ^ (t2 ^ t3)) & ~(x & t1) & ~(t2 & t3);
+    uint32_t n = ~one & M;
+    n = (n | (n >> 3)) & 0x03030303u;
+    n = (n | (n >> 6)) & 0x000f000fu;
+    flags8 = (n | (n >> 12)) & 0xffu;
 }
 
-// bit i set <=> nibble i is not one-hot (count_ones(enc) != 1: the reference's uncertainty test,
-// FwKmers.jl:112, UnambiguousKmers.jl:145; covers IUPAC ambiguity codes, N and gap)
-__device__ __forceinline__ uint32_t uncertain_word(uint64_t w)
+// one source word: 32 bits of 2-bit codes, 16 flags
+__device__ __forceinline__ void recode_word(uint64_t w, uint32_t &codes, uint32_t &flags)
 {
-    const uint64_t s = (w & 0x5555555555555555ull) + ((w >> 1) & 0x5555555555555555ull);
-    const uint64_t t = (s & 0x3333333333333333ull) + ((s >> 2) & 0x3333333333333333ull); // popcount per nibble
-    const uint64_t u = t ^ 0x1111111111111111ull;                                          // zero nibble <=> popcount 1
-    uint64_t n = (u | (u >> 1) | (u >> 2) | (u >> 3)) & 0x1111111111111111ull;
-    n = (n | (n >> 3)) & 0x0303030303030303ull;
-    n = (n | (n >> 6)) & 0x000f000f000f000full;
-    n = (n | (n >> 12)) & 0x000000ff000000ffull;
-    n = (n | (n >> 24)) & 0x000000000000ffffull;
-    return static_cast<uint32_t>(n);
+    uint32_t c0, c1, f0, f1;
+    recode_half(static_cast<uint32_t>(w), c0, f0);
+    recode_half(static_cast<uint32_t>(w >> 32), c1, f1);
+    codes = c0 | (c1 << 16);
+    flags = f0 | (f1 << 8);
 }
 
 // One thread per PAIR of source words (= one group of 32 symbols): 2 x u32 of 2-bit codes, 1 x u32 of
@@ -52,21 +56,44 @@ __global__ void __launch_bounds__(256) recode_vstart_kernel(const uint64_t *__re
 {
     __shared__ uint32_t s_bad[256 + 8];
     const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * 256;
-    auto load = [&](uint64_t i) -> uint64_t { return i < n_words ? __ldg(words + i) : 0x1111111111111111ull; };
+    // words past the end read as 'A' (one-hot): never part of a window, never flagged
+    auto load_pair = [&](uint64_t g, uint64_t &w0, uint64_t &w1) {
+        if (2 * g + 1 < n_words && (reinterpret_cast<uintptr_t>(words) & 15) == 0) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(words) + g);
+            w0 = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
+            w1 = static_cast<uint64_t>(v.z) | (static_cast<uint64_t>(v.w) << 32);
+        } else {
+            w0 = 2 * g < n_words ? __ldg(words + 2 * g) : 0x1111111111111111ull;
+            w1 = 2 * g + 1 < n_words ? __ldg(words + 2 * g + 1) : 0x1111111111111111ull;
+        }
+    };
     {
         const uint64_t g = g0 + threadIdx.x;
         uint32_t f = 0;
         if (g < n_groups) {
-            const uint64_t w0 = load(2 * g), w1 = load(2 * g + 1);
-            reinterpret_cast<uint2 *>(rec)[g] = make_uint2(recode_word(w0), recode_word(w1));
-            f = uncertain_word(w0) | (uncertain_word(w1) << 16);
+            uint64_t w0, w1;
+            load_pair(g, w0, w1);
+            uint32_t c0, c1, f0, f1;
+            recode_word(w0, c0, f0);
+            recode_word(w1, c1, f1);
+            reinterpret_cast<uint2 *>(rec)[g] = make_uint2(c0, c1);
+            f = f0 | (f1 << 16);
             bad[g] = f;
         }
         s_bad[threadIdx.x] = f;
     }
     if (threadIdx.x < kRecodeHalo) {
         const uint64_t g = g0 + 256 + threadIdx.x;
-        s_bad[256 + threadIdx.x] = g < n_groups ? (uncertain_word(load(2 * g)) | (uncertain_word(load(2 * g + 1)) << 16)) : 0u;
+        uint32_t f = 0;
+        if (g < n_groups) {
+            uint64_t w0, w1;
+            load_pair(g, w0, w1);
+            uint32_t c0, c1, f0, f1;
+            recode_word(w0, c0, f0);
+            recode_word(w1, c1, f1);
+            f = f0 | (f1 << 16);
+        }
+        s_bad[256 + threadIdx.x] = f;
     }
     __syncthreads();
     const uint64_t g = g0 + threadIdx.x;
@@ -154,6 +181,17 @@ ExtractLaunchFn strict_launcher(const Geometry &ge, int mode, bool hash, bool ra
     return nullptr;
 }
 
+CompactLaunchFn compact_launcher(const Geometry &ge, bool hash, bool ragged)
+{
+    switch (ge.n_limbs) {
+    case 1: return get_compact_launcher_n1(ge.nx, hash, ragged);
+    case 2: return get_compact_launcher_n2(ge.nx, hash, ragged);
+    case 3: return get_compact_launcher_n3(ge.nx, hash, ragged);
+    case 4: return get_compact_launcher_n4(ge.nx, hash, ragged);
+    }
+    return nullptr;
+}
+
 } // namespace
 
 uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
@@ -164,26 +202,18 @@ uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
     uint64_t need = 0;
     need += round_up(8 * (nb + 2), 256);     // rec32
     need += 3 * round_up(4 * (nb + 8), 256); // bad, vstart, err
-    need += 2 * 256;                         // err_flat, err_out
+    need += 3 * 256;                         // err_flat, err_out, total
     need += layout_scratch_bytes(s);
     if (mode == KMC_UNAMBIG) {
-        need += 2 * round_up(8 * (tb + 1), 256) + 2 * round_up(8 * (tb + 2), 256) + round_up(8 * scan_tmp_elems(tb), 256);
+        need += round_up(8 * (tb + 1), 256);                                                        // tile_state
         need += round_up(8 * (s->n_seqs + 1), 256) + round_up(8 * scan_tmp_elems(s->n_seqs), 256); // seq_out_offset
     }
     return need + 1024;
 }
 
-uint64_t run_scratch_bytes(uint64_t n_runs, uint64_t n_valid, int g)
-{
-    const uint64_t items = n_valid / static_cast<uint64_t>(g) + 2 * n_runs + 2;
-    const uint64_t tiles = (items + kTileItems - 1) / kTileItems + 1;
-    return 5 * round_up(8 * (n_runs + 2), 256) + round_up(8 * scan_tmp_elems(n_runs + 1), 256) +
-           round_up(8 * (tiles + 2), 256) + 1024;
-}
-
 int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,
                         cudaStream_t stream, const KnownTotals &known, uint64_t unit_bias, Scratch &scratch,
-                        uint64_t *host_small, FourBitState *st)
+                        uint64_t *host_small, bool count_first, FourBitState *st)
 {
     st->seqs = s;
     st->words4 = s->words;
@@ -194,6 +224,7 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     st->host_small = host_small;
     st->unit_bias = unit_bias;
     st->unambig = (mode == KMC_UNAMBIG);
+    st->counted = false;
     host_small[0] = 0;
     host_small[1] = kNone;
     const Geometry &ge = st->ge;
@@ -223,10 +254,10 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
         CU(cudaGetLastError());
     }
 
-    // strict modes lay the set out for the extraction kernel's G; UnambiguousKmers lays it out in
-    // groups of 32 windows for the run-marking kernels (the extraction runs over the run list)
+    // the set is laid out for the extraction / compaction kernel's G; a count-only call (out == NULL)
+    // lays it out in groups of 32 windows
     Geometry lay = ge;
-    if (st->unambig) lay.g = kRunLayoutG;
+    if (st->unambig && !out) lay.g = kCountLayoutG;
     int32_t rc = plan_layout(ctx, s, k, lay, stream, known, scratch, &st->L);
     if (rc) return rc;
     const Layout &L = st->L;
@@ -262,22 +293,18 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
         return KMC_OK;
     }
 
-    // UnambiguousKmers: survivors and run starts per tile -> scans -> totals
+    // UnambiguousKmers: the compaction kernel places its tiles itself; the survivors are counted up
+    // front only for callers that need the number before the k-mers exist
     const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
-    uint64_t *tile_valid = static_cast<uint64_t *>(scratch.take(8 * (tiles + 1)));
-    uint64_t *tile_runs = static_cast<uint64_t *>(scratch.take(8 * (tiles + 1)));
-    uint64_t *tile_valid_off = static_cast<uint64_t *>(scratch.take(8 * (tiles + 2)));
-    uint64_t *tile_runs_off = static_cast<uint64_t *>(scratch.take(8 * (tiles + 2)));
-    uint64_t *tmp = static_cast<uint64_t *>(scratch.take(8 * scan_tmp_elems(tiles)));
-    if (!tile_valid || !tile_runs || !tile_valid_off || !tile_runs_off || !tmp)
-        return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
-    st->tile_valid_off = tile_valid_off;
-    st->tile_runs_off = tile_runs_off;
-    CU(mark_runs(st->p, !L.uniform_len, tile_valid, tile_runs, stream));
-    CU(inclusive_offsets_u64(tile_valid, tile_valid_off, tiles, tmp, stream));
-    CU(inclusive_offsets_u64(tile_runs, tile_runs_off, tiles, tmp, stream));
-    CU(cudaMemcpyAsync(&host_small[0], tile_valid_off + tiles, 8, cudaMemcpyDeviceToHost, stream));
-    CU(cudaMemcpyAsync(&host_small[2], tile_runs_off + tiles, 8, cudaMemcpyDeviceToHost, stream));
+    st->total_dev = static_cast<unsigned long long *>(scratch.take(8));
+    st->tile_state = static_cast<unsigned long long *>(scratch.take(8 * (tiles + 1)));
+    if (!st->total_dev || !st->tile_state) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+    if (count_first || !out) {
+        CU(cudaMemsetAsync(st->total_dev, 0, 8, stream));
+        CU(count_valid(st->p, !L.uniform_len, lay.g, st->total_dev, stream));
+        CU(cudaMemcpyAsync(&host_small[0], st->total_dev, 8, cudaMemcpyDeviceToHost, stream));
+        st->counted = true;
+    }
     if (out && out->seq_out_offset) {
         uint64_t *cnt = static_cast<uint64_t *>(scratch.take(8 * (s->n_seqs + 1)));
         uint64_t *tmp2 = static_cast<uint64_t *>(scratch.take(8 * scan_tmp_elems(s->n_seqs)));
@@ -290,8 +317,7 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     return KMC_OK;
 }
 
-int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, Scratch &runs,
-                        kmc_result *res)
+int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, kmc_result *res)
 {
     const Layout &L = st->L;
     if (!st->unambig) {
@@ -321,53 +347,42 @@ int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cuda
         res->err_sym = static_cast<uint32_t>(st->host_small[6]);
         return fail(ctx, KMC_E_AMBIGUOUS, "cannot encode this byte in a 2-bit alphabet");
     }
-    const uint64_t total = L.total ? st->host_small[0] : 0;
-    const uint64_t n_runs = L.total ? st->host_small[2] : 0;
-    res->n_written = total;
-    if (total == 0) return KMC_OK;
-    if (total > out->capacity) return fail(ctx, KMC_E_OUT_TOO_SMALL, "output capacity smaller than the number of k-mers");
+    res->n_written = 0;
+    if (L.total == 0) {
+        st->counted = true; // nothing to emit: host_small[0] is already 0
+        return KMC_OK;
+    }
+    if (st->counted) {
+        const uint64_t total = st->host_small[0];
+        res->n_written = total;
+        if (total == 0) return KMC_OK;
+        if (total > out->capacity) return fail(ctx, KMC_E_OUT_TOO_SMALL, "output capacity smaller than the number of k-mers");
+    }
 
-    // ---- run list: the surviving windows as a ragged set of "sequences" ------------------------
-    const int G = st->ge.g;
-    uint64_t *run_sym = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
-    uint64_t *run_woff = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
-    uint64_t *run_ibase = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
-    uint64_t *slots = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
-    uint64_t *run_item_off = static_cast<uint64_t *>(runs.take(8 * (n_runs + 2)));
-    uint64_t *tmp = static_cast<uint64_t *>(runs.take(8 * scan_tmp_elems(n_runs + 1)));
-    const uint64_t items_bound = total / static_cast<uint64_t>(G) + 2 * n_runs + 2;
-    const uint64_t tiles_bound = (items_bound + kTileItems - 1) / kTileItems;
-    uint64_t *tile_first = static_cast<uint64_t *>(runs.take(8 * (tiles_bound + 2)));
-    if (!run_sym || !run_woff || !run_ibase || !slots || !run_item_off || !tmp || !tile_first)
-        return fail(ctx, KMC_E_BAD_ARG, "internal: run scratch window too small");
-    CU(emit_runs(st->p, !L.uniform_len, st->tile_valid_off, st->tile_runs_off, run_sym, run_woff, run_ibase, stream));
-    const uint64_t tiles32 = (L.items + kTileItems - 1) / kTileItems;
-    CU(cudaMemcpyAsync(run_woff + n_runs, st->tile_valid_off + tiles32, 8, cudaMemcpyDeviceToDevice, stream)); // sentinel = total
-    CU(group_slots(run_woff, n_runs, G, slots, stream));
-    CU(inclusive_offsets_u64(slots, run_item_off, n_runs, tmp, stream));
-    CU(tile_first_reads(run_item_off, n_runs, kTileItems, tiles_bound, tile_first, stream));
-
-    // ---- the ordinary ragged extraction over the runs (MODE_FW + index) ------------------------
+    // ---- ordered compaction of the surviving windows (forward k-mer + 1-based start) ------------
     ExtractParams p = st->p;
-    p.unit_bits = 2; // run offsets are absolute SYMBOL indices of the recoded stream
-    p.unit_bias = 0;
-    p.first = 0;
-    p.n_seqs = n_runs;
-    p.items = items_bound;             // grid upper bound;
-    p.items_dev = run_item_off + n_runs; // the exact number of work items lives on the device
-    p.stride_units = 0;
-    p.wpr = 0;
-    p.gprm = 1;
-    p.seq_unit_off = run_sym;
-    p.win_off = run_woff;
-    p.item_off = run_item_off;
-    p.tile_first = tile_first;
-    p.seq_index_base = run_ibase;
     int32_t rc = bind_outputs(ctx, out, KMC_UNAMBIG, st->flags, &p);
     if (rc) return rc;
-    ExtractLaunchFn fn = get_launcher(st->ge, MODE_FW, (st->flags & KMC_HASH_FX) != 0, true);
+    const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
+    CompactParams cp{st->tile_state, reinterpret_cast<uint64_t *>(st->total_dev), out->capacity};
+    CU(cudaMemsetAsync(st->tile_state, 0, 8 * tiles, stream));
+    CompactLaunchFn fn = compact_launcher(st->ge, (st->flags & KMC_HASH_FX) != 0, !L.uniform_len);
     if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
-    CU(fn(p, ctx->sm_count, stream));
+    CU(fn(p, cp, stream));
+    if (!st->counted) CU(cudaMemcpyAsync(&st->host_small[0], st->total_dev, 8, cudaMemcpyDeviceToHost, stream));
+    return KMC_OK;
+}
+
+// After the stream has been synchronised: what the compaction emitted (when it was not counted first).
+int32_t fourbit_unambig_result(kmc_ctx *ctx, const FourBitState *st, const kmc_out *out, kmc_result *res)
+{
+    if (!st->unambig || st->counted) return KMC_OK;
+    const uint64_t total = st->host_small[0];
+    if (total > out->capacity) {
+        res->n_written = 0;
+        return fail(ctx, KMC_E_OUT_TOO_SMALL, "output capacity smaller than the number of k-mers");
+    }
+    res->n_written = total;
     return KMC_OK;
 }
 
@@ -381,24 +396,12 @@ int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t 
     Scratch scratch{static_cast<char *>(ctx->scratch), ctx->scratch_bytes, 0};
     FourBitState st;
     CU(cudaEventRecord(ctx->ev_k0, stream));
-    rc = fourbit_phase_a(ctx, s, k, mode, flags, out, stream, KnownTotals(), 0, scratch, ctx->host_small, &st);
+    rc = fourbit_phase_a(ctx, s, k, mode, flags, out, stream, KnownTotals(), 0, scratch, ctx->host_small, false, &st);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(stream));
-    Scratch runs;
-    if (mode == KMC_UNAMBIG && st.L.total && ctx->host_small[0]) {
-        // the run list is sized exactly, now that the counts are known (second grow-only buffer, so
-        // the recoded stream in the first one stays where it is)
-        const uint64_t need = run_scratch_bytes(ctx->host_small[2], ctx->host_small[0], st.ge.g);
-        if (need > ctx->scratch2_bytes) {
-            if (ctx->scratch2) CU(cudaFree(ctx->scratch2));
-            ctx->scratch2 = nullptr;
-            ctx->scratch2_bytes = 0;
-            CU(cudaMalloc(&ctx->scratch2, need + need / 4));
-            ctx->scratch2_bytes = need + need / 4;
-        }
-        runs = Scratch{static_cast<char *>(ctx->scratch2), ctx->scratch2_bytes, 0};
-    }
-    rc = fourbit_phase_b(ctx, &st, out, stream, runs, res);
+    // strict modes and ASCII sources can fail: phase B needs the error word.  UnambiguousKmers over a
+    // 4-bit source cannot, and its compaction is enqueued right behind the recoding.
+    if (!st.unambig || st.err) CU(cudaStreamSynchronize(stream));
+    rc = fourbit_phase_b(ctx, &st, out, stream, res);
     if (rc) return rc;
     if (mode != KMC_UNAMBIG && out->seq_out_offset) {
         if (st.L.uniform_len)
@@ -409,7 +412,7 @@ int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t 
     CU(cudaEventRecord(ctx->ev_k1, stream));
     CU(cudaStreamSynchronize(stream));
     CU(cudaEventElapsedTime(&res->kernel_ms, ctx->ev_k0, ctx->ev_k1));
-    return KMC_OK;
+    return fourbit_unambig_result(ctx, &st, out, res);
 }
 
 int32_t count_unambiguous_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, uint64_t *n_out, cudaStream_t stream)
@@ -420,13 +423,12 @@ int32_t count_unambiguous_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, uint6
     if (rc) return rc;
     Scratch scratch{static_cast<char *>(ctx->scratch), ctx->scratch_bytes, 0};
     FourBitState st;
-    rc = fourbit_phase_a(ctx, s, k, KMC_UNAMBIG, 0, nullptr, stream, KnownTotals(), 0, scratch, ctx->host_small, &st);
+    rc = fourbit_phase_a(ctx, s, k, KMC_UNAMBIG, 0, nullptr, stream, KnownTotals(), 0, scratch, ctx->host_small, true, &st);
     if (rc) return rc;
     CU(cudaStreamSynchronize(stream));
     if (st.err && ctx->host_small[1] != kNone) { // ASCII: the iteration would throw before finishing
         kmc_result r{};
-        Scratch none;
-        return fourbit_phase_b(ctx, &st, nullptr, stream, none, &r);
+        return fourbit_phase_b(ctx, &st, nullptr, stream, &r);
     }
     *n_out = st.L.total ? ctx->host_small[0] : 0;
     return KMC_OK;

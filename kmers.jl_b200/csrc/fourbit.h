@@ -11,17 +11,18 @@
 //     the first window with an uncertain symbol is reported; the call fails with KMC_E_AMBIGUOUS
 //     and the position / encoding the reference's throw_uncertain (construction.jl:108-110) names;
 //   UnambiguousKmers (UnambiguousKmers.jl:134-148): windows with an uncertain symbol are skipped.
-//     The survivors form runs of consecutive windows; a run list is built from the valid-start
-//     bits (runs.cu) and the ordinary ragged extraction kernel emits the runs in order, each
-//     k-mer with its 1-based start inside its read.
+//     compact_kernel (compact_kernels.cuh) computes the windows like the 2-bit kernels do and
+//     compacts the survivors in order, each k-mer with its 1-based start inside its read, in a
+//     single pass (decoupled look-back over the tiles; aligned 256-bit stores from a staging buffer).
 #pragma once
 #include "plan.h"
 
 namespace kmc {
 
-// What one 4-bit extraction needs between its two phases.  Phase A enqueues everything whose size
-// is known up front and leaves two words in `host_small` (pinned): [0] = number of k-mers
-// UnambiguousKmers will emit, [1] = first offending flat window of a strict mode (~0 = none).
+// What one 4-bit extraction needs between its two phases.  Phase A enqueues the recoding (and, for
+// strict modes, the extraction) and leaves two words in `host_small` (pinned): [0] = number of k-mers
+// UnambiguousKmers will emit (only when asked to count first), [1] = first offending flat window of a
+// strict mode / first sequence with an invalid byte (~0 = none).
 // Phase B runs after the caller has synchronised the stream.
 struct FourBitState {
     const kmc_seqs *seqs = nullptr; // device descriptor (must outlive phase B)
@@ -29,31 +30,35 @@ struct FourBitState {
     int k = 0, mode = 0;
     uint32_t flags = 0;
     Geometry ge{};
-    Layout L{};      // strict: layout for the kernel's G; UnambiguousKmers: the G = 32 run-marking layout
+    Layout L{};      // layout for the kernel's G (count only: G = 32)
     ExtractParams p{};
     uint32_t *bad = nullptr;
     uint32_t *err = nullptr; // ASCII UnambiguousKmers: hard-error flags (bytes outside the skipping table)
-    uint64_t *tile_valid_off = nullptr, *tile_runs_off = nullptr; // UnambiguousKmers: scans of the per-tile counts
+    unsigned long long *tile_state = nullptr; // UnambiguousKmers: look-back descriptors of compact_kernel
+    unsigned long long *total_dev = nullptr;  // UnambiguousKmers: emitted k-mers (device)
+    bool counted = false;                     // host_small[0] holds the count when phase A has completed
     uint64_t *err_out = nullptr; // device u64[3]: seq, 1-based pos, encoding
     uint64_t *host_small = nullptr;
     uint64_t unit_bias = 0;
     bool unambig = false;
 };
 
-// bytes phase B of UnambiguousKmers needs for a run list of n_runs runs and n_valid k-mers
-uint64_t run_scratch_bytes(uint64_t n_runs, uint64_t n_valid, int g);
-
-// runs.cu
-cudaError_t mark_runs(const ExtractParams &p, bool ragged, uint64_t *tile_valid, uint64_t *tile_runs, cudaStream_t stream);
-cudaError_t emit_runs(const ExtractParams &p, bool ragged, const uint64_t *tile_valid_off, const uint64_t *tile_runs_off,
-                      uint64_t *run_sym, uint64_t *run_woff, uint64_t *run_ibase, cudaStream_t stream);
+// valid_count.cu: *total += survivors of the set laid out in groups of g windows (g = 2, 4, 8 or 32)
+cudaError_t count_valid(const ExtractParams &p, bool ragged, int g, unsigned long long *total, cudaStream_t stream);
 
 // Valid-start bits of one group of 32 symbols from the flag words a[0..4] of this and the next four
 // groups (a[5] = 0): bit t set <=> no flagged symbol in [t, t + K).  Sliding-window OR of length K by
 // doubling -- A_1 = flags, A_2L = A_L | A_L >> L while 2L <= K, then two windows of length L cover
-// [P, P+K): A_L | A_L >> (K - L).  Branch-free in the data (K is uniform), ~40 funnel shifts.
-__device__ __forceinline__ uint32_t valid_start_word(uint32_t (&a)[6], int k)
+// [P, P+K): A_L | A_L >> (K - L).  Branch-free in the data (K is uniform).  Only the first
+// NW = (30 + K) / 32 + 1 words can reach the result (a window starting at bit 31 ends at bit 30 + K), so
+// the doubling runs on NW words: 2 for K <= 33 instead of 5.
+template <int NW>
+__device__ __forceinline__ uint32_t valid_start_word_n(const uint32_t (&a6)[6], int k)
 {
+    uint32_t a[NW + 1];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) a[w] = a6[w];
+    a[NW] = 0;
     int L = 1;
 #pragma unroll
     for (int step = 0; step < 7; ++step) {
@@ -61,13 +66,13 @@ __device__ __forceinline__ uint32_t valid_start_word(uint32_t (&a)[6], int k)
         if (2 * s <= k) {
             if (s < 32) {
 #pragma unroll
-                for (int w = 0; w < 5; ++w) a[w] |= __funnelshift_r(a[w], a[w + 1], s);
+                for (int w = 0; w < NW; ++w) a[w] |= __funnelshift_r(a[w], a[w + 1], s);
             } else if (s == 32) {
 #pragma unroll
-                for (int w = 0; w < 5; ++w) a[w] |= a[w + 1];
+                for (int w = 0; w < NW; ++w) a[w] |= a[w + 1];
             } else {
 #pragma unroll
-                for (int w = 0; w < 4; ++w) a[w] |= a[w + 2];
+                for (int w = 0; w + 1 < NW; ++w) a[w] |= a[w + 2 <= NW ? w + 2 : NW];
             }
             L = 2 * s;
         }
@@ -76,10 +81,21 @@ __device__ __forceinline__ uint32_t valid_start_word(uint32_t (&a)[6], int k)
     uint32_t v = a[0];
     if (r) {
         const int b = r & 31;
-        if (r < 32) v |= __funnelshift_r(a[0], a[1], b);
-        else v |= b ? __funnelshift_r(a[1], a[2], b) : a[1];
+        if (r < 32) v |= __funnelshift_r(a[0], a[NW >= 1 ? 1 : 0], b);
+        else v |= b ? __funnelshift_r(a[1 <= NW ? 1 : NW], a[2 <= NW ? 2 : NW], b) : a[1 <= NW ? 1 : NW];
     }
     return ~v;
+}
+
+__device__ __forceinline__ uint32_t valid_start_word(const uint32_t (&a)[6], int k)
+{
+    switch ((30 + k) / 32) { // warp-uniform
+    case 0: return valid_start_word_n<1>(a, k);
+    case 1: return valid_start_word_n<2>(a, k);
+    case 2: return valid_start_word_n<3>(a, k);
+    case 3: return valid_start_word_n<4>(a, k);
+    }
+    return valid_start_word_n<5>(a, k);
 }
 constexpr int kRecodeHalo = 5; // flag words beyond a group that its windows can reach (31 + K - 1 <= 158 bits)
 
@@ -95,13 +111,16 @@ cudaError_t ascii_resolve_error(const ExtractParams &p, const uint8_t *bytes, co
 
 uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode);
 
+// count_first (UnambiguousKmers): also count the survivors, so that phase B knows n_written before it
+// enqueues the compaction (the host pipeline needs it to place the next chunk).  out == NULL: count only.
 int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,
                         cudaStream_t stream, const KnownTotals &known, uint64_t unit_bias, Scratch &scratch,
-                        uint64_t *host_small, FourBitState *st);
-// Fills res->n_written (and err_* with KMC_E_AMBIGUOUS).  For UnambiguousKmers: builds the run list in
-// `runs` (at least run_scratch_bytes(host_small[2], host_small[0], G) bytes) and enqueues the extraction.
-int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, Scratch &runs,
-                        kmc_result *res);
+                        uint64_t *host_small, bool count_first, FourBitState *st);
+// Fills res->n_written (and err_* with KMC_E_AMBIGUOUS).  For UnambiguousKmers: enqueues the compaction;
+// without count_first, n_written is host_small[0] once the stream has been synchronised
+// (fourbit_unambig_result).
+int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cudaStream_t stream, kmc_result *res);
+int32_t fourbit_unambig_result(kmc_ctx *ctx, const FourBitState *st, const kmc_out *out, kmc_result *res);
 
 // kmc_extract on device buffers: phase A, sync, phase B, sync.
 int32_t extract_device_4bit(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags,

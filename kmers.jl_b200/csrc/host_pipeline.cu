@@ -85,8 +85,8 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
     const bool want_digest = (flags & KMC_DIGEST) != 0;
     const bool want_index = (mode == KMC_UNAMBIG);
     const bool compacting = four && mode == KMC_UNAMBIG; // variable-length output
-    // windows per work item of the layout the device planner will build (run marking uses 32)
-    const uint64_t G = compacting ? 32 : static_cast<uint64_t>(ge.g);
+    // windows per work item of the layout the device planner will build
+    const uint64_t G = static_cast<uint64_t>(ge.g);
     const bool two = (mode == KMC_FWRV);
     const bool ragged_len = hs->seq_len != nullptr;
     const bool ragged_off = hs->seq_word_offset != nullptr;
@@ -219,10 +219,7 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
     worst.n_words = max_words;
     worst.n_seqs = single ? 1 : max_seq;
     if (single) worst.seq_len = nullptr;
-    // UnambiguousKmers over 4 bits: the run list of a chunk is carved from the slot's window at its
-    // worst case (every other window survives)
-    const uint64_t run_bytes = compacting ? round_up(run_scratch_bytes(max_out / 2 + 1, max_out, ge.g), 256) : 0;
-    const uint64_t scratch_per_slot = round_up(extract_scratch_bytes(&worst, k, mode), 256) + run_bytes;
+    const uint64_t scratch_per_slot = round_up(extract_scratch_bytes(&worst, k, mode), 256);
     st = ensure_scratch(ctx, scratch_per_slot * n_slots);
     if (st) return st;
     st = ensure_host_small(ctx);
@@ -311,12 +308,7 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
         CU(cudaEventSynchronize(sl.ev_a));
         kmc_result r{};
         if (compacting) bind_chunk_out(c, sl, emitted, dev_out ? ho->capacity - emitted : c.nout);
-        Scratch runs;
-        if (compacting) { // the tail of the slot's scratch window
-            runs.base = sl.scratch.base + (scratch_per_slot - run_bytes);
-            runs.bytes = run_bytes;
-        }
-        int32_t rc = fourbit_phase_b(ctx, &c.fb, &c.dout, sl.stream, runs, &r);
+        int32_t rc = fourbit_phase_b(ctx, &c.fb, &c.dout, sl.stream, &r);
         if (rc == KMC_E_AMBIGUOUS) {
             result->n_written = 0;
             result->err_seq = single ? 0 : c.seq0 + r.err_seq;
@@ -382,7 +374,6 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
         dout.seq_out_offset = want_seq_out ? sl.seq_out : nullptr;
         dout.index_base = c.index_base + ho->index_base;
         Scratch scratch = sl.scratch;
-        scratch.bytes -= run_bytes;
         scratch.used = 0;
         if (!four) {
             kmc_result r{};
@@ -393,7 +384,8 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
             st = download(sl, c.out0, c.nout);
             if (st) return st;
         } else {
-            st = fourbit_phase_a(ctx, &ds, k, mode, flags, &dout, sm, known, bias, scratch, sl.host_small, &c.fb);
+            // count first: the next chunk's place in the caller's buffer depends on this chunk's survivors
+            st = fourbit_phase_a(ctx, &ds, k, mode, flags, &dout, sm, known, bias, scratch, sl.host_small, true, &c.fb);
             if (st) return st;
             if (!compacting) {
                 st = digest_chunk(c, sl, c.nout);

@@ -18,8 +18,6 @@ struct kmc_ctx {
     // grow-only scratch (scans, recoded 4-bit streams, compaction counters)
     void *scratch = nullptr;
     uint64_t scratch_bytes = 0;
-    void *scratch2 = nullptr; // run lists of UnambiguousKmers over 4-bit sources (sized after the count pass)
-    uint64_t scratch2_bytes = 0;
     // host-pipeline device buffers, one per slot (grow-only)
     void *pipe_buf[3] = {nullptr, nullptr, nullptr};
     uint64_t pipe_bytes[3] = {0, 0, 0};

@@ -156,11 +156,9 @@ KMC_DEV void store_words(uint64_t *p, const uint64_t (&v)[CNT], int lo, int hi, 
 // outside the sequence buffer never fault; such bits only ever feed windows that are not
 // emitted) and produces the aligned x-stream.
 template <int NX>
-KMC_DEV void load_block(const uint32_t *__restrict__ w32, int64_t nw32, int64_t bit, uint32_t (&x)[NX])
+KMC_DEV void load_raw(const uint32_t *__restrict__ w32, int64_t nw32, int64_t bit, uint32_t (&a)[NX + 1])
 {
     const int64_t idx = bit >> 5;
-    const uint32_t s = static_cast<uint32_t>(bit) & 31u;
-    uint32_t a[NX + 1];
     if (idx >= 0 && idx + NX < nw32) {
 #pragma unroll
         for (int i = 0; i <= NX; ++i) a[i] = __ldg(w32 + idx + i);
@@ -172,6 +170,14 @@ KMC_DEV void load_block(const uint32_t *__restrict__ w32, int64_t nw32, int64_t 
             a[i] = __ldg(w32 + k);
         }
     }
+}
+
+template <int NX>
+KMC_DEV void load_block(const uint32_t *__restrict__ w32, int64_t nw32, int64_t bit, uint32_t (&x)[NX])
+{
+    uint32_t a[NX + 1];
+    load_raw<NX>(w32, nw32, bit, a);
+    const uint32_t s = static_cast<uint32_t>(bit) & 31u;
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = __funnelshift_r(a[i], a[i + 1], s);
 }

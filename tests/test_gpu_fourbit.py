@@ -179,6 +179,39 @@ def test_dense_ambiguity_many_runs(kc, k, amb):
     assert np.array_equal(e.kmers, km) and np.array_equal(e.index, pos)
 
 
+def test_unambiguous_capacity_is_respected(kc, ctx):
+    """The compaction finds its output positions on the device; a buffer that is too small must fail
+    with KMC_E_OUT_TOO_SMALL and nothing may be written past its end (unaligned base on purpose)."""
+    from kmerscuda import _abi
+    rng = np.random.default_rng(77)
+    n, k = 200_000, 31
+    codes = random_codes4(rng, n, 0.01)
+    w = kt.pack_codes(codes, 4)
+    rs = kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet4, w, n))
+    km, pos = ko.unambiguous(w, n, k, src_bits=4)
+    total = km.shape[0]
+    drs = kc.DeviceReadSet(ctx, rs)
+    cap = total - 1000
+    guard = 4096
+    sentinel = np.full(cap + guard + 1, 0xDEADBEEFDEADBEEF, dtype=np.uint64)
+    da, di = ctx.to_device(sentinel), ctx.to_device(sentinel)
+    res = _abi.kmc_result()
+    out = _abi.kmc_out(da.ptr + 8, None, None, di.ptr + 8, None, cap, 0)
+    st = ctx.lib.kmc_extract(ctx.handle, C.byref(drs.desc), k, UNAMBIG, 0, C.byref(out), C.byref(res))
+    assert st == _abi.KMC_E_OUT_TOO_SMALL and res.n_written == 0
+    assert np.all(da.download(np.uint64, guard, 8 * (cap + 1)) == 0xDEADBEEFDEADBEEF)
+    assert np.all(di.download(np.uint64, guard, 8 * (cap + 1)) == 0xDEADBEEFDEADBEEF)
+    assert da.download(np.uint64, 1)[0] == 0xDEADBEEFDEADBEEF
+    # exactly large enough: everything arrives, in order
+    out = _abi.kmc_out(da.ptr + 8, None, None, di.ptr + 8, None, total, 0)
+    da2, di2 = ctx.alloc(8 * (total + 1)), ctx.alloc(8 * (total + 1))
+    out = _abi.kmc_out(da2.ptr + 8, None, None, di2.ptr + 8, None, total, 0)
+    st = ctx.lib.kmc_extract(ctx.handle, C.byref(drs.desc), k, UNAMBIG, 0, C.byref(out), C.byref(res))
+    assert st == 0 and res.n_written == total
+    assert np.array_equal(da2.download(np.uint64, total, 8), km[:, 0])
+    assert np.array_equal(di2.download(np.int64, total, 8), pos)
+
+
 def make_ragged4(rng, lens, amb):
     codes = [random_codes4(rng, n, amb) for n in lens]
     packed = [kt.pack_codes(c, 4) if len(c) else np.zeros(0, np.uint64) for c in codes]
