@@ -12,9 +12,17 @@
 // do not occur in the sequence.  This kernel implements the prose definition (the true W
 // consecutive k-mers); tests/ check it against a naive per-window definition.
 //
-// One thread per window start.  The K+W-1 symbols of the window (<= 64 symbols = 128 bits) are
-// fetched once; k-mer j is a shift of the 2-bit-reversed block (forward) or of the complemented
-// raw block (reverse complement), exactly as in kmer_core.cuh.
+// Dense windows (step 1, W <= 31, uniform sets / single sequences: minimizer_dense_kernel): a thread
+// owns G consecutive window starts, so it hashes each of their G+W-1 k-mers ONCE (register-blocked
+// exactly like the extraction kernels: one block load, static funnel shifts) and takes the G
+// sliding minima by doubling: m_1 = h, m_2s[i] = min(m_s[i], m_s[i+s]), and a window of W =
+// 2^L + d k-mers is min(m_2^L[i], m_2^L[i+d]).  Ties keep the leftmost k-mer at every merge, so
+// the result is the first smallest, as the definition asks.  The winning k-mer is recovered from
+// its hash (fx_hash of one limb is a multiplication by an odd constant: invertible mod 2^64).
+//
+// Everything else (step > 1, ragged sets, W >= 32): one thread per window start.  The K+W-1 symbols
+// of the window (<= 64 symbols = 128 bits) are fetched once; k-mer j is a shift of the
+// 2-bit-reversed block (forward) or of the complemented raw block (reverse complement).
 #include "kmer_core.cuh"
 #include "plan.h"
 
@@ -74,16 +82,17 @@ __global__ void __launch_bounds__(256) minimizer_kernel(const MinimizerParams p)
     const int L = p.k + p.w - 1; // symbols in the window, <= 64
     unsigned __int128 S = (static_cast<unsigned __int128>(hi) << 64) | lo;
     if (L < 64) S &= (static_cast<unsigned __int128>(1) << (2 * L)) - 1;
-    // rev2 of the whole block: symbol i -> L-1-i
+    // rev2 of the whole 128-bit register pair: symbol i -> 63-i, so k-mer j sits in the top 2K bits
+    // after a left shift by 2j -- both streams advance by a constant 2 bits per k-mer
     unsigned __int128 T = (static_cast<unsigned __int128>(rev2_64(lo)) << 64) | rev2_64(hi);
-    T >>= (128 - 2 * L);
     const uint64_t mask = p.k == 32 ? ~0ull : ((1ull << (2 * p.k)) - 1);
+    const int top = 64 - 2 * p.k; // 0..62
     uint64_t best_k = 0, best_h = 0;
     int best_j = 0;
     for (int j = 0; j < p.w; ++j) {
-        uint64_t km = static_cast<uint64_t>(T >> (2 * (p.w - 1 - j))) & mask;
+        uint64_t km = static_cast<uint64_t>(T >> 64) >> top;
         if (p.canon) {
-            const uint64_t rv = ~static_cast<uint64_t>(S >> (2 * j)) & mask;
+            const uint64_t rv = ~static_cast<uint64_t>(S) & mask;
             km = km < rv ? km : rv;
         }
         const uint64_t h = km * FX_CONSTANT; // fx_hash of a one-limb k-mer, h0 = 0 (src/kmer.jl:255-261)
@@ -92,10 +101,181 @@ __global__ void __launch_bounds__(256) minimizer_kernel(const MinimizerParams p)
             best_k = km;
             best_j = j;
         }
+        T <<= 2;
+        S >>= 2;
     }
     p.out_kmer[e] = best_k;
     if (p.out_hash) p.out_hash[e] = best_h;
     if (p.out_index) p.out_index[e] = static_cast<int64_t>(sym) + best_j + 1 + p.index_base;
+}
+
+constexpr uint64_t FX_INVERSE = 0x2040003d780970bdull; // FX_CONSTANT * FX_INVERSE == 1 (mod 2^64)
+static_assert(FX_CONSTANT * FX_INVERSE == 1ull, "inverse of the fx_hash multiplier");
+
+struct DenseParams {
+    const uint32_t *w32;
+    int64_t nw32;
+    uint64_t n_seqs;
+    const uint64_t *seq_word_off; // or NULL
+    uint64_t stride_words;
+    uint32_t first;
+    uint64_t cnt;   // window starts per sequence
+    uint64_t ipr;   // work items (groups of G window starts) per sequence
+    uint64_t items; // ipr * n_seqs
+    int k, w;
+    uint64_t mask;
+    uint64_t *out_kmer, *out_hash;
+    int64_t *out_index;
+    int64_t index_base;
+};
+
+// windows per thread for the class 2^L <= W < 2^(L+1)
+#ifndef KMC_MIN_G
+#define KMC_MIN_G 16
+#endif
+constexpr int dense_group(int l) { return l <= 3 ? KMC_MIN_G : 8; }
+
+template <int CNT>
+KMC_DEV void store_dense(uint64_t *p, const uint64_t (&v)[CNT], int n)
+{
+    if (n == CNT && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < CNT; i += 4) st_v4(p + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if (n == CNT && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < CNT; i += 2) st_v2(p + i, v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i)
+            if (i < n) st_u64(p + i, v[i]);
+    }
+}
+
+template <int L, bool CANON, bool INDEX>
+__global__ void __launch_bounds__(128) minimizer_dense_kernel(const DenseParams p)
+{
+    constexpr int G = dense_group(L);
+    constexpr int WCLASS = (2 << L) - 1;            // largest W of the class
+    constexpr int MM = G + WCLASS - 1;              // k-mers a thread hashes (those beyond G+W-1 never reach a result)
+    constexpr int NX = (64 + 2 * (MM - 1) + 31) / 32; // block words for K = 32
+    const uint64_t item = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (item >= p.items) return;
+    const uint64_t r = item / p.ipr;
+    const uint64_t t0 = (item - r * p.ipr) * G; // first window start of this thread within its sequence
+    const uint64_t left = p.cnt - t0;
+    const int nwin = left < static_cast<uint64_t>(G) ? static_cast<int>(left) : G;
+    const uint64_t word_off = p.seq_word_off ? __ldg(p.seq_word_off + r) : r * p.stride_words;
+    const int64_t bit = static_cast<int64_t>(word_off) * 64 + 2 * static_cast<int64_t>(p.first + t0);
+    uint32_t x[NX];
+    load_block<NX>(p.w32, p.nw32, bit, x);
+
+    // forward k-mer j = rev2(block) >> 2(MM-1-j) once the block is right-aligned to k-mer MM-1:
+    // drop s0 = 32 NX - 2K - 2(MM-1) bits; s0 = 32 q + sr with a uniform q in 0..2 (NX is sized for K = 32)
+    uint32_t t[NX];
+    {
+        uint32_t y[NX + 3];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) y[i] = rev2_32(x[NX - 1 - i]);
+        y[NX] = y[NX + 1] = y[NX + 2] = 0u;
+        const uint32_t s0 = 32u * NX - 2u * p.k - 2u * (MM - 1);
+        const uint32_t q = s0 >> 5, sr = s0 & 31u;
+        if (q == 0) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) t[i] = __funnelshift_r(y[i], y[i + 1], sr);
+        } else if (q == 1) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) t[i] = __funnelshift_r(y[i + 1], y[i + 2], sr);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) t[i] = __funnelshift_r(y[i + 2], y[i + 3], sr);
+        }
+    }
+    uint32_t nx[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) nx[i] = ~x[i];
+
+    uint64_t h[MM];
+    uint32_t pos[INDEX ? MM : 1];
+#pragma unroll
+    for (int j = 0; j < MM; ++j) {
+        uint64_t km = stream64<NX>(t, 2 * (MM - 1 - j)) & p.mask;
+        if (CANON) {
+            const uint64_t rv = stream64<NX>(nx, 2 * j) & p.mask; // ~W: the reverse complement (kmer_core.cuh)
+            km = km < rv ? km : rv;
+        }
+        h[j] = km * FX_CONSTANT; // fx_hash of a one-limb k-mer, h0 = 0 (src/kmer.jl:255-261)
+        if (INDEX) pos[j] = j;
+    }
+    // sliding minima by doubling; ties keep the left (earlier) k-mer
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int s = 1 << l;
+#pragma unroll
+        for (int i = 0; i + s < MM; ++i) {
+            const bool take = h[i + s] < h[i];
+            h[i] = take ? h[i + s] : h[i];
+            if (INDEX) pos[i] = take ? pos[i + s] : pos[i];
+        }
+    }
+    // the window of W = 2^L + d k-mers: two blocks of 2^L, d apart (in place: h[i + d] is still a block minimum
+    // when h[i] is overwritten, for every d >= 0)
+    const int d = p.w - (1 << L); // 0 <= d < 2^L, uniform
+#pragma unroll
+    for (int dd = 1; dd < (1 << L); ++dd) {
+        if (d == dd) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const bool take = h[i + dd] < h[i];
+                h[i] = take ? h[i + dd] : h[i];
+                if (INDEX) pos[i] = take ? pos[i + dd] : pos[i];
+            }
+        }
+    }
+    const uint64_t e0 = r * p.cnt + t0;
+    uint64_t o[G];
+    if (p.out_hash) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) o[i] = h[i];
+        store_dense<G>(p.out_hash + e0, o, nwin);
+    }
+    if (INDEX) {
+        const int64_t ib = static_cast<int64_t>(t0) + 1 + p.index_base;
+#pragma unroll
+        for (int i = 0; i < G; ++i) o[i] = static_cast<uint64_t>(ib + pos[i]);
+        store_dense<G>(reinterpret_cast<uint64_t *>(p.out_index) + e0, o, nwin);
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) o[i] = h[i] * FX_INVERSE; // the k-mer itself
+    store_dense<G>(p.out_kmer + e0, o, nwin);
+}
+
+using DenseLaunchFn = void (*)(const DenseParams &, unsigned, cudaStream_t);
+
+template <int L, bool CANON, bool INDEX>
+void launch_dense(const DenseParams &p, unsigned blocks, cudaStream_t stream)
+{
+    minimizer_dense_kernel<L, CANON, INDEX><<<blocks, 128, 0, stream>>>(p);
+}
+
+template <int L>
+DenseLaunchFn pick_dense(bool canon, bool index)
+{
+    if (canon) return index ? &launch_dense<L, true, true> : &launch_dense<L, true, false>;
+    return index ? &launch_dense<L, false, true> : &launch_dense<L, false, false>;
+}
+
+DenseLaunchFn dense_launcher(int l, bool canon, bool index)
+{
+    switch (l) {
+    case 0: return pick_dense<0>(canon, index);
+    case 1: return pick_dense<1>(canon, index);
+    case 2: return pick_dense<2>(canon, index);
+    case 3: return pick_dense<3>(canon, index);
+    case 4: return pick_dense<4>(canon, index);
+    }
+    return nullptr;
 }
 
 __global__ void minimizer_counts_kernel(const uint64_t *__restrict__ seq_len, uint64_t n, uint64_t span, uint64_t step,
@@ -173,7 +353,33 @@ extern "C" int32_t kmc_minimizers(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, in
     p.out_index = out->index;
     p.index_base = out->index_base;
     if (p.total > 0x7fffffffull * 256) return fail(ctx, KMC_E_UNSUPPORTED, "too many minimizers for one launch");
-    minimizer_kernel<<<static_cast<unsigned>((p.total + 255) / 256), 256, 0, stream>>>(p);
+    if (step == 1 && w <= 31 && s->seq_len == nullptr) {
+        int l = 0;
+        while ((2 << l) <= w) ++l; // 2^l <= w < 2^(l+1)
+        const uint64_t g = static_cast<uint64_t>(dense_group(l));
+        DenseParams d{};
+        d.w32 = reinterpret_cast<const uint32_t *>(s->words);
+        d.nw32 = static_cast<int64_t>(s->n_words) * 2;
+        d.n_seqs = s->n_seqs;
+        d.seq_word_off = s->seq_word_offset;
+        d.stride_words = s->uniform_stride_words;
+        d.first = s->first_symbol_offset;
+        d.cnt = p.uniform_cnt;
+        d.ipr = (p.uniform_cnt + g - 1) / g;
+        d.items = d.ipr * s->n_seqs;
+        d.k = k;
+        d.w = w;
+        d.mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+        d.out_kmer = p.out_kmer;
+        d.out_hash = p.out_hash;
+        d.out_index = p.out_index;
+        d.index_base = p.index_base;
+        DenseLaunchFn fn = dense_launcher(l, p.canon != 0, p.out_index != nullptr);
+        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no dense minimizer kernel for this W");
+        fn(d, static_cast<unsigned>((d.items + 127) / 128), stream);
+    } else {
+        minimizer_kernel<<<static_cast<unsigned>((p.total + 255) / 256), 256, 0, stream>>>(p);
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev_k1, stream));
     CU(cudaStreamSynchronize(stream));

@@ -49,6 +49,78 @@ def test_single_sequence(kc, k, w):
                 assert off.tolist() == [0, len(want)]
 
 
+FX = np.uint64(0x517cc1b727220a95)
+
+
+def fast_minimizers(codes, k, w, canonical):
+    """Vectorised restatement of the same definition for dense windows (step 1) over 2-bit codes:
+    (kmers, 1-based starts, hashes) per window start."""
+    n = len(codes)
+    nk = n - k + 1
+    c = codes.astype(np.uint64)
+    fw = np.zeros(nk, dtype=np.uint64)
+    rc = np.zeros(nk, dtype=np.uint64)
+    for j in range(k):
+        fw |= c[j:j + nk] << np.uint64(2 * (k - 1 - j))
+        rc |= (np.uint64(3) - c[j:j + nk]) << np.uint64(2 * j)
+    km = np.minimum(fw, rc) if canonical else fw
+    with np.errstate(over="ignore"):
+        h = km * FX
+    nwin = nk - w + 1
+    best_h, best_j = h[:nwin].copy(), np.zeros(nwin, dtype=np.int64)
+    for j in range(1, w):
+        take = h[j:j + nwin] < best_h
+        best_h = np.where(take, h[j:j + nwin], best_h)
+        best_j = np.where(take, j, best_j)
+    idx = np.arange(nwin, dtype=np.int64) + best_j
+    return km[idx], idx + 1, best_h
+
+
+@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 23, 31])
+@pytest.mark.parametrize("k", [1, 2, 13, 16, 17, 31, 32])
+def test_dense_windows_all_classes(kc, k, w):
+    """Every W class of the register-blocked sliding-minimum kernel, K at the word / limb edges, a
+    sequence long enough to span many thread blocks and a length that leaves a partial group."""
+    from kmerscuda import _abi
+    import ctypes as C
+    rng = np.random.default_rng(1000 * k + w)
+    n = 70_001 + 3 * w
+    codes = rng.integers(0, 4, size=n).astype(np.uint8)
+    # a long homopolymer run: equal hashes inside a window, the first must win
+    codes[5000:5200] = 2
+    words = kt.pack_codes(codes.astype(np.uint64), 2)
+    rs = kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet2, words, n))
+    ctx = kc.default_context()
+    drs = kc.DeviceReadSet(ctx, rs)
+    for canonical in (False, True):
+        wk, wi, wh = fast_minimizers(codes, k, w, canonical)
+        km, idx, h, off = kc.minimizers(drs, k, w, 1, canonical=canonical, hash=True)
+        assert np.array_equal(km, wk) and np.array_equal(idx, wi) and np.array_equal(h, wh)
+        # without the index stream (another kernel instantiation), unaligned output base
+        cap = len(wk)
+        da = ctx.alloc(8 * (cap + 1))
+        out = _abi.kmc_out(da.ptr + 8, None, None, None, None, cap, 0)
+        res = _abi.kmc_result()
+        st = ctx.lib.kmc_minimizers(ctx.handle, C.byref(drs.desc), k, w, 1, 2 if canonical else 0, 0, C.byref(out), C.byref(res))
+        assert st == 0 and res.n_written == cap
+        assert np.array_equal(da.download(np.uint64, cap, 8), wk)
+
+
+def test_dense_windows_uniform_reads(kc):
+    rng = np.random.default_rng(99)
+    n_reads, length, stride = 3000, 150, 5
+    codes = rng.integers(0, 4, size=(n_reads, stride * 32)).astype(np.uint64)
+    words = np.concatenate([kt.pack_codes(row, 2) for row in codes])
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    for k, w in ((31, 10), (21, 11), (15, 4)):
+        want = [fast_minimizers(row[:length], k, w, True) for row in codes]
+        km, idx, h, so = kc.minimizers(rs, k, w, 1, canonical=True, hash=True)
+        assert np.array_equal(km, np.concatenate([x[0] for x in want]))
+        assert np.array_equal(idx, np.concatenate([x[1] for x in want]))
+        assert np.array_equal(h, np.concatenate([x[2] for x in want]))
+        assert so.tolist() == (np.arange(n_reads + 1) * (length - k - w + 2)).tolist()
+
+
 def test_read_sets(kc):
     rng = np.random.default_rng(8)
     k, w = 15, 10
