@@ -186,6 +186,24 @@ int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t 
 int32_t kmc_minimizers(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t w, int32_t step, int32_t mode,
                        uint32_t flags, const kmc_out *out, kmc_result *result);
 
+/* Bottom-s MinHash sketch under fx_hash: the reference's example
+ * `sketch(fx_hash, CanonicalDNAMers{16}(seq), 1000)` (docs/src/minhash.md:31-36; MinHash.jl is an
+ * external package: the published bottom-s definition is used) -- the s smallest DISTINCT fx_hash
+ * values over all (forward: KMC_FW, canonical: KMC_CANON) k-mers of the set, ascending, into
+ * out_hashes (device u64[s]); result->n_written = how many there are (< s if the set has fewer
+ * distinct k-mers).  2-bit sources, K <= 64.  The k-mer stream is never written: two passes over
+ * the sequence (a 4096-bucket histogram of the top hash bits, then the candidates below the
+ * threshold bucket), a sort of s + one bucket's worth of candidates. */
+int32_t kmc_minhash_sketch(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, uint64_t s,
+                           uint64_t *out_hashes, kmc_result *result);
+
+/* k-mer composition vector: table[as_integer(kmer)] += 1 for every k-mer of the set
+ * (docs/src/composition.md:28-39 counts FwDNAMers{4}; as_integer: src/kmer.jl:305-326), forward
+ * (KMC_FW) or canonical (KMC_CANON) k-mers, K <= 14.  table: device u32[4^K], caller-zeroed
+ * (accumulates, so several sets / GPUs can be summed).  2-bit sources. */
+int32_t kmc_composition(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, uint32_t *table,
+                        kmc_result *result);
+
 /* XOR and wrapping sum of n u64 words in device memory -> out[0], out[1] (host).  A cheap
  * fingerprint of a device-resident stream: parity checks and result read-back at sizes where
  * downloading the stream itself would only measure PCIe.  Synchronises. */

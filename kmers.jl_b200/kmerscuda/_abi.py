@@ -94,6 +94,10 @@ SIGNATURES = {
                                      C.POINTER(kmc_result)]),
     "kmc_minimizers": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
                                    C.POINTER(kmc_out), C.POINTER(kmc_result)]),
+    "kmc_minhash_sketch": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,
+                                       C.POINTER(kmc_result)]),
+    "kmc_composition": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p,
+                                    C.POINTER(kmc_result)]),
     "kmc_digest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "kmc_timer_begin": (C.c_int32, [C.c_void_p]),
     "kmc_timer_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -636,6 +636,42 @@ def minimizers(rs, K: int, W: int, step: int = 1, *, canonical: bool = False, ha
     return r
 
 
+def minhash_sketch(rs, K: int, s: int, *, canonical: bool = True, ctx: Optional[Context] = None):
+    """Bottom-s MinHash sketch under fx_hash -- `sketch(fx_hash, CanonicalDNAMers{K}(seq), s)` of the
+    reference's example (docs/src/minhash.md:31-36): the s smallest distinct fx_hash values over the
+    k-mers of the whole set, ascending (u64[<= s])."""
+    _check_K(K)
+    ctx = ctx or default_context()
+    drs = rs if isinstance(rs, DeviceReadSet) else DeviceReadSet(ctx, rs)
+    dh = ctx.alloc(max(int(s), 1) * 8)
+    res = kmc_result()
+    ctx._check(ctx.lib.kmc_minhash_sketch(ctx.handle, C.byref(drs.desc), K, KMC_CANON if canonical else KMC_FW, int(s), dh.ptr,
+                                          C.byref(res)))
+    out = dh.download(np.uint64, int(res.n_written))
+    dh.free()
+    return out
+
+
+def composition(rs, K: int, *, canonical: bool = False, ctx: Optional[Context] = None, table: Optional[DeviceBuffer] = None):
+    """k-mer composition vector: counts[as_integer(kmer)] over every k-mer of the set
+    (docs/src/composition.md:28-39), u32[4^K], K <= 14."""
+    _check_K(K)
+    ctx = ctx or default_context()
+    drs = rs if isinstance(rs, DeviceReadSet) else DeviceReadSet(ctx, rs)
+    n = 1 << (2 * K)
+    own = table is None
+    if own:
+        table = ctx.alloc(4 * n)
+        ctx._check(ctx.lib.kmc_memset(ctx.handle, table.ptr, 0, 4 * n))
+    res = kmc_result()
+    ctx._check(ctx.lib.kmc_composition(ctx.handle, C.byref(drs.desc), K, KMC_CANON if canonical else KMC_FW, table.ptr,
+                                       C.byref(res)))
+    host = table.download(np.uint32, n)
+    if own:
+        table.free()
+    return host, int(res.n_written), float(res.kernel_ms)
+
+
 def bucket_count(rs, K: int, bucket_bits: int, ctx: Optional[Context] = None, table: Optional[DeviceBuffer] = None):
     """Histogram of fx_hash(canonical k-mer) >> (64 - bucket_bits) (north_star extension).
     Returns (table u32[2^bucket_bits] on the host, n_kmers, kernel_ms)."""

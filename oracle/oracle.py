@@ -321,3 +321,24 @@ def batch_unambiguous(words, n_seqs, k, *, word_off=None, seq_len=None, uniform_
 
 def max_threads() -> int:
     return lib().ko_max_threads()
+
+
+# ---- consumers of the stream (docs examples) -------------------------------------------------
+def minhash_sketch(words, n, k, s, canonical=True):
+    """Bottom-s MinHash sketch under fx_hash: `sketch(fx_hash, CanonicalDNAMers{K}(seq), s)`
+    (/root/reference/docs/src/minhash.md:31-36).  MinHash.jl is an external package that is not
+    vendored; its published definition (Mash, Ondov et al. 2016) is restated: the s smallest
+    distinct hash values over all k-mers, ascending."""
+    if n < k:
+        return np.zeros(0, dtype=np.uint64)
+    _, _, h = iterate(words, n, k, CANON if canonical else FW, want_hash=True)
+    return np.unique(h)[:s]
+
+
+def composition(words, n, k, canonical=False):
+    """`counts[as_integer(kmer) + 1] += 1` for every k-mer (/root/reference/docs/src/composition.md:28-39;
+    as_integer: src/kmer.jl:305-326 -- the k-mer's bits as one integer), 0-based here."""
+    if n < k:
+        return np.zeros(4**k, dtype=np.uint32)
+    a, _, _ = iterate(words, n, k, CANON if canonical else FW)
+    return np.bincount(a[:, -1].astype(np.int64), minlength=4**k).astype(np.uint32)

@@ -259,6 +259,39 @@ def case_minimizers(ctx, steps, scale):
         del a, idx
 
 
+def case_sketch(ctx, steps, scale):
+    """Consumers that never write the stream: the bottom-1000 MinHash sketch of the reference's example
+    (docs/src/minhash.md:31-36, CanonicalDNAMers{16}) and K = 31, and the composition vector
+    (docs/src/composition.md:28-39, FwDNAMers{4}) and K = 11, over one 1 Gbp 2-bit sequence.
+    Algorithmic bytes: the sequence is read (twice for the sketch); the outputs are O(s) / O(4^K)."""
+    length = int(1_000_000_000 * scale)
+    words = rand_words_2bit((length + 31) // 32, 23)
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), 1, None, None, length, words.numel(), 2, 0)
+    res = _abi.kmc_result()
+    for k in (16, 31):
+        s = 1000
+        out = torch.empty(s, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+
+        def stepf():
+            st = ctx.lib.kmc_minhash_sketch(ctx.handle, C.byref(desc), k, CANON, s, out.data_ptr(), C.byref(res))
+            if st != 0:
+                raise RuntimeError(ctx.lib.kmc_last_error(ctx.handle).decode())
+        med, mn = timed(ctx, stepf, steps)
+        emit("MinHash sketch s=1000 of CanonicalDNAMers{%d} under fx_hash, one %d bp sequence (no stream written)" % (k, length),
+             length - k + 1, 2 * 0.25 * length + 8 * s, med, mn)
+    for k, mode, name in ((4, FW, "FwDNAMers{4}"), (11, CANON, "CanonicalDNAMers{11}")):
+        table = torch.zeros(4 ** k, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+
+        def stepc():
+            st = ctx.lib.kmc_composition(ctx.handle, C.byref(desc), k, mode, table.data_ptr(), C.byref(res))
+            if st != 0:
+                raise RuntimeError(ctx.lib.kmc_last_error(ctx.handle).decode())
+        med, mn = timed(ctx, stepc, steps)
+        emit("composition vector of %s, one %d bp sequence" % (name, length), length - k + 1, 0.25 * length + 4.0 * 4 ** k, med, mn)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="c3,c3long,c4,c5,modes")
@@ -270,7 +303,7 @@ def main():
     WARMUP = args.warmup
     torch.cuda.set_device(0)
     ctx = kc.Context(0)
-    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii, "minimizers": case_minimizers}
+    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii, "minimizers": case_minimizers, "sketch": case_sketch}
     for c in args.cases.split(","):
         table[c](ctx, args.steps, args.scale)
         torch.cuda.empty_cache()
