@@ -35,7 +35,7 @@ for _ in range(30):
     lib.kmc_timer_begin(ctx); step(); t=C.c_float(); lib.kmc_timer_end(ctx,C.byref(t)); ms.append(t.value)
 print("median %.4f min %.4f ms" % (float(np.median(ms)), float(np.min(ms))))
 '''
-libs = sys.argv[1:3]
+libs = sys.argv[1:]
 cases = [(2, 1, "canon+hash"), (2, 0, "canon"), (0, 0, "fw")]
 for mode, flags, nm in cases:
     for rep in range(2):

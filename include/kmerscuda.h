@@ -35,6 +35,7 @@ extern "C" {
 
 #define KMC_VERSION 100 /* 0.1.0 */
 #define KMC_MAX_K 128   /* N <= 4 limbs */
+#define KMC_MAX_K4 64   /* k-mers over a 4-bit alphabet (KMC_KMER4): N <= 4 limbs */
 
 /* status codes */
 #define KMC_OK 0
@@ -69,6 +70,10 @@ extern "C" {
 #define KMC_RNA 0x20u    /* the k-mer alphabet is RNAAlphabet{2} (default DNAAlphabet{2}).  The limbs are
                             bit-identical; it only matters for strict iteration over ASCII sources,
                             where U (not T) is the fourth valid letter. */
+#define KMC_KMER4 0x40u  /* the k-mers are over a 4-bit alphabet, Kmer{DNAAlphabet{4},K,N} / Kmer{RNAAlphabet{4},K,N}
+                            with N = cld(4K, 64) limbs, K <= KMC_MAX_K4: FW / FWRV / CANON from a 4-bit source
+                            (Copyable, FwKmers.jl:88-94, CanonicalKmers.jl:107-120; every symbol is allowed)
+                            or from a 2-bit source (TwoToFour, FwKmers.jl:96-102, CanonicalKmers.jl:122-129). */
 #define KMC_DIGEST 0x10u /* kmc_extract_host only: also fingerprint what was written -- xor and wrapping
                             sum of the out.a words and of the out.hash words -> result->digest[4].
                             Computed chunk by chunk inside the pipeline, while the chunk is L2-hot. */

@@ -485,6 +485,15 @@ int32_t kmc_extract(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode,
     result->err_seq = result->err_pos = 0;
     result->err_sym = 0;
     result->kernel_ms = 0.f;
+    if (flags & KMC_KMER4) {
+        st = check_kmer4(ctx, seqs, k, mode);
+        if (st) return st;
+        st = ensure_scratch(ctx, kmer4_scratch_bytes(seqs));
+        if (st) return st;
+        Scratch scratch{static_cast<char *>(ctx->scratch), ctx->scratch_bytes, 0};
+        return extract_device_kmer4(ctx, seqs, k, mode, flags, out, result, ctx->stream, KnownTotals(), 0,
+                                    (flags & KMC_NO_SYNC) == 0, scratch);
+    }
     if (seqs->src_bits != 2) return extract_device_4bit(ctx, seqs, k, mode, flags, out, result, ctx->stream);
     st = ensure_scratch(ctx, extract_scratch_bytes(seqs, k, mode));
     if (st) return st;

@@ -1,0 +1,5 @@
+// Instantiations of the extraction kernels for k-mers over 4-bit alphabets, N = 3 limbs (K in [33, 48]).
+#include "extract_kernels.cuh"
+namespace kmc {
+KMC_DEFINE_KMER4_TABLE(get_kmer4_launcher_n3, 3)
+}

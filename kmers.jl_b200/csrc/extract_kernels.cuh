@@ -45,9 +45,7 @@ struct ExtractParams {
     uint64_t wpr;        // windows per read
     uint64_t gprm;       // group slots per read
     uint64_t it_dq, it_dr; // divmod(kBlockThreads, gprm): per-iteration advance of (r, gi)
-    uint64_t it_df0;       // it_dq * wpr: per-iteration advance of the read's first flat window
     uint64_t read_bits;    // stride_units * unit_bits: stream bits from one read to the next (uniform offsets)
-    uint64_t it_dbits;     // it_dq * read_bits
     // ragged locator
     const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
     const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
@@ -116,7 +114,7 @@ struct TileCursor {
     // derived for the current item
     uint64_t f0, wcount;  // flat index of the read's first window, its window count
     uint64_t unit_off;    // ragged: where the read starts in the stream (units of p.unit_bits)
-    uint64_t ubit;        // the same in bits; uniform offsets: kept incrementally (no multiplies per item)
+    uint64_t ubit;        // the same in bits
     uint64_t seq_ibase;   // p.seq_index_base[r] (0 without it)
     uint64_t q;           // aligned flat group of this item
     int64_t wbase;        // window (within the read) of slot 0, in (-G, wcount)
@@ -150,8 +148,6 @@ struct TileCursor {
                 gi -= static_cast<uint64_t>(d) * p.gprm;
                 r += d;
             }
-            f0 = r * p.wpr;
-            ubit = r * p.read_bits;
         } else {
             r_first = __ldg(p.tile_first + blockIdx.x);
             const uint64_t r_last = __ldg(p.tile_first + blockIdx.x + 1);
@@ -217,8 +213,11 @@ struct TileCursor {
             }
             ubit = unit_off * p.unit_bits;
         } else {
-            wcount = p.wpr; // f0 and ubit follow r incrementally (init / advance)
-            if (p.seq_unit_off) ubit = (__ldg(p.seq_unit_off + r) - p.unit_bias) * p.unit_bits;
+            // (recomputed per item: carrying f0 / ubit incrementally across the iterations measured 2 % slower
+            // on the ALU-bound modes -- two more live 64-bit values per thread)
+            f0 = r * p.wpr;
+            wcount = p.wpr;
+            ubit = p.seq_unit_off ? (__ldg(p.seq_unit_off + r) - p.unit_bias) * p.unit_bits : r * p.read_bits;
         }
         q = f0 / G + gi;
         wbase = static_cast<int64_t>(q * G - f0);
@@ -227,10 +226,11 @@ struct TileCursor {
         jhi = rem < G ? static_cast<int>(rem) : G;
     }
 
-    // bit offset in the stream of slot 0's first symbol
+    // bit offset in the stream of slot 0's first symbol (BPS = bits per symbol of the stream)
+    template <int BPS = 2>
     KMC_DEV int64_t bit(const ExtractParams &p) const
     {
-        return static_cast<int64_t>(ubit) + 2 * (static_cast<int64_t>(p.first) + wbase);
+        return static_cast<int64_t>(ubit) + BPS * (static_cast<int64_t>(p.first) + wbase);
     }
 
     // to the item kBlockThreads further on
@@ -239,13 +239,9 @@ struct TileCursor {
         if (!RAGGED) {
             r += p.it_dq;
             gi += p.it_dr;
-            f0 += p.it_df0;
-            ubit += p.it_dbits;
             if (gi >= p.gprm) {
                 gi -= p.gprm;
                 ++r;
-                f0 += p.wpr;
-                ubit += p.read_bits;
             }
         }
     }
@@ -256,14 +252,12 @@ inline void set_iteration_strides(ExtractParams &p)
 {
     p.it_dq = kBlockThreads / p.gprm;
     p.it_dr = kBlockThreads % p.gprm;
-    p.it_df0 = p.it_dq * p.wpr;
     p.read_bits = p.stride_units * p.unit_bits;
-    p.it_dbits = p.it_dq * p.read_bits;
 }
 
 
 
-template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false>
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false, int BPS = 2>
 __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractParams p)
 {
     constexpr int G = GroupOf<N>::G;
@@ -290,7 +284,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
         const int jlo = cur.jlo, jhi = cur.jhi;
 
         if (jhi > jlo) {
-            const int64_t bit = cur.bit(p);
+            const int64_t bit = cur.template bit<BPS>(p);
             if (STRICT4) {
                 // FourToTwo, strict (FwKmers.jl:104-115, CanonicalKmers.jl:131-144): an uncertain symbol
                 // is an error.  Record the first offending window; the host resolves it to the symbol
@@ -302,7 +296,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             uint32_t x[NX];
             load_block<NX>(p.w32, p.nw32, bit, x);
             uint64_t fw[G][N], rv[G][N];
-            block_kmers<N, NX, G, WANT_FW, WANT_RV>(x, p.s0, p.head_mask, fw, rv);
+            block_kmers<N, NX, G, WANT_FW, WANT_RV, BPS>(x, p.s0, p.head_mask, fw, rv);
 
             // what lands in out_a, and its hash
             uint64_t a[G][N], h[G];
@@ -402,14 +396,14 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
 // extract_n*.cu so the instantiations compile in parallel.
 using ExtractLaunchFn = cudaError_t (*)(ExtractParams, int sm_count, cudaStream_t);
 
-template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false>
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false, int BPS = 2>
 cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t stream)
 {
     const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
     if (tiles == 0) return cudaSuccess;
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     set_iteration_strides(p);
-    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4>
+    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS>
         <<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -457,6 +451,42 @@ constexpr int MODE_BUCKET_IDS = -2; // canonical + fx_hash -> flat array of 32-b
         if (nx == NXMAX) return pick_mode_##N<NXMAX>(mode, hash, ragged);                           \
         if (nx == NXMAX - 1) return pick_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
         if (nx == NXMAX - 2) return pick_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
+        return nullptr;                                                                             \
+    }
+
+// Kmer{<:NucleicAcidAlphabet{4}} (BPS = 4: the Copyable 4 -> 4 scheme, and TwoToFour over an expanded
+// stream), one translation unit per N (extract_b4_n{1,2,3,4}.cu): K <= 16 N, the three streaming modes.
+ExtractLaunchFn get_kmer4_launcher_n1(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_kmer4_launcher_n2(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_kmer4_launcher_n3(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_kmer4_launcher_n4(int nx, int mode, bool hash, bool ragged);
+
+#define KMC_DEFINE_KMER4_TABLE(FN, N)                                                               \
+    template <int NX, int MODE>                                                                     \
+    static ExtractLaunchFn pickb4_##N(bool hash, bool ragged)                                       \
+    {                                                                                               \
+        if (hash)                                                                                   \
+            return ragged ? &launch_extract<N, NX, MODE, true, true, SINK_STREAMS, false, 4>        \
+                          : &launch_extract<N, NX, MODE, true, false, SINK_STREAMS, false, 4>;      \
+        return ragged ? &launch_extract<N, NX, MODE, false, true, SINK_STREAMS, false, 4>           \
+                      : &launch_extract<N, NX, MODE, false, false, SINK_STREAMS, false, 4>;         \
+    }                                                                                               \
+    template <int NX>                                                                               \
+    static ExtractLaunchFn pickb4_mode_##N(int mode, bool hash, bool ragged)                        \
+    {                                                                                               \
+        switch (mode) {                                                                             \
+        case MODE_FW: return pickb4_##N<NX, MODE_FW>(hash, ragged);                                 \
+        case MODE_FWRV: return pickb4_##N<NX, MODE_FWRV>(hash, ragged);                             \
+        case MODE_CANON: return pickb4_##N<NX, MODE_CANON>(hash, ragged);                           \
+        }                                                                                           \
+        return nullptr;                                                                             \
+    }                                                                                               \
+    ExtractLaunchFn FN(int nx, int mode, bool hash, bool ragged)                                    \
+    {                                                                                               \
+        constexpr int NXMAX = (64 * N + 4 * GroupOf<N>::G - 4 + 31) / 32;                           \
+        if (nx == NXMAX) return pickb4_mode_##N<NXMAX>(mode, hash, ragged);                         \
+        if (nx == NXMAX - 1) return pickb4_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
+        if (nx == NXMAX - 2) return pickb4_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
         return nullptr;                                                                             \
     }
 

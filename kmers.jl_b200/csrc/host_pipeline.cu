@@ -72,9 +72,14 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
     result->kernel_ms = 0.f;
     memset(result->digest, 0, sizeof result->digest);
 
-    const Geometry ge = geometry(k);
+    const bool kmer4 = (flags & KMC_KMER4) != 0; // k-mers over a 4-bit alphabet (kmer4.cu): no recoding, no checks
+    if (kmer4) {
+        st = check_kmer4(ctx, hs, k, mode);
+        if (st) return st;
+    }
+    const Geometry ge = geometry(k, kmer4 ? 4 : 2);
     const uint64_t N = static_cast<uint64_t>(ge.n_limbs);
-    const bool four = hs->src_bits != 2; // recoded on the device first: 4-bit words or ASCII bytes (fourbit.h)
+    const bool four = hs->src_bits != 2 && !kmer4; // recoded on the device first: 4-bit words or ASCII bytes (fourbit.h)
     const bool ascii = hs->src_bits == 8;
     const uint64_t spw = ascii ? 1 : hs->src_bits == 4 ? 16 : 32; // symbols per source unit (word, or byte for ASCII)
     const uint64_t unit_bytes = ascii ? 1 : 8;
@@ -219,7 +224,7 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
     worst.n_words = max_words;
     worst.n_seqs = single ? 1 : max_seq;
     if (single) worst.seq_len = nullptr;
-    const uint64_t scratch_per_slot = round_up(extract_scratch_bytes(&worst, k, mode), 256);
+    const uint64_t scratch_per_slot = round_up(kmer4 ? kmer4_scratch_bytes(&worst) : extract_scratch_bytes(&worst, k, mode), 256);
     st = ensure_scratch(ctx, scratch_per_slot * n_slots);
     if (st) return st;
     st = ensure_host_small(ctx);
@@ -377,7 +382,8 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
         scratch.used = 0;
         if (!four) {
             kmc_result r{};
-            st = extract_device(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch);
+            st = kmer4 ? extract_device_kmer4(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch)
+                       : extract_device(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch);
             if (st) return st;
             st = digest_chunk(c, sl, c.nout);
             if (st) return st;

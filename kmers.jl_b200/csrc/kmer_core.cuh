@@ -46,6 +46,19 @@ KMC_DEV uint32_t rev2_32(uint32_t x)
     return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
 }
 
+// 4-bit alphabets (Kmer{DNAAlphabet{4}} / Kmer{RNAAlphabet{4}}).  The closed form is
+// the same with nibbles for bit pairs: LongSequence stores the first symbol lowest, Kmer highest, so
+//   forward k-mer             fw = rev4(W)   reversebits(x, BitsPerSymbol{4}): nibble order reversed
+//   reverse-complement k-mer  rv = comp4(W)  complement_bitpar for 4-bit alphabets reverses the four
+//                                            bits of every nibble (A=1<->T=8, C=2<->G=4, IUPAC sets
+//                                            likewise; src/transformations.jl:14-18) -- in place
+KMC_DEV uint32_t rev4_32(uint32_t x)
+{
+    x = __byte_perm(x, 0u, 0x0123);
+    return ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+}
+KMC_DEV uint32_t comp4_32(uint32_t x) { return __brev(rev4_32(x)); }
+
 KMC_DEV uint64_t pack64(uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; }
 
 // 64 bits of a 32-bit-word stream starting at bit offset `off`.  `off` is a compile-time
@@ -182,10 +195,11 @@ KMC_DEV void load_block(const uint32_t *__restrict__ w32, int64_t nw32, int64_t 
     for (int i = 0; i < NX; ++i) x[i] = __funnelshift_r(a[i], a[i + 1], s);
 }
 
-// fw[j] / rv[j] for the G windows of a block, limbs head first.
-//   s0        = 32*NX - 2K - 2(G-1), in [0, 32)
+// fw[j] / rv[j] for the G windows of a block, limbs head first.  BPS = bits per symbol of the k-mer
+// alphabet (and of the stream): 2 or 4.
+//   s0        = 32*NX - BPS*K - BPS*(G-1), in [0, 32)
 //   head_mask = get_mask (src/kmer.jl:603-605)
-template <int N, int NX, int G, bool WANT_FW, bool WANT_RV>
+template <int N, int NX, int G, bool WANT_FW, bool WANT_RV, int BPS = 2>
 KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mask, uint64_t (&fw)[G][N],
                          uint64_t (&rv)[G][N])
 {
@@ -194,12 +208,12 @@ KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mas
         // src/transformations.jl:21-25), then each window is a static funnel shift.
         uint32_t nx[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) nx[i] = ~x[i];
+        for (int i = 0; i < NX; ++i) nx[i] = BPS == 2 ? ~x[i] : comp4_32(x[i]);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
 #pragma unroll
             for (int m = 0; m < N; ++m) { // m = 0 is the least significant limb
-                uint64_t v = stream64<NX>(nx, 2 * j + 64 * m);
+                uint64_t v = stream64<NX>(nx, BPS * j + 64 * m);
                 if (m == N - 1) v &= head_mask;
                 rv[j][N - 1 - m] = v;
             }
@@ -209,7 +223,7 @@ KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mas
         // rev2 of the whole block: symbol i of the x-stream lands at symbol 16*NX-1-i.
         uint32_t y[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) y[i] = rev2_32(x[NX - 1 - i]);
+        for (int i = 0; i < NX; ++i) y[i] = BPS == 2 ? rev2_32(x[NX - 1 - i]) : rev4_32(x[NX - 1 - i]);
         // drop the s0 bits that lie beyond the last window
         uint32_t t[NX];
 #pragma unroll
@@ -218,7 +232,7 @@ KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mas
         for (int j = 0; j < G; ++j) {
 #pragma unroll
             for (int m = 0; m < N; ++m) {
-                uint64_t v = stream64<NX>(t, 2 * (G - 1 - j) + 64 * m);
+                uint64_t v = stream64<NX>(t, BPS * (G - 1 - j) + 64 * m);
                 if (m == N - 1) v &= head_mask;
                 fw[j][N - 1 - m] = v;
             }

@@ -24,15 +24,15 @@ struct Geometry {
     uint64_t head_mask;
 };
 
-// src/kmer.jl:117-137 (N = cld(2K, 64)) and :603-605 (get_mask)
-inline Geometry geometry(int k)
+// src/kmer.jl:117-137 (N = cld(K * bps, 64)) and :603-605 (get_mask); bps = bits per symbol of the k-mer alphabet
+inline Geometry geometry(int k, int bps = 2)
 {
     Geometry ge;
-    ge.n_limbs = (2 * k + 63) / 64;
+    ge.n_limbs = (bps * k + 63) / 64;
     ge.g = group_of(ge.n_limbs);
-    ge.nx = (2 * k + 2 * ge.g - 2 + 31) / 32;
-    ge.s0 = static_cast<uint32_t>(32 * ge.nx - 2 * k - 2 * (ge.g - 1));
-    int used = 2 * k - 64 * (ge.n_limbs - 1); // bits used in the head limb, 2..64
+    ge.nx = (bps * k + bps * ge.g - bps + 31) / 32;
+    ge.s0 = static_cast<uint32_t>(32 * ge.nx - bps * k - bps * (ge.g - 1));
+    int used = bps * k - 64 * (ge.n_limbs - 1); // bits used in the head limb, bps..64
     ge.head_mask = used >= 64 ? ~0ull : ((1ull << used) - 1);
     return ge;
 }
@@ -104,5 +104,12 @@ int32_t extract_device(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode,
                        kmc_result *res, cudaStream_t stream, const KnownTotals &known, uint64_t unit_bias, bool sync,
                        Scratch &scratch);
 uint64_t extract_scratch_bytes(const kmc_seqs *s, int k, int mode);
+
+// kmer4.cu: k-mers over a 4-bit alphabet (KMC_KMER4) from 4-bit (Copyable) or 2-bit (TwoToFour) sources
+int32_t check_kmer4(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode);
+uint64_t kmer4_scratch_bytes(const kmc_seqs *s);
+int32_t extract_device_kmer4(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,
+                             kmc_result *res, cudaStream_t stream, const KnownTotals &known, uint64_t unit_bias, bool sync,
+                             Scratch &scratch);
 
 } // namespace kmc

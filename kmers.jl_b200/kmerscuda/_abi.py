@@ -23,7 +23,9 @@ KMC_E_UNSUPPORTED = 6
 
 KMC_FW, KMC_FWRV, KMC_CANON, KMC_UNAMBIG = 0, 1, 2, 3
 KMC_HASH_FX, KMC_AOS, KMC_NO_SYNC, KMC_OUT_DEVICE, KMC_DIGEST, KMC_RNA = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+KMC_KMER4 = 0x40
 KMC_MAX_K = 128
+KMC_MAX_K4 = 64
 
 
 class kmc_seqs(C.Structure):

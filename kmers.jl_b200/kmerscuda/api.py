@@ -23,8 +23,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _abi
-from ._abi import (KMC_AOS, KMC_CANON, KMC_E_AMBIGUOUS, KMC_E_BAD_K, KMC_FW, KMC_FWRV, KMC_HASH_FX, KMC_MAX_K,
-                   KMC_NO_SYNC, KMC_OK, KMC_OUT_DEVICE, KMC_RNA, KMC_UNAMBIG, kmc_out, kmc_result, kmc_seqs)
+from ._abi import (KMC_AOS, KMC_CANON, KMC_E_AMBIGUOUS, KMC_E_BAD_K, KMC_FW, KMC_FWRV, KMC_HASH_FX, KMC_KMER4, KMC_MAX_K,
+                   KMC_MAX_K4, KMC_NO_SYNC, KMC_OK, KMC_OUT_DEVICE, KMC_RNA, KMC_UNAMBIG, kmc_out, kmc_result, kmc_seqs)
 
 # ----------------------------------------------------------------------------------------------
 # alphabets (only what the path needs: the 2- and 4-bit nucleic acid alphabets)
@@ -60,9 +60,9 @@ class KmersCUDAError(RuntimeError):
     pass
 
 
-def n_limbs(K: int) -> int:
-    """N of Kmer{A,K,N} for a 2-bit alphabet (src/kmer.jl:97-111)."""
-    return (2 * K + 63) // 64
+def n_limbs(K: int, bits: int = 2) -> int:
+    """N of Kmer{A,K,N} (src/kmer.jl:97-111): cld(K * bits per symbol, 64)."""
+    return (bits * K + 63) // 64
 
 
 def _check_K(K):
@@ -367,13 +367,13 @@ def extract(mode: int, rs, K: int, *, A: Alphabet = DNAAlphabet2, hash: bool = F
     only downloaded afterwards.
     """
     _check_K(K)
-    if K > KMC_MAX_K:
-        raise ValueError(f"K must be at most {KMC_MAX_K}")
-    if A.bits != 2:
-        raise NotImplementedError("only 2-bit output alphabets are on the accelerated path")
+    if K > (KMC_MAX_K if A.bits == 2 else KMC_MAX_K4):
+        raise ValueError(f"K must be at most {KMC_MAX_K if A.bits == 2 else KMC_MAX_K4} for {A.name}")
+    if A.bits == 4 and mode == KMC_UNAMBIG:
+        raise TypeError("UnambiguousKmers{A<:TwoBit}: the k-mer alphabet must be a 2-bit alphabet")  # UnambiguousKmers.jl:29
     ctx = ctx or default_context()
     lib = ctx.lib
-    N = n_limbs(K)
+    N = n_limbs(K, A.bits)
     if isinstance(rs, DeviceReadSet):
         drs, hrs = rs, rs.host
     else:
@@ -383,6 +383,8 @@ def extract(mode: int, rs, K: int, *, A: Alphabet = DNAAlphabet2, hash: bool = F
     want_index = mode == KMC_UNAMBIG
     a_elems = (2 * N if two else N + 1 if want_index else N) if aos else N
     flags = (KMC_HASH_FX if hash else 0) | (KMC_AOS if aos else 0) | (KMC_RNA if A.name.startswith("RNA") else 0)
+    if A.bits == 4:
+        flags |= KMC_KMER4  # Copyable (4-bit source) or TwoToFour (2-bit source): construction.jl:75-100
     res = kmc_result()
 
     if host_path and device_out:

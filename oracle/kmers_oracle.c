@@ -511,6 +511,110 @@ int ko_max_threads(void)
 }
 
 /* ======================================================================
+ * k-mers over the 4-bit alphabets: Kmer{DNAAlphabet{4},K,N}, N = cld(4K, 64) (src/kmer.jl:117-137
+ * with bps = 4).  Sources: 4-bit LongSequence (Copyable) or 2-bit LongSequence (TwoToFour).
+ * BioSequences (not vendored) supplies complement / reversebits for 4-bit encodings:
+ *   complement of a 4-bit nucleotide reverses its four bits (A=0001 <-> T=1000, C=0010 <-> G=0100,
+ *   ambiguity sets likewise, N and gap are fixed points); complement_bitpar does so per nibble;
+ *   reversebits(x, BitsPerSymbol{4}) reverses the order of the 16 nibbles.
+ * Pinned by the reference's FwRvIterator{DNAAlphabet{4},3}("AGCGT") doctest
+ * (src/iterators/CanonicalKmers.jl:13-18) and by the string-level definitions of the tests.
+ * ====================================================================== */
+INL u64 complement_nibble(u64 e) { return ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3); }
+
+INL u64 complement_bitpar4(u64 x)
+{
+    return ((x & 0x1111111111111111ull) << 3) | ((x & 0x8888888888888888ull) >> 3) |
+           ((x & 0x2222222222222222ull) << 1) | ((x & 0x4444444444444444ull) >> 1);
+}
+
+INL u64 reversebits4(u64 x)
+{
+    x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+    return __builtin_bswap64(x);
+}
+
+/* src/construction_utils.jl:129-134 with bps = 4 */
+INL void shift_encoding4(u64 *d, int K, const int N, u64 enc)
+{
+    leftshift_carry(d, N, 4, enc);
+    d[0] &= get_mask(K, N, 4);
+}
+
+/* src/kmer.jl:511-518 with bps = 4 */
+INL void shift_first_encoding4(u64 *d, int K, const int N, u64 enc)
+{
+    rightshift_carry(d, N, 4, 0);
+    d[0] |= left_shift(enc, (unsigned)((elements_in_head(K, N, 4) - 1) * 4));
+}
+
+/* src/transformations.jl:14-18 (no head mask: the complement of gap is gap), :1-10, :32-34 */
+INL void reverse_complement4(u64 *d, int K, const int N)
+{
+    u64 t[KO_MAX_LIMBS];
+    for (int i = 0; i < N; ++i) d[i] = complement_bitpar4(d[i]);
+    for (int i = 0; i < N; ++i) t[i] = reversebits4(d[N - 1 - i]);
+    rightshift_carry(t, N, (unsigned)bits_unused(K, N, 4), 0);
+    for (int i = 0; i < N; ++i) d[i] = t[i];
+}
+
+/* FwKmers.jl:62-66 (first window), :88-94 (Copyable), :96-102 (TwoToFour);
+ * CanonicalKmers.jl:61-66, :107-120 (Copyable, 4-bit), :122-129 (TwoToFour), :220-225.
+ * src_bits = 4: Copyable; src_bits = 2: TwoToFour (enc4 = 1 << enc2, construction_utils.jl:27-39). */
+static void iterate4_one(const u64 *words, u64 first, u64 len, int src_bits, int K, int N, int mode,
+                         u64 *out_a, u64 *out_b, u64 *out_hash, u64 *n_out)
+{
+    u64 fw[KO_MAX_LIMBS], rv[KO_MAX_LIMBS];
+    u64 n = 0;
+    *n_out = 0;
+    if (len < (u64)K) return;
+    for (int i = 0; i < N; ++i) fw[i] = 0;
+    for (u64 i = first + 1; i < first + 1 + (u64)K; ++i) {
+        u64 enc = extract_encoded_element(words, i, src_bits);
+        if (src_bits == 2) enc = left_shift(1, (unsigned)enc);
+        leftshift_carry(fw, N, 4, enc);
+    }
+    if (mode != KO_FW) {
+        for (int i = 0; i < N; ++i) rv[i] = fw[i];
+        reverse_complement4(rv, K, N);
+    }
+    u64 i = (u64)K + 1;
+    for (;;) {
+        const u64 *a = fw;
+        if (mode == KO_CANON) a = (cmp_limbs(fw, rv, N) == -1) ? fw : rv;
+        for (int j = 0; j < N; ++j) out_a[n * (u64)N + j] = a[j];
+        if (mode == KO_FWRV)
+            for (int j = 0; j < N; ++j) out_b[n * (u64)N + j] = rv[j];
+        if (out_hash) out_hash[n] = fx_hash_limbs(a, N, 0);
+        ++n;
+        if (i > len) break;
+        u64 enc = extract_encoded_element(words, first + i, src_bits);
+        u64 rc;
+        if (src_bits == 2) {
+            rc = left_shift(1, (unsigned)(enc ^ 3u));
+            enc = left_shift(1, (unsigned)enc);
+        } else {
+            rc = complement_nibble(enc);
+        }
+        shift_encoding4(fw, K, N, enc);
+        if (mode != KO_FW) shift_first_encoding4(rv, K, N, rc);
+        ++i;
+    }
+    *n_out = n;
+}
+
+int ko_n_limbs4(int K) { return n_limbs(K, 4); }
+
+int ko_iterate4(const uint64_t *words, uint64_t first, uint64_t len, int src_bits, int K, int mode,
+                uint64_t *out_a, uint64_t *out_b, uint64_t *out_hash, uint64_t *n_out)
+{
+    if (K < 1 || n_limbs(K, 4) > KO_MAX_LIMBS) return KO_E_BAD_K;
+    if (mode < KO_FW || mode > KO_CANON || (src_bits != 2 && src_bits != 4)) return KO_E_BAD_K;
+    iterate4_one(words, first, len, src_bits, K, n_limbs(K, 4), mode, out_a, out_b, out_hash, n_out);
+    return KO_OK;
+}
+
+/* ======================================================================
  * ASCII sources (the AsciiEncode recoding scheme, src/construction.jl:95-96).
  *
  * BioSequences.ascii_encode(A, byte) is not in the reference tree; restated from

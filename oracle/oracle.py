@@ -39,6 +39,9 @@ def lib():
         L.ko_n_limbs.restype = C.c_int
         L.ko_n_windows.restype = C.c_uint64
         L.ko_n_windows.argtypes = [C.c_uint64, C.c_int]
+        L.ko_iterate4.restype = C.c_int
+        L.ko_iterate4.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.ko_iterate.restype = C.c_int
         L.ko_iterate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u64p, _u64p]
@@ -120,6 +123,31 @@ def iterate(words, length, k, mode, src_bits=2, first=0, want_hash=False):
                       C.byref(n_out), C.byref(ep), C.byref(ee))
     if st == KO_E_AMBIGUOUS:
         raise AmbiguousError(0, ep.value, ee.value, n_out.value)
+    if st != KO_OK:
+        raise ValueError(f"oracle status {st}")
+    assert n_out.value == n
+    return a, b, h
+
+
+def n_limbs4(k):
+    """N of Kmer{<:NucleicAcidAlphabet{4},K,N} (src/kmer.jl:117-137, bps = 4)."""
+    return (4 * k + 63) // 64
+
+
+def iterate4(words, length, k, mode, src_bits=4, first=0, want_hash=False):
+    """One sequence -> k-mers over a 4-bit alphabet (Copyable from a 4-bit source, TwoToFour from a
+    2-bit source).  Returns (a, b, hash) like iterate()."""
+    L = lib()
+    if k < 1:
+        raise ValueError("K must be at least 1")
+    N = n_limbs4(k)
+    n = max(0, length - k + 1)
+    w = _words(words)
+    a = np.zeros((n, N), dtype=np.uint64)
+    b = np.zeros((n, N), dtype=np.uint64) if mode == FWRV else None
+    h = np.zeros(n, dtype=np.uint64) if want_hash else None
+    n_out = C.c_uint64(0)
+    st = L.ko_iterate4(_ptr(w), first, length, src_bits, k, mode, _ptr(a), _ptr(b), _ptr(h), C.byref(n_out))
     if st != KO_OK:
         raise ValueError(f"oracle status {st}")
     assert n_out.value == n

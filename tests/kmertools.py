@@ -131,3 +131,35 @@ def random_dna(rng: np.random.Generator, n: int, ambiguous: float = 0.0) -> str:
         mask = rng.random(n) < ambiguous
         base = np.where(mask, amb, base)
     return "".join(base.tolist())
+
+
+# ---- k-mers over the 4-bit alphabets (independent string-level definitions) ---------------------
+# IUPAC complements (BioSymbols: complement of an ambiguity set = the set of complements)
+COMPLEMENT4 = {"A": "T", "C": "G", "G": "C", "T": "A", "M": "K", "K": "M", "R": "Y", "Y": "R", "W": "W", "S": "S",
+               "V": "B", "B": "V", "H": "D", "D": "H", "N": "N", "-": "-"}
+SYM4 = "-ACMGRSVTWYHKDBN"
+
+
+def n_limbs4(k: int) -> int:
+    return (4 * k + 63) // 64
+
+
+def kmer4_limbs(s: str) -> tuple:
+    """Kmer{DNAAlphabet{4},K,N}.data of a string: first symbol in the highest used nibble."""
+    v = 0
+    for c in s.upper().replace("U", "T"):
+        v = (v << 4) | CODE4[c]
+    N = n_limbs4(len(s))
+    return tuple((v >> (64 * (N - 1 - i))) & (2**64 - 1) for i in range(N))
+
+
+def revcomp4(s: str) -> str:
+    return "".join(COMPLEMENT4[c] for c in reversed(s.upper().replace("U", "T")))
+
+
+def naive_fwrv4(seq: str, k: int):
+    return [(kmer4_limbs(seq[i:i + k]), kmer4_limbs(revcomp4(seq[i:i + k]))) for i in range(len(seq) - k + 1)]
+
+
+def random_iupac(rng: np.random.Generator, n: int) -> str:
+    return "".join(rng.choice(list(SYM4), size=n).tolist())

@@ -259,6 +259,36 @@ def case_minimizers(ctx, steps, scale):
         del a, idx
 
 
+def case_kmer4(ctx, steps, scale):
+    """k-mers over the 4-bit alphabet on the C2 shape: CanonicalKmers{DNAAlphabet{4},31} (2 limbs) + fx_hash from a
+    4-bit source (Copyable; any IUPAC symbol) and from a 2-bit source (TwoToFour), FwKmers{DNAAlphabet{4},16} (1 limb)."""
+    n_reads, length, k = int(10_000_000 * scale), 150, 31
+    wpr = length - k + 1
+    n = n_reads * wpr
+    a = torch.empty(2 * n, dtype=torch.int64, device="cuda")
+    h = torch.empty(n, dtype=torch.int64, device="cuda")
+    res = _abi.kmc_result()
+    w4 = rand_words_2bit(n_reads * 10, 7)   # random nibbles: every IUPAC symbol
+    w2 = rand_words_2bit(n_reads * 5, 8)
+    fl = _abi.KMC_KMER4 | _abi.KMC_NO_SYNC
+    out = _abi.kmc_out(a.data_ptr(), None, h.data_ptr(), None, None, n, 0)
+    d4 = _abi.kmc_seqs(w4.data_ptr(), w4.numel(), n_reads, None, None, length, 10, 4, 0)
+    d2 = _abi.kmc_seqs(w2.data_ptr(), w2.numel(), n_reads, None, None, length, 5, 2, 0)
+    med, mn = timed(ctx, lambda: run_extract(ctx, d4, k, CANON, fl | _abi.KMC_HASH_FX, out, res), steps)
+    emit("C2-shape CanonicalKmers{DNAAlphabet{4},31}+fx_hash (2 limbs), 4-bit source (Copyable), %d x 150 bp" % n_reads, n,
+         (0.5 * length / wpr + 24) * n, med, mn)
+    med, mn = timed(ctx, lambda: run_extract(ctx, d2, k, CANON, fl | _abi.KMC_HASH_FX, out, res), steps)
+    emit("C2-shape CanonicalKmers{DNAAlphabet{4},31}+fx_hash (2 limbs), 2-bit source (TwoToFour), %d x 150 bp" % n_reads, n,
+         (0.25 * length / wpr + 24) * n, med, mn)
+    k16 = 16
+    n16 = n_reads * (length - k16 + 1)
+    a16 = torch.empty(n16, dtype=torch.int64, device="cuda")
+    out16 = _abi.kmc_out(a16.data_ptr(), None, None, None, None, n16, 0)
+    med, mn = timed(ctx, lambda: run_extract(ctx, d4, k16, FW, fl, out16, res), steps)
+    emit("C2-shape FwKmers{DNAAlphabet{4},16} (1 limb), 4-bit source, %d x 150 bp" % n_reads, n16,
+         (0.5 * length / (length - k16 + 1) + 8) * n16, med, mn)
+
+
 def case_sketch(ctx, steps, scale):
     """Consumers that never write the stream: the bottom-1000 MinHash sketch of the reference's example
     (docs/src/minhash.md:31-36, CanonicalDNAMers{16}) and K = 31, and the composition vector
@@ -303,7 +333,7 @@ def main():
     WARMUP = args.warmup
     torch.cuda.set_device(0)
     ctx = kc.Context(0)
-    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii, "minimizers": case_minimizers, "sketch": case_sketch}
+    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii, "minimizers": case_minimizers, "sketch": case_sketch, "kmer4": case_kmer4}
     for c in args.cases.split(","):
         table[c](ctx, args.steps, args.scale)
         torch.cuda.empty_cache()
