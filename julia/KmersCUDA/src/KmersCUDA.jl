@@ -18,7 +18,7 @@ using Kmers
 using Kmers: FwKmers, FwRvIterator, CanonicalKmers, UnambiguousKmers, Kmer, derive_type
 using Libdl
 
-export fx_hash_device, hash_device, extract, set_library!
+export fx_hash_device, hash_device, extract, set_library!, minhash_sketch, composition, minimizers
 
 # ---------------------------------------------------------------------------------------------
 # library handle
@@ -31,6 +31,7 @@ const KMC_E_BAD_K = Int32(1)
 const KMC_E_AMBIGUOUS = Int32(3)
 const KMC_FW, KMC_FWRV, KMC_CANON, KMC_UNAMBIG = Int32(0), Int32(1), Int32(2), Int32(3)
 const KMC_HASH_FX, KMC_AOS = UInt32(1), UInt32(2)
+const KMC_KMER4 = UInt32(0x40)   # k-mers over a 4-bit alphabet (Copyable 4 -> 4, TwoToFour)
 
 # struct kmc_seqs / kmc_out / kmc_result of include/kmerscuda.h (same field order and sizes)
 struct KmcSeqs
@@ -127,10 +128,35 @@ end
     KmersCUDA.collect(it) -> Vector{eltype}
 
 Same result as `Base.collect(it)` for `FwKmers`, `FwRvIterator`, `CanonicalKmers` and
-`UnambiguousKmers` whose source is a `LongSequence` over a 2- or 4-bit nucleotide alphabet and
-whose k-mer alphabet is 2-bit.  `Kmer{A,K,N}` and tuples of `Kmer`/`Int` are isbits, so the
-device writes the Julia element layout directly into the vector (KMC_AOS).
+`UnambiguousKmers` whose source is a `LongSequence` over a 2- or 4-bit nucleotide alphabet.  The
+k-mer alphabet may be 2-bit (Copyable / FourToTwo) or, for the first three iterators, 4-bit
+(Copyable 4 -> 4 and TwoToFour: `KMC_KMER4`, K <= 64).  `Kmer{A,K,N}` and tuples of `Kmer`/`Int`
+are isbits, so the device writes the Julia element layout directly into the vector (KMC_AOS).
 """
+function collect(it::Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, K}};
+        ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{4}, K}
+    seq = source(it)
+    seq isa LongSequence || throw(ArgumentError("4-bit k-mers are accelerated for LongSequence sources"))
+    K <= 64 || throw(ArgumentError("KmersCUDA handles K <= 64 for k-mers over a 4-bit alphabet"))
+    T = derive_type(Kmer{A, K})
+    mode = mode_of(it)
+    len = length(seq)
+    nwin = max(0, len - K + 1)
+    words = seq.data
+    ET = mode == KMC_FWRV ? Tuple{T, T} : T
+    out = Vector{ET}(undef, nwin)
+    res = KmcResult()
+    GC.@preserve words out begin
+        s = Ref(KmcSeqs(pointer(words), length(words), 1, C_NULL, C_NULL, len, length(words), src_bits(typeof(seq)), 0))
+        o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, C_NULL, C_NULL, C_NULL, nwin, 0))
+        st = ccall((:kmc_extract_host, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
+            ctx.handle, s, K, mode, KMC_AOS | KMC_KMER4, o, pointer_from_objref(res))
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    return out
+end
+
 function collect(it::Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, K}, UnambiguousKmers{A, K}};
         ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
     seq = source(it)
@@ -314,5 +340,102 @@ end
 "`hash.(v, h)` (Base.hash of k-mers): on the device when this Julia's hashing matches, else on the host."
 hash_device(v::Vector{<:Kmer}, h::UInt = UInt(0); ctx::Context = default_context()) =
     base_hash_matches() ? _hash_device(v, h; ctx) : hash.(v, h)
+
+# ---------------------------------------------------------------------------------------------
+# consumers of the stream that never materialise it (device-resident sequence, small results)
+# ---------------------------------------------------------------------------------------------
+function with_device_sequence(f, ctx::Context, seq::LongSequence)
+    words = seq.data
+    dw = device_upload(ctx, words)
+    try
+        s = Ref(KmcSeqs(dw, length(words), 1, C_NULL, C_NULL, length(seq), length(words), src_bits(typeof(seq)), 0))
+        return f(s)
+    finally
+        device_free(ctx, dw)
+    end
+end
+
+"""
+    minhash_sketch(CanonicalKmers{A,K}(seq) | FwKmers{A,K}(seq), s) -> Vector{UInt64}
+
+Bottom-`s` MinHash sketch under `fx_hash` -- `sketch(fx_hash, CanonicalDNAMers{K}(seq), s)` of
+docs/src/minhash.md:31-36 -- the `s` smallest distinct hash values, ascending (`kmc_minhash_sketch`).
+"""
+function minhash_sketch(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}}, s::Integer;
+        ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
+    out = Vector{UInt64}(undef, s)
+    res = KmcResult()
+    with_device_sequence(ctx, source(it)) do d
+        dout = Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 8 * s, dout)
+        st = ccall((:kmc_minhash_sketch, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt64, Ptr{Cvoid}, Ptr{KmcResult}),
+            ctx.handle, d, K, mode_of(typeof(it)), s, dout[], pointer_from_objref(res))
+        st == KMC_OK && ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64),
+            ctx.handle, out, dout[], 8 * res.n_written)
+        device_free(ctx, dout[])
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    resize!(out, res.n_written)
+    return out
+end
+
+"""
+    composition(FwKmers{A,K}(seq) | CanonicalKmers{A,K}(seq)) -> Vector{UInt32}  (length 4^K, K <= 14)
+
+`counts[as_integer(kmer) + 1] += 1` for every k-mer (docs/src/composition.md:28-39), `kmc_composition`.
+"""
+function composition(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}};
+        ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
+    counts = zeros(UInt32, 4^K)
+    res = KmcResult()
+    with_device_sequence(ctx, source(it)) do d
+        dt = Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(counts), dt)
+        ccall((:kmc_memset, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, UInt64), ctx.handle, dt[], 0, sizeof(counts))
+        st = ccall((:kmc_composition, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Ptr{Cvoid}, Ptr{KmcResult}),
+            ctx.handle, d, K, mode_of(typeof(it)), dt[], pointer_from_objref(res))
+        st == KMC_OK && ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64),
+            ctx.handle, counts, dt[], sizeof(counts))
+        device_free(ctx, dt[])
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    return counts
+end
+
+"""
+    minimizers(FwKmers{A,K}(seq) | CanonicalKmers{A,K}(seq), W; step = 1) -> (Vector{Kmer}, Vector{Int})
+
+For every window start 1, 1+step, ...: the k-mer with the smallest `fx_hash` among `W` consecutive
+k-mers and its 1-based start (docs/src/replacements.md:28-58), `kmc_minimizers`; K <= 32, K + W - 1 <= 64.
+"""
+function minimizers(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}}, W::Integer; step::Integer = 1,
+        ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
+    seq = source(it)
+    T = derive_type(Kmer{A, K})
+    span = K + W - 1
+    n = length(seq) >= span ? (length(seq) - span) ÷ step + 1 : 0
+    kmers = Vector{T}(undef, n)
+    starts = Vector{Int}(undef, n)
+    res = KmcResult()
+    with_device_sequence(ctx, seq) do d
+        dk, di = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 8 * max(n, 1), dk)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 8 * max(n, 1), di)
+        o = Ref(KmcOut(Ptr{UInt64}(dk[]), C_NULL, C_NULL, Ptr{Int64}(di[]), C_NULL, n, 0))
+        st = ccall((:kmc_minimizers, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
+            ctx.handle, d, K, W, step, mode_of(typeof(it)), UInt32(0), o, pointer_from_objref(res))
+        if st == KMC_OK
+            ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, kmers, dk[], 8 * n)
+            ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, starts, di[], 8 * n)
+        end
+        device_free(ctx, dk[])
+        device_free(ctx, di[])
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    return kmers, starts
+end
 
 end # module
