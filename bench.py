@@ -199,6 +199,9 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout, which must carry exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import kmerscuda as kc

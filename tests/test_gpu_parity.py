@@ -427,3 +427,64 @@ def test_full_size_properties(kc, ctx):
         a, _, h = ko.iterate(w, length, k, ko.CANON, want_hash=True)
         assert np.array_equal(canon[r * wpr:(r + 1) * wpr].cpu().numpy().view(np.uint64), a[:, 0])
         assert np.array_equal(hsh[r * wpr:(r + 1) * wpr].cpu().numpy().view(np.uint64), h)
+
+
+# ----------------------------------------------- full-size properties (BASELINE config C4 shape)
+def test_full_size_properties_c4(kc, ctx):
+    """CanonicalDNAMers{63} (two limbs) + fx_hash over one 1 Gbp 2-bit sequence, streams resident (24 GB).
+    Size-independent checks: (1) the fused hash equals kmc_fx_hash over the canonical stream, (2) the
+    8 shards of the 1/2/4/8-GPU plan (window ranges with a K-1 halo, kmerscuda.sharding), run one after
+    the other into their slices, reproduce the unsharded streams exactly, (3) strand symmetry on a slice,
+    (4) sampled windows against the oracle."""
+    import torch
+    from kmerscuda import _abi, sharding
+    free, _ = torch.cuda.mem_get_info()
+    n = 1_000_000_000 if free > 80e9 else 50_000_000
+    k, N = 63, 2
+    nwin = n - k + 1
+    g = torch.Generator(device="cuda").manual_seed(63)
+    words = torch.randint(-2**63, 2**63 - 1, ((n + 31) // 32,), dtype=torch.int64, device="cuda", generator=g)
+    canon = torch.empty(nwin * N, dtype=torch.int64, device="cuda")
+    hsh = torch.empty(nwin, dtype=torch.int64, device="cuda")
+    desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), 1, None, None, n, words.numel(), 2, 0)
+    out = _abi.kmc_out(canon.data_ptr(), None, hsh.data_ptr(), None, None, nwin, 0)
+    res = _abi.kmc_result()
+    torch.cuda.synchronize()
+    ctx._check(ctx.lib.kmc_extract(ctx.handle, C.byref(desc), k, MODES["canon"], _abi.KMC_HASH_FX, C.byref(out), C.byref(res)))
+    assert res.n_written == nwin
+    # (1)
+    h2 = torch.empty_like(hsh)
+    ctx._check(ctx.lib.kmc_fx_hash(ctx.handle, canon.data_ptr(), nwin, N, 0, h2.data_ptr()))
+    ctx.sync()
+    assert torch.equal(hsh, h2)
+    # (2) the sharded plan, into h2 / a second canonical buffer slice by slice
+    ref_digest = ctx.digest(canon.data_ptr(), nwin * N), ctx.digest(hsh.data_ptr(), nwin)
+    h2.zero_()
+    c2 = torch.zeros_like(canon)
+    for sh in sharding.plan_sequence_shards(n, k, 2, 8):
+        if sh.n_windows == 0:
+            continue
+        d = _abi.kmc_seqs(words.data_ptr() + 8 * sh.word0, sh.n_words, 1, None, None, sh.length, sh.n_words, 2, sh.first_symbol_offset)
+        o = _abi.kmc_out(c2.data_ptr() + 8 * N * sh.window0, None, h2.data_ptr() + 8 * sh.window0, None, None, sh.n_windows, 0)
+        ctx._check(ctx.lib.kmc_extract(ctx.handle, C.byref(d), k, MODES["canon"], _abi.KMC_HASH_FX, C.byref(o), C.byref(res)))
+        assert res.n_written == sh.n_windows
+    assert (ctx.digest(c2.data_ptr(), nwin * N), ctx.digest(h2.data_ptr(), nwin)) == ref_digest
+    assert torch.equal(c2, canon) and torch.equal(h2, hsh)
+    del c2, h2
+    # (3) strand symmetry on the first 1 M symbols
+    m = 1_000_000
+    sl = words[: m // 32].cpu().numpy().view(np.uint64)
+    codes = ((sl.reshape(-1, 1) >> (np.arange(32, dtype=np.uint64) * np.uint64(2))) & np.uint64(3)).reshape(-1)
+    rc = kt.pack_codes((3 - codes[::-1]).astype(np.uint64), 2)
+    e = kc.extract(MODES["canon"], kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet2, rc, m)), k)
+    fwd = canon[: (m - k + 1) * N].cpu().numpy().view(np.uint64).reshape(-1, N)
+    assert np.array_equal(e.kmers[::-1], fwd)
+    # (4) sampled windows (slices of 200 windows at random places, limb / word boundaries included)
+    rng = np.random.default_rng(4)
+    for s in np.concatenate([[0, nwin - 200], rng.integers(0, nwin - 200, size=300)]):
+        s = int(s)
+        w0 = s // 32
+        w = words[w0: w0 + (200 + k + 62) // 32 + 1].cpu().numpy().view(np.uint64)
+        a, _, h = ko.iterate(w, 200 + k - 1, k, ko.CANON, first=s - 32 * w0, want_hash=True)
+        assert np.array_equal(canon[s * N:(s + 200) * N].cpu().numpy().view(np.uint64).reshape(-1, N), a)
+        assert np.array_equal(hsh[s:s + 200].cpu().numpy().view(np.uint64), h)
