@@ -209,6 +209,24 @@ int32_t kmc_minhash_sketch(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_
 int32_t kmc_composition(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, uint32_t *table,
                         kmc_result *result);
 
+/* Exact k-mer counts, keyed by the k-mer: the `Dict{Kmer,Int}` a user of the iterators builds (the reference
+ * discusses counting in src/iterators/CanonicalKmers.jl:183-185 and docs/src/composition.md).  The table is
+ * open addressing in caller-owned device memory: keys u64[2^log2_capacity] (free slot = ~0: initialise with
+ * kmc_memset(keys, 0xff, ...)), vals u32[2^log2_capacity] (zeroed); fx_hash of the k-mer picks the slot, linear
+ * probing.  Accumulates, so several sets can be counted into one table.  Forward (KMC_FW, K <= 31) or canonical
+ * (KMC_CANON, K <= 32) k-mers of a 2-bit source.  result->n_written = k-mers counted, result->digest[0] = keys
+ * this call added; KMC_E_OUT_TOO_SMALL when the table is full (its contents are then incomplete). */
+int32_t kmc_kmer_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, uint64_t *keys, uint32_t *vals,
+                       uint32_t log2_capacity, kmc_result *result);
+/* Adds every (key, count) with key != ~0 of src (another table, or an entry list from kmc_kmer_table_export:
+ * n_src slots) into the table -- the merge step of a multi-GPU count: each rank exports, the entries travel
+ * (all-gather / all-to-all by key owner), the owner merges.  *n_new (optional) = keys added. */
+int32_t kmc_kmer_table_merge(kmc_ctx *ctx, uint64_t *keys, uint32_t *vals, uint32_t log2_capacity,
+                             const uint64_t *src_keys, const uint32_t *src_vals, uint64_t n_src, uint64_t *n_new);
+/* The table's entries as two dense device arrays (unordered); *n_out = how many. */
+int32_t kmc_kmer_table_export(kmc_ctx *ctx, const uint64_t *keys, const uint32_t *vals, uint32_t log2_capacity,
+                              uint64_t *out_keys, uint32_t *out_vals, uint64_t capacity, uint64_t *n_out);
+
 /* XOR and wrapping sum of n u64 words in device memory -> out[0], out[1] (host).  A cheap
  * fingerprint of a device-resident stream: parity checks and result read-back at sizes where
  * downloading the stream itself would only measure PCIe.  Synchronises. */

@@ -6,6 +6,11 @@
 //                       the s smallest DISTINCT hash values over all k-mers, ascending)
 //   kmc_composition     k-mer composition vector -- `counts[as_integer(kmer) + 1] += 1` over
 //                       FwDNAMers{K} (docs/src/composition.md:28-39), K <= 14
+//   kmc_kmer_count      exact k-mer counts keyed by the k-mer itself (the `Dict{Kmer,Int}` a user of the
+//                       iterators builds; CanonicalKmers.jl:183-185 on counting), K <= 32: an
+//                       open-addressing table in device memory (fx_hash of the k-mer picks the slot,
+//                       linear probing, 64-bit compare-and-swap on the key, 32-bit add on the count);
+//                       kmc_kmer_table_merge / _export move entries between tables (multi-GPU merge)
 //
 // Both run consume_kernel: the same (read, group slot) work items, block load and static funnel
 // shifts as extract_kernel (kmer_core.cuh), with the stores replaced by a small functor.
@@ -20,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
+#include <algorithm>
 #include <vector>
 
 #include "plan.h"
@@ -28,7 +34,34 @@ namespace kmc {
 
 namespace {
 
-enum : int { OP_HASH_HIST = 0, OP_HASH_BELOW = 1, OP_COMPOSITION = 2, OP_COMPOSITION_SHARED = 3 };
+enum : int { OP_HASH_HIST = 0, OP_HASH_BELOW = 1, OP_COMPOSITION = 2, OP_COMPOSITION_SHARED = 3, OP_TABLE = 4 };
+
+constexpr uint64_t kEmptyKey = ~0ull; // never a k-mer: K <= 31, or K = 32 canonical (the all-T 32-mer is not canonical)
+
+// table[key] += inc.  Returns false when the table is full.  Most k-mers of a read set are already in the
+// table, so the slot is read before the compare-and-swap is attempted.
+__device__ __forceinline__ bool table_add(unsigned long long *keys, uint32_t *vals, uint32_t log2cap, uint64_t key,
+                                          uint64_t hash, uint32_t inc, unsigned long long *distinct)
+{
+    const uint64_t mask = (1ull << log2cap) - 1;
+    uint64_t slot = hash >> (64 - log2cap);
+    for (uint64_t probes = 0; probes <= mask; ++probes) {
+        unsigned long long cur = keys[slot];
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(keys + slot, kEmptyKey, static_cast<unsigned long long>(key));
+            if (cur == kEmptyKey) {
+                atomicAdd(distinct, 1ull);
+                cur = key;
+            }
+        }
+        if (cur == key) {
+            atomicAdd(vals + slot, inc);
+            return true;
+        }
+        slot = (slot + 1) & mask;
+    }
+    return false;
+}
 
 struct ConsumeParams {
     uint32_t *table;               // OP_HASH_HIST: u32[2^12]; OP_COMPOSITION*: u32[4^K]
@@ -38,6 +71,10 @@ struct ConsumeParams {
     unsigned long long *cursor;    // OP_HASH_BELOW: elements appended so far
     uint64_t cand_cap;
     uint32_t table_entries;        // OP_HASH_HIST, OP_COMPOSITION_SHARED: counters kept in shared memory
+    unsigned long long *keys;      // OP_TABLE: u64[2^log2cap] keys (kEmptyKey = free), vals = table
+    uint32_t log2cap;
+    unsigned long long *distinct;  // OP_TABLE: keys in the table
+    uint32_t *overflow;            // OP_TABLE: set when a k-mer found no slot
 };
 
 constexpr int kSharedCompositionMax = 4096; // 4^6 counters = 16 KB of shared memory
@@ -87,6 +124,8 @@ __global__ void __launch_bounds__(kBlockThreads) consume_kernel(const ExtractPar
                         const unsigned long long at = atomicAdd(c.cursor, 1ull);
                         if (at < c.cand_cap) c.cand[at] = h;
                     }
+                } else if (OP == OP_TABLE) {
+                    if (!table_add(c.keys, c.table, c.log2cap, a[N - 1], fx_hash<N>(a, 0), 1u, c.distinct)) *c.overflow = 1u;
                 } else if (OP == OP_COMPOSITION) {
                     atomicAdd(c.table + a[N - 1], 1u); // as_integer(kmer): K <= 14, one limb
                 } else {
@@ -143,6 +182,43 @@ ConsumeLaunchFn consume_launcher(const Geometry &ge, bool ragged, bool canon)
     case 2: return pick_consume_nx<2, OP>(ge.nx, ragged, canon);
     }
     return nullptr;
+}
+
+// every non-empty (key, count) of a source table / entry list into the destination table
+__global__ void __launch_bounds__(256) table_merge_kernel(unsigned long long *keys, uint32_t *vals, uint32_t log2cap,
+                                                          const unsigned long long *__restrict__ src_keys,
+                                                          const uint32_t *__restrict__ src_vals, uint64_t n,
+                                                          unsigned long long *distinct, uint32_t *overflow)
+{
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t key = src_keys[i];
+        if (key == kEmptyKey) continue;
+        const uint64_t d[1] = {key};
+        if (!table_add(keys, vals, log2cap, key, fx_hash<1>(d, 0), src_vals[i], distinct)) *overflow = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256) table_export_kernel(const unsigned long long *__restrict__ keys,
+                                                           const uint32_t *__restrict__ vals, uint64_t n_slots,
+                                                           uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
+                                                           uint64_t capacity, unsigned long long *cursor)
+{
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_slots;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t key = keys[i];
+        if (key == kEmptyKey) continue;
+        const uint32_t active = __activemask(); // warp-aggregated append: one atomic per converged group
+        const int leader = __ffs(active) - 1;
+        unsigned long long base = 0;
+        if ((threadIdx.x & 31) == leader) base = atomicAdd(cursor, static_cast<unsigned long long>(__popc(active)));
+        base = __shfl_sync(active, base, leader);
+        const uint64_t at = base + __popc(active & ((1u << (threadIdx.x & 31)) - 1u));
+        if (at < capacity) {
+            out_keys[at] = key;
+            out_vals[at] = vals[i];
+        }
+    }
 }
 
 struct AsyncBuf { // stream-ordered temporary
@@ -299,5 +375,117 @@ extern "C" int32_t kmc_composition(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k
     CU(cudaEventRecord(ctx->ev_k1, stream));
     CU(cudaStreamSynchronize(stream));
     CU(cudaEventElapsedTime(&result->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+    return KMC_OK;
+}
+
+// ---- exact k-mer counts ------------------------------------------------------------------------
+static int32_t table_status(kmc_ctx *ctx, cudaStream_t stream, unsigned long long *distinct, uint32_t *overflow, kmc_result *result)
+{
+    CU(cudaMemcpyAsync(&ctx->host_small[100], distinct, 8, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&ctx->host_small[101], overflow, 4, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    if (result) result->digest[0] = ctx->host_small[100]; // keys added by this call
+    if (static_cast<uint32_t>(ctx->host_small[101]) != 0)
+        return fail(ctx, KMC_E_OUT_TOO_SMALL, "the k-mer table is full");
+    return KMC_OK;
+}
+
+extern "C" int32_t kmc_kmer_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode, uint64_t *keys, uint32_t *vals,
+                                  uint32_t log2_capacity, kmc_result *result)
+{
+    int32_t st = check_common(ctx, seqs, k);
+    if (st) return st;
+    if (!keys || !vals || !result) return fail(ctx, KMC_E_BAD_ARG, "keys / vals / result is NULL");
+    if (mode != KMC_FW && mode != KMC_CANON) return fail(ctx, KMC_E_BAD_ARG, "mode must be KMC_FW or KMC_CANON");
+    if (seqs->src_bits != 2) return fail(ctx, KMC_E_UNSUPPORTED, "the k-mer table needs a 2-bit source");
+    if (k > 32 || (k == 32 && mode == KMC_FW))
+        return fail(ctx, KMC_E_UNSUPPORTED, "the k-mer table supports K <= 31, and K = 32 for canonical k-mers");
+    if (log2_capacity < 1 || log2_capacity > 40) return fail(ctx, KMC_E_BAD_ARG, "log2_capacity must be in 1..40");
+    CU(cudaSetDevice(ctx->device));
+    memset(result, 0, sizeof *result);
+    const Geometry ge = geometry(k);
+    cudaStream_t stream = ctx->stream;
+    CU(cudaEventRecord(ctx->ev_k0, stream));
+    st = ensure_scratch(ctx, layout_scratch_bytes(seqs) + 1024);
+    if (st) return st;
+    st = ensure_host_small(ctx);
+    if (st) return st;
+    Scratch scratch{static_cast<char *>(ctx->scratch), ctx->scratch_bytes, 0};
+    unsigned long long *distinct = static_cast<unsigned long long *>(scratch.take(16));
+    uint32_t *overflow = reinterpret_cast<uint32_t *>(distinct + 1);
+    Layout L;
+    st = plan_layout(ctx, seqs, k, ge, stream, KnownTotals(), scratch, &L);
+    if (st) return st;
+    result->n_written = L.total;
+    if (L.total == 0) return KMC_OK;
+    ExtractParams p = base_params(seqs, k, ge, L, 0);
+    ConsumeParams c{};
+    c.table = vals;
+    c.keys = reinterpret_cast<unsigned long long *>(keys);
+    c.log2cap = log2_capacity;
+    c.distinct = distinct;
+    c.overflow = overflow;
+    CU(cudaMemsetAsync(distinct, 0, 16, stream));
+    ConsumeLaunchFn fn = consume_launcher<OP_TABLE>(ge, !L.uniform_len, mode == KMC_CANON);
+    if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+    CU(fn(p, c, stream));
+    CU(cudaEventRecord(ctx->ev_k1, stream));
+    st = table_status(ctx, stream, distinct, overflow, result);
+    CU(cudaEventElapsedTime(&result->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+    return st;
+}
+
+extern "C" int32_t kmc_kmer_table_merge(kmc_ctx *ctx, uint64_t *keys, uint32_t *vals, uint32_t log2_capacity,
+                                        const uint64_t *src_keys, const uint32_t *src_vals, uint64_t n_src, uint64_t *n_new)
+{
+    if (!ctx) return KMC_E_BAD_ARG;
+    if (!keys || !vals || (n_src && (!src_keys || !src_vals))) return fail(ctx, KMC_E_BAD_ARG, "NULL table");
+    if (log2_capacity < 1 || log2_capacity > 40) return fail(ctx, KMC_E_BAD_ARG, "log2_capacity must be in 1..40");
+    CU(cudaSetDevice(ctx->device));
+    int32_t st = ensure_scratch(ctx, 1024);
+    if (st) return st;
+    st = ensure_host_small(ctx);
+    if (st) return st;
+    cudaStream_t stream = ctx->stream;
+    unsigned long long *distinct = static_cast<unsigned long long *>(ctx->scratch);
+    uint32_t *overflow = reinterpret_cast<uint32_t *>(distinct + 1);
+    CU(cudaMemsetAsync(distinct, 0, 16, stream));
+    if (n_src) {
+        const uint64_t blocks = std::min<uint64_t>((n_src + 255) / 256, static_cast<uint64_t>(ctx->sm_count) * 16);
+        table_merge_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<unsigned long long *>(keys), vals,
+                                                                              log2_capacity,
+                                                                              reinterpret_cast<const unsigned long long *>(src_keys),
+                                                                              src_vals, n_src, distinct, overflow);
+        CU(cudaGetLastError());
+    }
+    kmc_result r{};
+    st = table_status(ctx, stream, distinct, overflow, &r);
+    if (n_new) *n_new = r.digest[0];
+    return st;
+}
+
+extern "C" int32_t kmc_kmer_table_export(kmc_ctx *ctx, const uint64_t *keys, const uint32_t *vals, uint32_t log2_capacity,
+                                         uint64_t *out_keys, uint32_t *out_vals, uint64_t capacity, uint64_t *n_out)
+{
+    if (!ctx) return KMC_E_BAD_ARG;
+    if (!keys || !vals || !n_out || (capacity && (!out_keys || !out_vals))) return fail(ctx, KMC_E_BAD_ARG, "NULL buffer");
+    if (log2_capacity < 1 || log2_capacity > 40) return fail(ctx, KMC_E_BAD_ARG, "log2_capacity must be in 1..40");
+    CU(cudaSetDevice(ctx->device));
+    int32_t st = ensure_scratch(ctx, 1024);
+    if (st) return st;
+    st = ensure_host_small(ctx);
+    if (st) return st;
+    cudaStream_t stream = ctx->stream;
+    unsigned long long *cursor = static_cast<unsigned long long *>(ctx->scratch);
+    CU(cudaMemsetAsync(cursor, 0, 8, stream));
+    const uint64_t n_slots = 1ull << log2_capacity;
+    const uint64_t blocks = std::min<uint64_t>((n_slots + 255) / 256, static_cast<uint64_t>(ctx->sm_count) * 16);
+    table_export_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const unsigned long long *>(keys), vals,
+                                                                           n_slots, out_keys, out_vals, capacity, cursor);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&ctx->host_small[100], cursor, 8, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    *n_out = ctx->host_small[100];
+    if (*n_out > capacity) return fail(ctx, KMC_E_OUT_TOO_SMALL, "export capacity smaller than the number of keys in the table");
     return KMC_OK;
 }

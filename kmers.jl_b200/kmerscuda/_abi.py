@@ -100,6 +100,12 @@ SIGNATURES = {
                                        C.POINTER(kmc_result)]),
     "kmc_composition": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p,
                                     C.POINTER(kmc_result)]),
+    "kmc_kmer_count": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                   C.POINTER(kmc_result)]),
+    "kmc_kmer_table_merge": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.POINTER(C.c_uint64)]),
+    "kmc_kmer_table_export": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                          C.POINTER(C.c_uint64)]),
     "kmc_digest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "kmc_timer_begin": (C.c_int32, [C.c_void_p]),
     "kmc_timer_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),

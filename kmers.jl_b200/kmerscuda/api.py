@@ -674,6 +674,54 @@ def composition(rs, K: int, *, canonical: bool = False, ctx: Optional[Context] =
     return host, int(res.n_written), float(res.kernel_ms)
 
 
+class KmerTable:
+    """Exact k-mer counts on the device (kmc_kmer_count): an open-addressing table keyed by the k-mer,
+    the `Dict{Kmer,Int}` a user of the reference's iterators builds.  K <= 31 (forward) / 32 (canonical)."""
+
+    def __init__(self, log2_capacity: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.log2_capacity = int(log2_capacity)
+        n = 1 << self.log2_capacity
+        self.keys, self.vals = self.ctx.alloc(8 * n), self.ctx.alloc(4 * n)
+        self.ctx._check(self.ctx.lib.kmc_memset(self.ctx.handle, self.keys.ptr, 0xFF, 8 * n))
+        self.ctx._check(self.ctx.lib.kmc_memset(self.ctx.handle, self.vals.ptr, 0, 4 * n))
+        self.n_keys = 0
+
+    def count(self, rs, K: int, *, canonical: bool = True):
+        """Adds every k-mer of the set.  Returns (k-mers counted, kernel_ms)."""
+        _check_K(K)
+        drs = rs if isinstance(rs, DeviceReadSet) else DeviceReadSet(self.ctx, rs)
+        res = kmc_result()
+        self.ctx._check(self.ctx.lib.kmc_kmer_count(self.ctx.handle, C.byref(drs.desc), K, KMC_CANON if canonical else KMC_FW,
+                                                    self.keys.ptr, self.vals.ptr, self.log2_capacity, C.byref(res)))
+        self.n_keys += int(res.digest[0])
+        return int(res.n_written), float(res.kernel_ms)
+
+    def merge(self, other: "KmerTable"):
+        """self[k] += other[k] for every key of `other` (same device): the merge step of a sharded count."""
+        n_new = C.c_uint64(0)
+        self.ctx._check(self.ctx.lib.kmc_kmer_table_merge(self.ctx.handle, self.keys.ptr, self.vals.ptr, self.log2_capacity,
+                                                          other.keys.ptr, other.vals.ptr, 1 << other.log2_capacity, C.byref(n_new)))
+        self.n_keys += int(n_new.value)
+
+    def items(self):
+        """(keys u64[n], counts u32[n]) sorted by key."""
+        n = max(self.n_keys, 1)
+        dk, dv = self.ctx.alloc(8 * n), self.ctx.alloc(4 * n)
+        n_out = C.c_uint64(0)
+        self.ctx._check(self.ctx.lib.kmc_kmer_table_export(self.ctx.handle, self.keys.ptr, self.vals.ptr, self.log2_capacity,
+                                                           dk.ptr, dv.ptr, n, C.byref(n_out)))
+        k, v = dk.download(np.uint64, int(n_out.value)), dv.download(np.uint32, int(n_out.value))
+        dk.free()
+        dv.free()
+        order = np.argsort(k, kind="stable")
+        return k[order], v[order]
+
+    def free(self):
+        self.keys.free()
+        self.vals.free()
+
+
 def bucket_count(rs, K: int, bucket_bits: int, ctx: Optional[Context] = None, table: Optional[DeviceBuffer] = None):
     """Histogram of fx_hash(canonical k-mer) >> (64 - bucket_bits) (north_star extension).
     Returns (table u32[2^bucket_bits] on the host, n_kmers, kernel_ms)."""

@@ -97,3 +97,51 @@ def test_argument_checks(kc):
         kc.minhash_sketch(rs, 65, 10)
     with pytest.raises(kc.KmersCUDAError):
         kc.minhash_sketch(rs, 16, 0)
+
+
+# ------------------------------------------------------------------------------ exact k-mer counts
+@pytest.mark.parametrize("k,canonical", [(1, True), (5, False), (16, True), (21, True), (31, False), (32, True)])
+def test_kmer_table_matches_unique_counts(kc, k, canonical):
+    rng = np.random.default_rng(500 + k)
+    # a genome sampled by overlapping reads: most k-mers occur many times
+    genome = rng.integers(0, 4, size=20_000).astype(np.uint64)
+    n_reads, length, stride = 4000, 150, 5
+    starts = rng.integers(0, len(genome) - length, size=n_reads)
+    codes = np.zeros((n_reads, stride * 32), dtype=np.uint64)
+    for r, s0 in enumerate(starts):
+        codes[r, :length] = genome[s0:s0 + length]
+    words = np.concatenate([kt.pack_codes(row, 2) for row in codes])
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    a, _, _, _ = ko.batch_iterate(words, n_reads, k, ko.CANON if canonical else ko.FW, uniform_len=length, uniform_stride=stride)
+    want_k, want_c = np.unique(a[:, 0], return_counts=True)
+    t = kc.KmerTable(17)
+    n, _ = t.count(rs, k, canonical=canonical)
+    assert n == a.shape[0] and t.n_keys == len(want_k)
+    got_k, got_c = t.items()
+    assert np.array_equal(got_k, want_k) and np.array_equal(got_c, want_c.astype(np.uint32))
+    # counting the set again doubles every count; merging a second table adds it
+    t.count(rs, k, canonical=canonical)
+    t2 = kc.KmerTable(16)
+    t2.count(rs, k, canonical=canonical)
+    t.merge(t2)
+    got_k, got_c = t.items()
+    assert np.array_equal(got_k, want_k) and np.array_equal(got_c, 3 * want_c.astype(np.uint32))
+    for x in (t, t2):
+        x.free()
+
+
+def test_kmer_table_full_and_argument_checks(kc):
+    rng = np.random.default_rng(1)
+    n = 10_000
+    words = rng.integers(0, 2**64, size=(n + 31) // 32, dtype=np.uint64)
+    rs = kc.ReadSet.single(kc.LongSequence(kc.DNAAlphabet2, words, n))
+    t = kc.KmerTable(8)  # 256 slots for ~10 000 distinct 21-mers
+    with pytest.raises(kc.KmersCUDAError, match="full"):
+        t.count(rs, 21)
+    t.free()
+    t = kc.KmerTable(10)
+    with pytest.raises(kc.KmersCUDAError):
+        t.count(rs, 33)
+    with pytest.raises(kc.KmersCUDAError):
+        t.count(rs, 32, canonical=False)
+    t.free()

@@ -322,6 +322,49 @@ def case_sketch(ctx, steps, scale):
         emit("composition vector of %s, one %d bp sequence" % (name, length), length - k + 1, 0.25 * length + 4.0 * 4 ** k, med, mn)
 
 
+def case_count(ctx, steps, scale):
+    """Exact canonical 31-mer counts (kmc_kmer_count) over reads sampled from a genome at 30x coverage:
+    4 M x 150 bp reads of a 20 Mbp genome (about 20 M distinct canonical 31-mers, each seen ~24 times), table of 2^26
+    slots (768 MB: beyond L2); and over a 1 Mbp genome (table of 2^22 slots = 48 MB: L2-resident)."""
+    n_reads, length, stride, k = int(4_000_000 * scale), 150, 5, 31
+    wpr = length - k + 1
+    res = _abi.kmc_result()
+    g = torch.Generator(device="cuda").manual_seed(77)
+    shifts = (torch.arange(32, device="cuda", dtype=torch.int64) * 2)
+    for genome_len, log2cap in ((int(20_000_000 * scale), 26), (1_000_000, 22)):
+        genome = torch.randint(0, 4, (genome_len,), dtype=torch.int64, device="cuda", generator=g)
+        words = torch.empty(n_reads * stride, dtype=torch.int64, device="cuda")
+        pos = torch.arange(stride * 32, device="cuda")
+        for c0 in range(0, n_reads, 250_000):
+            c1 = min(n_reads, c0 + 250_000)
+            starts = torch.randint(0, genome_len - length, (c1 - c0, 1), device="cuda", generator=g)
+            codes = genome[(starts + pos).clamp(max=genome_len - 1)] * (pos < length)
+            words[c0 * stride:c1 * stride] = (codes.view(c1 - c0, stride, 32) << shifts).sum(-1).view(-1)
+        desc = _abi.kmc_seqs(words.data_ptr(), words.numel(), n_reads, None, None, length, stride, 2, 0)
+        keys = torch.empty(1 << log2cap, dtype=torch.int64, device="cuda")
+        vals = torch.empty(1 << log2cap, dtype=torch.int32, device="cuda")
+        distinct = [0]
+
+        def stepf():
+            keys.fill_(-1)
+            vals.zero_()
+            st = ctx.lib.kmc_kmer_count(ctx.handle, C.byref(desc), k, CANON, keys.data_ptr(), vals.data_ptr(), log2cap, C.byref(res))
+            if st != 0:
+                raise RuntimeError(ctx.lib.kmc_last_error(ctx.handle).decode())
+            distinct[0] = int(res.digest[0])
+        torch.cuda.synchronize()
+        ms = []
+        for i in range(WARMUP + steps):
+            stepf()
+            if i >= WARMUP:
+                ms.append(float(res.kernel_ms))
+        med, mn = float(np.median(ms)), float(np.min(ms))
+        n = n_reads * wpr
+        emit("exact canonical 31-mer count table, %d x 150 bp reads at 30x of a %d bp genome, 2^%d slots" % (n_reads, genome_len, log2cap),
+             n, 0.25 * length / wpr * n + 12.0 * distinct[0], med, mn, {"distinct_keys": distinct[0], "table_bytes": 12 << log2cap})
+        del words, keys, vals, genome
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="c3,c3long,c4,c5,modes")
@@ -333,7 +376,7 @@ def main():
     WARMUP = args.warmup
     torch.cuda.set_device(0)
     ctx = kc.Context(0)
-    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii, "minimizers": case_minimizers, "sketch": case_sketch, "kmer4": case_kmer4}
+    table = {"c3": case_c3_reads, "c3long": case_c3_long, "c4": case_c4, "c5": case_c5, "modes": case_modes, "ragged": case_ragged, "ascii": case_ascii, "minimizers": case_minimizers, "sketch": case_sketch, "kmer4": case_kmer4, "count": case_count}
     for c in args.cases.split(","):
         table[c](ctx, args.steps, args.scale)
         torch.cuda.empty_cache()
