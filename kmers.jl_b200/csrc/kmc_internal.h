@@ -50,6 +50,7 @@ cudaError_t tile_first_reads(const uint64_t *item_off, uint64_t n_seqs, uint64_t
 
 // buckets.cu: histogram of n bucket ids into a table too large for L2, by binning the ids first
 int binned_count_bin_bits(int bucket_bits);
+int apply_group(int dflt); // bins applied per launch (KMC_APPLY_GROUP overrides the default, for experiments)
 uint64_t binned_count_blocks(uint64_t n);
 cudaError_t warm_table(const uint32_t *table, uint64_t n_counters, int sm_count, cudaStream_t stream);
 cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint32_t *table, uint32_t *binned, uint64_t *matrix,

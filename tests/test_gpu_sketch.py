@@ -130,6 +130,49 @@ def test_kmer_table_matches_unique_counts(kc, k, canonical):
         x.free()
 
 
+@pytest.mark.parametrize("k,canonical,log2cap,ragged", [(21, True, 23, False), (31, False, 24, True), (32, True, 28, True)])
+def test_kmer_table_beyond_l2_takes_the_binned_path(kc, k, canonical, log2cap, ragged):
+    """Tables larger than L2 are filled slice by slice from binned k-mers (64 bins for 2^23 / 2^24 slots, 256 for
+    2^28); the result is the same table content."""
+    rng = np.random.default_rng(900 + k)
+    genome = rng.integers(0, 4, size=60_000).astype(np.uint64)
+    n_reads = 3000
+    lens = rng.integers(0, 260, size=n_reads) if ragged else np.full(n_reads, 150)
+    seq_codes = []
+    for ln in lens:
+        s0 = int(rng.integers(0, len(genome) - 260))
+        seq_codes.append(genome[s0:s0 + int(ln)])
+    if ragged:
+        words_l, off = [], [0]
+        for c in seq_codes:
+            w = kt.pack_codes(c, 2) if len(c) else np.zeros(0, dtype=np.uint64)
+            words_l.append(w)
+            off.append(off[-1] + len(w))
+        words = np.concatenate(words_l) if words_l else np.zeros(0, dtype=np.uint64)
+        off = np.asarray(off, dtype=np.uint64)
+        ln = np.asarray(lens, dtype=np.uint64)
+        rs = kc.ReadSet(2, words, n_reads, seq_word_offset=off, seq_len=ln)
+        a, _, _, _ = ko.batch_iterate(words, n_reads, k, ko.CANON if canonical else ko.FW, word_off=off, seq_len=ln)
+    else:
+        codes = np.zeros((n_reads, 5 * 32), dtype=np.uint64)
+        for r, c in enumerate(seq_codes):
+            codes[r, :150] = c
+        words = np.concatenate([kt.pack_codes(row, 2) for row in codes])
+        rs = kc.ReadSet(2, words, n_reads, uniform_len=150, uniform_stride_words=5)
+        a, _, _, _ = ko.batch_iterate(words, n_reads, k, ko.CANON if canonical else ko.FW, uniform_len=150, uniform_stride=5)
+    want_k, want_c = np.unique(a[:, 0], return_counts=True)
+    t = kc.KmerTable(log2cap)
+    n, _ = t.count(rs, k, canonical=canonical)
+    assert n == a.shape[0] and t.n_keys == len(want_k)
+    got_k, got_c = t.items()
+    assert np.array_equal(got_k, want_k) and np.array_equal(got_c, want_c.astype(np.uint32))
+    n, _ = t.count(rs, k, canonical=canonical)  # every key is already there
+    assert t.n_keys == len(want_k)
+    got_k, got_c = t.items()
+    assert np.array_equal(got_k, want_k) and np.array_equal(got_c, 2 * want_c.astype(np.uint32))
+    t.free()
+
+
 def test_kmer_table_full_and_argument_checks(kc):
     rng = np.random.default_rng(1)
     n = 10_000
