@@ -180,6 +180,17 @@ int32_t kmc_base_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n
 int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
                          uint32_t *table, kmc_result *result);
 
+/* kmc_bucket_count without the final synchronisation and with progress events, so that the merge of
+ * the tables of several GPUs -- the path's only collective -- overlaps the counting: the table is cut
+ * into n_parts equal contiguous ranges (n_parts = 1, 2, 4, ... 32) and events[i] (a cudaEvent_t created
+ * by the caller) is recorded on the context's stream as soon as range i holds its final counts.  A
+ * caller all-reduces range i on a second stream that waits for events[i] while later ranges are still
+ * being counted (tables beyond L2 are filled slice after slice; an L2-sized table is final only at the
+ * end, and all events are recorded there).  result->n_written is set; result->kernel_ms is not.  The
+ * call is complete when events[n_parts - 1] has completed (or after kmc_sync). */
+int32_t kmc_bucket_count_async(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
+                               uint32_t *table, uint32_t n_parts, void *const *events, kmc_result *result);
+
 /* Minimizers: "the minimum of W consecutive kmers, as ordered by some ordering O"
  * (docs/src/replacements.md:28-30) with fx_hash as the ordering (replacements.md:32-58,
  * test/benchmark.jl:96-119).  For every window start i = 1, 1+step, 1+2*step, ... that has W

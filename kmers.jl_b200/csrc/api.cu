@@ -523,8 +523,32 @@ int32_t kmc_base_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n
     return KMC_OK;
 }
 
+namespace {
+int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits, uint32_t *table, uint32_t n_parts,
+                          void *const *events, kmc_result *result);
+}
+
 int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits, uint32_t *table,
                          kmc_result *result)
+{
+    return bucket_count_impl(ctx, seqs, k, bucket_bits, table, 0, nullptr, result);
+}
+
+int32_t kmc_bucket_count_async(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits, uint32_t *table,
+                               uint32_t n_parts, void *const *events, kmc_result *result)
+{
+    if (!ctx) return KMC_E_BAD_ARG;
+    if (!events || n_parts < 1 || n_parts > 32 || (n_parts & (n_parts - 1)))
+        return fail(ctx, KMC_E_BAD_ARG, "n_parts must be a power of two <= 32 and events non-NULL");
+    for (uint32_t i = 0; i < n_parts; ++i)
+        if (!events[i]) return fail(ctx, KMC_E_BAD_ARG, "NULL event");
+    return bucket_count_impl(ctx, seqs, k, bucket_bits, table, n_parts, events, result);
+}
+
+namespace {
+// n_parts == 0: the synchronous call (kernel_ms measured); otherwise progress events and no synchronisation
+int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits, uint32_t *table, uint32_t n_parts,
+                          void *const *events, kmc_result *result)
 {
     int32_t st = check_common(ctx, seqs, k);
     if (st) return st;
@@ -546,7 +570,11 @@ int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t 
     st = plan_layout(ctx, seqs, k, ge, stream, KnownTotals(), scratch, &L);
     if (st) return st;
     result->n_written = L.total;
-    if (L.total == 0) return KMC_OK;
+    auto record_all = [&]() -> int32_t {
+        for (uint32_t i = 0; i < n_parts; ++i) CU(cudaEventRecord(static_cast<cudaEvent_t>(events[i]), stream));
+        return KMC_OK;
+    };
+    if (L.total == 0) return record_all();
     ExtractParams p = base_params(seqs, k, ge, L, 0);
     p.bucket_shift = static_cast<uint32_t>(64 - bucket_bits);
     // Tables beyond L2 (B = 28 is 1 GiB): write the bucket ids out, bin them by their high bits, apply
@@ -580,7 +608,7 @@ int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t 
         ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKET_IDS, true, !L.uniform_len);
         if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
         CU(fn(p, ctx->sm_count, stream));
-        CU(binned_count(ids, L.total, bucket_bits, table, tmp_ids, matrix, offs, scan_tmp, ctx->sm_count, stream));
+        CU(binned_count(ids, L.total, bucket_bits, table, tmp_ids, matrix, offs, scan_tmp, ctx->sm_count, stream, n_parts, events));
         for (void *q : {static_cast<void *>(ids), static_cast<void *>(tmp_ids), static_cast<void *>(matrix),
                         static_cast<void *>(offs), static_cast<void *>(scan_tmp)})
             CU(cudaFreeAsync(q, stream));
@@ -591,12 +619,16 @@ int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t 
         ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKETS, true, !L.uniform_len);
         if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
         CU(fn(p, ctx->sm_count, stream));
+        st = record_all();
+        if (st) return st;
     }
+    if (n_parts) return KMC_OK; // asynchronous form: the caller waits for its events
     CU(cudaEventRecord(ctx->ev_k1, stream));
     CU(cudaStreamSynchronize(stream));
     CU(cudaEventElapsedTime(&result->kernel_ms, ctx->ev_k0, ctx->ev_k1));
     return KMC_OK;
 }
+} // namespace
 
 int32_t kmc_digest(kmc_ctx *ctx, const uint64_t *dptr, uint64_t n, uint64_t *out)
 {

@@ -66,9 +66,16 @@ __global__ void __launch_bounds__(256) bin_apply_kernel(const uint32_t *__restri
 // ids[0..n) are bucket ids of `bucket_bits` bits; adds their histogram to table.  tmp: n u32 (binned ids),
 // matrix / offs: (n_bins * n_blocks + 1) u64 each, scan_tmp: scan_tmp_elems(n_bins * n_blocks) u64.
 cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint32_t *table, uint32_t *binned, uint64_t *matrix,
-                         uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream)
+                         uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events)
 {
-    if (n == 0) return cudaSuccess;
+    if (!events) n_parts = 0;
+    if (n == 0) {
+        for (uint32_t i = 0; i < n_parts; ++i) {
+            cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(events[i]), stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     const int p = binned_count_bin_bits(bucket_bits);
     if (bucket_bits < p) return cudaErrorInvalidValue; // the caller bins only tables far larger than 2^p counters
     const int n_bins = 1 << p, shift = bucket_bits - p;
@@ -78,11 +85,17 @@ cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint3
     // offs has n_bins * n_blocks + 1 entries: offs[(bin + 1) * n_blocks] of the last bin is the total
     const uint64_t slice = 1ull << shift; // counters per bin
     const int group = apply_group(2); // bins applied per launch
+    uint32_t parts_done = 0;
     for (int b = 0; b < n_bins; b += group) {
         const int b_end = b + group < n_bins ? b + group : n_bins;
         warm_slice_kernel<<<static_cast<unsigned>(sm_count * 8), 256, 0, stream>>>(table + static_cast<uint64_t>(b) * slice,
                                                                                   slice * (b_end - b), reinterpret_cast<uint32_t *>(scan_tmp));
         bin_apply_kernel<<<static_cast<unsigned>(sm_count * 16), 256, 0, stream>>>(binned, offs, n_blocks, b, b_end, table);
+        // range i of the table = bins [i * n_bins / n_parts, (i + 1) * n_bins / n_parts): final once they are applied
+        while (parts_done < n_parts && static_cast<uint64_t>(parts_done + 1) * n_bins <= static_cast<uint64_t>(b_end) * n_parts) {
+            e = cudaEventRecord(static_cast<cudaEvent_t>(events[parts_done++]), stream);
+            if (e != cudaSuccess) return e;
+        }
     }
     return cudaGetLastError();
 }

@@ -14,6 +14,7 @@
 //                   pre-kernel), a per-warp-bucket first read (65 short searches per block, kept
 //                   in shared memory), and a 0-2 step search per item inside its bucket's range
 #pragma once
+#include <cstdlib>
 #include "kmer_core.cuh"
 
 namespace kmc {
@@ -68,6 +69,8 @@ struct ExtractParams {
     // absolute symbol index in the stream.
     const uint32_t *vstart;
     unsigned long long *err_flat;  // strict modes: atomicMin of the first flat window with an uncertain symbol
+    // source prefetch in bursts (see burst_prefetch): tiles per chunk; 0 = off.  Set by launch_extract.
+    uint32_t pf_tiles;
 };
 
 // Validity bits of the slots [jlo, jhi) of one item: bit j set <=> window j has no uncertain symbol.
@@ -247,6 +250,72 @@ struct TileCursor {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Source prefetch in bursts.  The kernels write 16-50 bytes for every byte they read, and HBM pays for the
+// mix out of proportion: a pure stream of these stores runs at 7.48 TB/s, the same stores with the 2 % trickle
+// of source reads among them at 6.5 TB/s (tools/bw_probe.py, KMC_STORE_PROBE_PATTERN=2 / 3) -- every read that
+// reaches DRAM interrupts a run of writes.  So the reads are taken out of the trickle: the tiles are cut into
+// chunks of pf_tiles tiles (about 20 MB of source), and kPfBlocks blocks shortly before the end of chunk c
+// pull the source of chunk c + 1 into L2 with evict_last prefetches -- one short burst of reads per chunk --
+// where the loads of the tiles find it; the stores are marked evict_first so that they do not push it out again.
+// Probe (pattern 7): 7.1 TB/s, 95 % of the pure-write ceiling.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPfBlocks = 32;   // blocks that share one chunk's prefetch
+constexpr uint32_t kPfLead = 128;    // tiles before the chunk boundary at which they run (blocks are dispatched in order)
+constexpr uint64_t kPfChunkBytes = 20ull << 20;
+
+// bit offset in the source stream of the first item of `tile` (end of the stream for tiles beyond the last)
+template <bool RAGGED, int G, int BPS>
+KMC_DEV int64_t tile_start_bit(const ExtractParams &p, uint64_t tile, uint64_t n_items)
+{
+    const int64_t end = p.nw32 * 32;
+    const uint64_t item = tile * kTileItems;
+    if (item >= n_items) return end;
+    uint64_t r, gi, f0, ubit;
+    if (RAGGED) {
+        r = __ldg(p.tile_first + tile);
+        gi = item - __ldg(p.item_off + r);
+        f0 = __ldg(p.win_off + r);
+        ubit = (p.seq_unit_off ? __ldg(p.seq_unit_off + r) - p.unit_bias : r * p.stride_units) * p.unit_bits;
+    } else {
+        r = item / p.gprm;
+        gi = item - r * p.gprm;
+        f0 = r * p.wpr;
+        ubit = p.seq_unit_off ? (__ldg(p.seq_unit_off + r) - p.unit_bias) * p.unit_bits : r * p.read_bits;
+    }
+    const int64_t wbase = static_cast<int64_t>((f0 / G + gi) * G - f0);
+    const int64_t bit = static_cast<int64_t>(ubit) + BPS * (static_cast<int64_t>(p.first) + wbase);
+    return bit < 0 ? 0 : (bit > end ? end : bit);
+}
+
+template <bool RAGGED, int G, int BPS>
+KMC_DEV void burst_prefetch(const ExtractParams &p, uint64_t n_items)
+{
+    const uint32_t T = p.pf_tiles;
+    const uint32_t c = blockIdx.x / T, k = blockIdx.x - c * T;
+    const uint32_t lead = kPfLead < T ? kPfLead : T, k0 = T - lead;
+    const bool first = blockIdx.x < kPfBlocks; // the first blocks of the grid pull chunk 0
+    if (!first && (k < k0 || k >= k0 + kPfBlocks)) return;
+    const uint64_t cc = first ? 0 : c + 1, kk = first ? blockIdx.x : k - k0;
+    const int64_t b0 = (tile_start_bit<RAGGED, G, BPS>(p, cc * T, n_items) >> 3) & ~127ll;
+    int64_t b1 = (tile_start_bit<RAGGED, G, BPS>(p, (cc + 1) * T, n_items) >> 3) + 256; // + the halo of the last item
+    if (b1 > p.nw32 * 4) b1 = p.nw32 * 4;
+    const char *base = reinterpret_cast<const char *>(p.w32);
+    for (int64_t o = b0 + (static_cast<int64_t>(kk) * kBlockThreads + threadIdx.x) * 128; o < b1;
+         o += static_cast<int64_t>(kPfBlocks) * kBlockThreads * 128)
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + o));
+}
+
+// KMC_PREFETCH=0 switches the burst prefetch off (A/B measurements)
+inline bool prefetch_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("KMC_PREFETCH");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 // per-iteration strides of the uniform locator (every launcher calls this before the launch)
 inline void set_iteration_strides(ExtractParams &p)
 {
@@ -271,6 +340,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
     const uint64_t n_items = p.items_dev ? __ldg(p.items_dev) : p.items;
     if (tile_base >= n_items) return; // block-uniform
+    if (p.pf_tiles) burst_prefetch<RAGGED, G, BPS>(p, n_items);
     TileCursor<RAGGED, G> cur;
     cur.init(p, tile_base, sh, threadIdx.x);
 
@@ -403,6 +473,13 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
     if (tiles == 0) return cudaSuccess;
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     set_iteration_strides(p);
+    p.pf_tiles = 0;
+    if (SINK != SINK_BUCKETS && prefetch_enabled()) {
+        // chunks of about kPfChunkBytes of source: tiles per chunk from the average source bytes per tile
+        const uint64_t per_tile = static_cast<uint64_t>(p.nw32) * 4 / tiles + 1;
+        const uint64_t t = kPfChunkBytes / per_tile;
+        p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
+    }
     extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS>
         <<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
     return cudaGetLastError();

@@ -53,8 +53,10 @@ int binned_count_bin_bits(int bucket_bits);
 int apply_group(int dflt); // bins applied per launch (KMC_APPLY_GROUP overrides the default, for experiments)
 uint64_t binned_count_blocks(uint64_t n);
 cudaError_t warm_table(const uint32_t *table, uint64_t n_counters, int sm_count, cudaStream_t stream);
+// events (may be NULL): n_parts events, events[i] recorded once the i-th of n_parts equal ranges of the table is final
 cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint32_t *table, uint32_t *binned, uint64_t *matrix,
-                         uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream);
+                         uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream, uint32_t n_parts = 0,
+                         void *const *events = nullptr);
 
 // misc_kernels.cu -----------------------------------------------------------------------------
 cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,

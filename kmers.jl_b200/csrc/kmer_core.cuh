@@ -103,19 +103,42 @@ KMC_DEV uint64_t fx_hash(const uint64_t (&d)[N], uint64_t h)
 }
 
 // ---- streaming stores --------------------------------------------------------------------
+// The output streams are written once and never read by the kernel that writes them: no L1 allocation, and
+// first in line for eviction from L2 (so that they do not displace the prefetched source, extract_kernels.cuh).
+// kEvictFirst is what `createpolicy.fractional.L2::evict_first.b64 p, 1.0` returns (a constant encoding).
+#ifndef KMC_STORE_EVICT_FIRST
+#define KMC_STORE_EVICT_FIRST 1
+#endif
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+
 KMC_DEV void st_u64(uint64_t *p, uint64_t v)
 {
+#if KMC_STORE_EVICT_FIRST
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(kEvictFirst) : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
 }
 KMC_DEV void st_v2(uint64_t *p, uint64_t a, uint64_t b)
 {
+#if KMC_STORE_EVICT_FIRST
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(p), "l"(a), "l"(b), "l"(kEvictFirst)
+                 : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+#endif
 }
 // 256-bit store: one STG.E.256 on sm_100a
 KMC_DEV void st_v4(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
+#if KMC_STORE_EVICT_FIRST
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d),
+                 "l"(kEvictFirst)
+                 : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d)
                  : "memory");
+#endif
 }
 
 // CNT contiguous u64 values; `aligned32` says p is 32-byte aligned.

@@ -94,6 +94,8 @@ SIGNATURES = {
     "kmc_base_hash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]),
     "kmc_bucket_count": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p,
                                      C.POINTER(kmc_result)]),
+    "kmc_bucket_count_async": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p, C.c_uint32,
+                                           C.POINTER(C.c_void_p), C.POINTER(kmc_result)]),
     "kmc_minimizers": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
                                    C.POINTER(kmc_out), C.POINTER(kmc_result)]),
     "kmc_minhash_sketch": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,

@@ -132,6 +132,41 @@ def allreduce_table(table, group=None):
     return table
 
 
+def count_and_merge_table(ctx, desc, K: int, bucket_bits: int, table, n_parts: int = 8, group=None, comm_stream=None):
+    """Bucket-count this rank's reads into `table` (a zeroed CUDA int32 torch tensor of 2^bucket_bits entries) and
+    sum the tables of all ranks, with the merge overlapping the count: kmc_bucket_count_async records one
+    event per finished range of the table, and every range is all-reduced on `comm_stream` as soon as its
+    event has fired, while the context's stream is still counting the later ranges.  Returns the number of
+    k-mers this rank counted.  `ctx`'s stream must be torch's current stream.  With one rank (or an
+    L2-sized table, which is final only at the end) this degenerates to count, then merge."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _abi
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    main = torch.cuda.current_stream()
+    # torch creates the CUDA event on first use: record once so that the handle exists
+    events = [torch.cuda.Event() for _ in range(n_parts)]
+    for e in events:
+        e.record(main)
+    handles = (C.c_void_p * n_parts)(*[C.c_void_p(e.cuda_event) for e in events])
+    res = _abi.kmc_result()
+    ctx._check(ctx.lib.kmc_bucket_count_async(ctx.handle, C.byref(desc), K, bucket_bits, table.data_ptr(), n_parts, handles,
+                                              C.byref(res)))
+    if multi:
+        comm = comm_stream or torch.cuda.Stream()
+        part = table.numel() // n_parts
+        with torch.cuda.stream(comm):
+            for i, e in enumerate(events):
+                comm.wait_event(e)
+                dist.all_reduce(table[i * part:(i + 1) * part], op=dist.ReduceOp.SUM, group=group)
+        main.wait_stream(comm)
+        table.record_stream(comm)
+    return int(res.n_written)
+
+
 def gather_counts(n_local: int, group=None) -> Optional[list[int]]:
     """Element counts of every rank (for the global offsets of variable-length outputs:
     UnambiguousKmers); a host-side all_gather of one integer, not a data-path collective."""

@@ -57,6 +57,18 @@ def _worker(rank, world, port, ret):
     sharding.allreduce_table(table)
     want = np.bincount((h >> np.uint64(64 - bits)).astype(np.int64), minlength=1 << bits).astype(np.int32)
     ok &= bool(np.array_equal(table.cpu().numpy(), want))
+    # (1b) a table beyond L2, counted slice after slice with the merge of finished ranges overlapping the count
+    bits2 = 26
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx.set_stream(stream.cuda_stream)
+        table2 = torch.zeros(1 << bits2, dtype=torch.int32, device="cuda")
+        n_counted = sharding.count_and_merge_table(ctx, drs.desc, k, bits2, table2, n_parts=8)
+        stream.synchronize()
+        ctx.set_stream(None)
+    ok &= n_counted == e.n
+    want2 = np.bincount((h >> np.uint64(64 - bits2)).astype(np.int64), minlength=1 << bits2).astype(np.int32)
+    ok &= bool(np.array_equal(table2.cpu().numpy(), want2))
     # (2) one long 4-bit sequence: unambiguous k-mers with global indices
     n = 400_001
     codes = np.where(rng.random(n) < 0.01, np.uint64(15), np.uint64(1) << rng.integers(0, 4, size=n).astype(np.uint64))

@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--reads-per-gpu", type=int, default=25_000_000)
     ap.add_argument("--bits", type=int, default=28)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--overlap", type=int, default=0,
+                    help="N > 0: kmc_bucket_count_async with N progress events, finished table ranges all-reduced while "
+                         "later ranges are still being counted (sharding.count_and_merge_table)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -54,16 +57,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    comm = torch.cuda.Stream()
     t_count, t_merge = [], []
     for step in range(args.steps + 2):
         table.zero_()
         barrier()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
-        st = ctx.lib.kmc_bucket_count(ctx.handle, C.byref(desc), k, args.bits, table.data_ptr(), C.byref(res))
-        assert st == 0, ctx.lib.kmc_last_error(ctx.handle)
-        e1.record(stream)
-        sharding.allreduce_table(table)
+        if args.overlap:
+            sharding.count_and_merge_table(ctx, desc, k, args.bits, table, n_parts=args.overlap, comm_stream=comm)
+            e1.record(stream)  # (count and merge are not separable here: merge_ms reads ~0)
+        else:
+            st = ctx.lib.kmc_bucket_count(ctx.handle, C.byref(desc), k, args.bits, table.data_ptr(), C.byref(res))
+            assert st == 0, ctx.lib.kmc_last_error(ctx.handle)
+            e1.record(stream)
+            sharding.allreduce_table(table)
         e2.record(stream)
         barrier()
         if step >= 2:
@@ -82,7 +90,7 @@ def main():
             "n_gpus": world, "kmers": n, "count_ms": ms_c, "merge_ms": ms_m,
             "kmers_per_s": n / ((ms_c + ms_m) / 1e3), "kmers_per_s_count_only": n / (ms_c / 1e3),
             "table_bytes": tb, "allreduce_busbw_GBps": (2 * (world - 1) / world * tb / (ms_m / 1e3) / 1e9) if world > 1 else None,
-            "merged_total_ok": total == n, "collective": "torch.distributed all_reduce(SUM), NCCL" if world > 1 else None}), flush=True)
+            "merged_total_ok": total == n, "overlap_parts": args.overlap, "total_ms": ms_c + ms_m, "collective": "torch.distributed all_reduce(SUM), NCCL" if world > 1 else None}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -43,6 +43,19 @@ def main():
     half = buf.numel() // 2
     ms = timed(lambda: buf[:half].copy_(buf[half:2 * half]))
     out["torch_copy_read_plus_write_GBps"] = 2 * half * 8 / ms / 1e6
+    # host -> device over PCIe from pinned memory: the ceiling of bench.py's e2e leg (400 MB per step)
+    h = torch.empty(400_000_000 // 8, dtype=torch.int64).pin_memory()
+    d = torch.empty_like(h, device="cuda")
+    ms = timed(lambda: d.copy_(h, non_blocking=True))
+    out["h2d_pinned_400MB_GBps"] = h.numel() * 8 / ms / 1e6
+    for mb in (10, 32, 100):
+        step = mb * 1_000_000 // 8
+
+        def chunks():
+            for o in range(0, h.numel(), step):
+                d[o:o + step].copy_(h[o:o + step], non_blocking=True)
+        ms = timed(chunks)
+        out["h2d_pinned_400MB_in_%dMB_copies_GBps" % mb] = h.numel() * 8 / ms / 1e6
     print(json.dumps(out))
 
 
