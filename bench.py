@@ -15,6 +15,7 @@ CanonicalDNAMers{31} + fx_hash over 10 M x 150 bp 2-bit reads per GPU (1.2 G k-m
             itself cannot run; see DESIGN.md.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -77,9 +78,10 @@ def measured_peak():
 
 
 class ClockSampler:
+    # (timestamp last: it contains no comma-separated sub-fields, but keeps the indices below stable)
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, device):
         self.device, self.proc, self.path = device, None, None
@@ -94,7 +96,9 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock, maximum power and the throttle reasons over the samples taken between the wall-clock
+        times t0 and t1 (the timed region), all samples if none fall inside."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
             return out
@@ -103,25 +107,34 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    row = {"sm": float(f[1]), "mx": float(f[2]), "w": float(f[3]), "t": None,
+                           "reasons": {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                                "sw_power_cap"), f[5:9]) if v.lower().startswith("active")}}
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                if len(f) > 9:
+                    try:
+                        row["t"] = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        pass
+                rows.append(row)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if t0 is not None and r["t"] is not None and t0 <= r["t"] <= t1]
+        use = inside or rows
+        if use:
+            reasons = set().union(*[r["reasons"] for r in use])
+            out.update(sm_mhz=float(np.median([r["sm"] for r in use])), sm_max_mhz=float(max(r["mx"] for r in use)),
+                       reasons=sorted(reasons), samples=len(use), power_w_max=float(max(r["w"] for r in use)),
+                       window="timed region" if inside else "whole run (no sample carried a timestamp inside the timed region)")
         return out
 
 
@@ -251,6 +264,7 @@ def run_ours(args, rank, local_rank, world):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     t_begin.record(stream)
     for i in range(args.steps):
         ev[i][0].record(stream)
@@ -258,10 +272,26 @@ def run_ours(args, rank, local_rank, world):
         ev[i][1].record(stream)
     t_end.record(stream)
     barrier()
+    wall1 = time.time()
     total_ms = t_begin.elapsed_time(t_end)
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     assert res.n_written == n_kmers
+
+    # The same launch with idle gaps (outside the timed region, reported beside the roofline): back to back the
+    # kernel runs into the board's power cap and the SM clock drops (tools/diag_power.py: 1000 W, ~1650 of 1965 MHz);
+    # with 25 ms of idle between launches it runs at full clock.  The gap between the two is power, not the kernel.
+    gap_ms = []
+    if rank == 0:
+        for _ in range(12):
+            time.sleep(0.025)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step()
+            b.record(stream)
+            torch.cuda.synchronize()
+            gap_ms.append(a.elapsed_time(b))
+    barrier()
 
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -388,7 +418,13 @@ def run_ours(args, rank, local_rank, world):
                        "l2": "no explicit flush: each step streams 0.4 GB in + 19.2 GB out, far larger than the 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "extract_kernel<N=1,NX=3,CANON,HASH,uniform,G=8>",
-                         "kernel_ms": k_ms, "bytes_per_kmer": BYTES_PER_KMER, "peak_source": peak_src},
+                         "kernel_ms": k_ms, "bytes_per_kmer": BYTES_PER_KMER, "peak_source": peak_src,
+                         "idle_gaps": {"kernel_ms": float(np.median(gap_ms)),
+                                       "achieved": BYTES_PER_KMER * n_kmers / (float(np.median(gap_ms)) / 1e3) / 1e9,
+                                       "how": "the same launch, 12 times with 25 ms of idle before each (full SM clock, no "
+                                              "power cap); not the timed region"} if gap_ms else None,
+                         "write_ceiling_note": "the peak is a copy (half reads); this kernel is 98 % writes, whose ceiling "
+                                               "measures 7480 GB/s (profiles/r01_bw_probe_v2.json, tools/bw_probe.py)"},
             "gpu_launches": args.steps,
             "clocks": clocks,
         }

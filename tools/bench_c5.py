@@ -89,7 +89,7 @@ def main():
             "case": f"C5 canonical 31-mer bucket-count table, B={args.bits}, {n_reads:,} x 150 bp reads per GPU, {world} GPU(s)",
             "n_gpus": world, "kmers": n, "count_ms": ms_c, "merge_ms": ms_m,
             "kmers_per_s": n / ((ms_c + ms_m) / 1e3), "kmers_per_s_count_only": n / (ms_c / 1e3),
-            "table_bytes": tb, "allreduce_busbw_GBps": (2 * (world - 1) / world * tb / (ms_m / 1e3) / 1e9) if world > 1 else None,
+            "table_bytes": tb, "allreduce_busbw_GBps": (2 * (world - 1) / world * tb / (ms_m / 1e3) / 1e9) if world > 1 and not args.overlap else None,
             "merged_total_ok": total == n, "overlap_parts": args.overlap, "total_ms": ms_c + ms_m, "collective": "torch.distributed all_reduce(SUM), NCCL" if world > 1 else None}), flush=True)
     if world > 1:
         dist.barrier()
