@@ -240,7 +240,7 @@ int32_t ensure_host_small(kmc_ctx *ctx)
     if (ctx->host_small) return KMC_OK;
     CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->host_small), 4096, cudaHostAllocDefault));
     memset(ctx->host_small, 0, 4096);
-    CU(cudaMalloc(reinterpret_cast<void **>(&ctx->dev_small), 64));
+    CU(cudaMalloc(reinterpret_cast<void **>(&ctx->dev_small), 128));
     return KMC_OK;
 }
 
@@ -614,7 +614,7 @@ int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t
             CU(cudaFreeAsync(q, stream));
     } else {
         // a table that fits L2 is pulled into it first: increments that miss L2 serialise at DRAM latency
-        if (table_bytes <= (96ull << 20)) CU(warm_table(table, 1ull << bucket_bits, ctx->sm_count, stream));
+        if (table_bytes <= (96ull << 20)) CU(warm_table(table, 1ull << bucket_bits, ctx->sm_count, warm_sink(ctx), stream));
         p.bucket_table = table;
         ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKETS, true, !L.uniform_len);
         if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");

@@ -114,13 +114,8 @@ int apply_group(int dflt)
     return env ? env : dflt;
 }
 
-cudaError_t warm_table(const uint32_t *table, uint64_t n_counters, int sm_count, cudaStream_t stream)
+cudaError_t warm_table(const uint32_t *table, uint64_t n_counters, int sm_count, uint32_t *sink, cudaStream_t stream)
 {
-    static uint32_t *sink = nullptr; // never written in practice (see warm_slice_kernel)
-    if (!sink) {
-        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&sink), 256);
-        if (e != cudaSuccess) return e;
-    }
     warm_slice_kernel<<<static_cast<unsigned>(sm_count * 8), 256, 0, stream>>>(table, n_counters, sink);
     return cudaGetLastError();
 }

@@ -279,13 +279,11 @@ cudaError_t launch_compact(ExtractParams p, CompactParams cp, cudaStream_t strea
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     set_iteration_strides(p);
     constexpr size_t smem = static_cast<size_t>(kWarpsPerBlock) * stage_words(N) * sizeof(uint64_t);
-    static bool configured = false; // per instantiation; the attribute is sticky for the process
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(compact_kernel<N, NX, HASH, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // (set on every launch: the attribute belongs to the function on the CURRENT device, and a process may hold
+    // contexts on several devices; the call costs a few microseconds)
+    cudaError_t e = cudaFuncSetAttribute(compact_kernel<N, NX, HASH, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
     compact_kernel<N, NX, HASH, RAGGED><<<static_cast<unsigned>(tiles), kBlockThreads, smem, stream>>>(p, cp);
     return cudaGetLastError();
 }

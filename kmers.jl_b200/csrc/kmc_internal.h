@@ -24,11 +24,13 @@ struct kmc_ctx {
     // small pinned host block for device->host read-backs of counts and error records:
     // 16 u64 per pipeline slot, slot 3 = the context's own stream
     uint64_t *host_small = nullptr;
-    uint64_t *dev_small = nullptr; // 64 bytes of device memory: KMC_DIGEST accumulators
+    uint64_t *dev_small = nullptr; // 128 bytes of device memory: KMC_DIGEST accumulators (first 64), warm_table's sink (byte 96)
     std::string last_error;
 };
 
 namespace kmc {
+
+inline uint32_t *warm_sink(kmc_ctx *ctx) { return reinterpret_cast<uint32_t *>(ctx->dev_small) + 24; }
 
 // scratch carving -------------------------------------------------------------------------
 int32_t ensure_scratch(kmc_ctx *ctx, uint64_t bytes);
@@ -52,7 +54,8 @@ cudaError_t tile_first_reads(const uint64_t *item_off, uint64_t n_seqs, uint64_t
 int binned_count_bin_bits(int bucket_bits);
 int apply_group(int dflt); // bins applied per launch (KMC_APPLY_GROUP overrides the default, for experiments)
 uint64_t binned_count_blocks(uint64_t n);
-cudaError_t warm_table(const uint32_t *table, uint64_t n_counters, int sm_count, cudaStream_t stream);
+// pulls table[0..n_counters) into L2; sink: 4 bytes of device memory on the table's device (never written in practice)
+cudaError_t warm_table(const uint32_t *table, uint64_t n_counters, int sm_count, uint32_t *sink, cudaStream_t stream);
 // events (may be NULL): n_parts events, events[i] recorded once the i-th of n_parts equal ranges of the table is final
 cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint32_t *table, uint32_t *binned, uint64_t *matrix,
                          uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream, uint32_t n_parts = 0,

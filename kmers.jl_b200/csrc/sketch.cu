@@ -508,8 +508,8 @@ extern "C" int32_t kmc_kmer_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k,
         for (int b = 0; b < (1 << bin_bits); b += group) {
             const int b_end = std::min(b + group, 1 << bin_bits);
             const uint64_t slots = slice * static_cast<uint64_t>(b_end - b);
-            CU(warm_table(reinterpret_cast<const uint32_t *>(keys + static_cast<uint64_t>(b) * slice), 2 * slots, ctx->sm_count, stream));
-            CU(warm_table(vals + static_cast<uint64_t>(b) * slice, slots, ctx->sm_count, stream));
+            CU(warm_table(reinterpret_cast<const uint32_t *>(keys + static_cast<uint64_t>(b) * slice), 2 * slots, ctx->sm_count, warm_sink(ctx), stream));
+            CU(warm_table(vals + static_cast<uint64_t>(b) * slice, slots, ctx->sm_count, warm_sink(ctx), stream));
             bin_insert_kernel<<<static_cast<unsigned>(ctx->sm_count * 16), 256, 0, stream>>>(
                 sorted, offs, n_blocks, b, b_end, c.keys, vals, log2_capacity, distinct, overflow);
         }
