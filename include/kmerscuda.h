@@ -247,7 +247,10 @@ int32_t kmc_digest(kmc_ctx *ctx, const uint64_t *dptr, uint64_t n, uint64_t *out
 int32_t kmc_timer_begin(kmc_ctx *ctx);
 int32_t kmc_timer_end(kmc_ctx *ctx, float *ms); /* synchronises */
 
-/* ---- measurement aid: pure 256-bit streaming store of `bytes` (write roofline probe) -- */
+/* ---- measurement aid: pure 256-bit streaming store of `bytes` (write roofline probe) --
+ * The environment variable KMC_STORE_PROBE_PATTERN selects variants of the probe that reproduce the
+ * extraction kernels' store pattern with and without their source reads (tools/bw_probe.py; the
+ * experiments behind DESIGN.md 3.1).  Not part of the drop-in boundary. */
 int32_t kmc_store_probe(kmc_ctx *ctx, void *dptr, uint64_t bytes);
 
 #ifdef __cplusplus

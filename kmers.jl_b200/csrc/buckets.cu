@@ -1,14 +1,15 @@
 // buckets.cu -- the canonical k-mer bucket-count table (north_star extension; not in the reference):
 // table[fx_hash(canonical k-mer) >> (64 - B)] += 1 over a read set.
 //
-// Two regimes, both bound by how fast L2 can apply 4-byte increments (2.2e11 / s measured):
-//   * the table fits L2 (<= 64 MB): extract_kernel<SINK_BUCKETS> increments it directly;
-//   * larger tables (B = 28 is 1 GiB): random increments miss L2 and every one of them becomes a
-//     32-byte DRAM sector read + write (measured 24 G k-mers/s).  So the bucket ids are first
-//     written out (SINK_IDS), partitioned by their high bits into bins whose table slice is
-//     <= 16 MB (per-block counting sort in shared memory, exact placement from a count matrix --
-//     no atomics on global cursors), and then applied bin after bin, so that all SMs work on one
-//     L2-resident slice of the table at a time.
+// Two regimes, both bound by how fast an SM can issue scattered 4-byte increments (1.29 cycles per lane:
+// 2.2e11 / s measured; shared-memory atomics are no faster, so there is nothing to privatise):
+//   * the table fits L2 (<= 96 MB): extract_kernel<SINK_BUCKETS> increments it directly;
+//   * larger tables (B = 28 is 1 GiB): random increments miss L2 and serialise at DRAM latency (measured
+//     24 G k-mers/s).  So the bucket ids are first written out (SINK_IDS), partitioned by their high bits into
+//     bins whose table slice is <= 16 MB (binning.cuh: no atomics, exact placement from a count matrix), and
+//     then applied bin after bin, so that all SMs work on an L2-resident part of the table at a time.  The
+//     table is final range by range, which kmc_bucket_count_async reports through events so that the merge of
+//     several GPUs' tables can overlap the count.
 #include <cstdlib>
 
 #include "binning.cuh"
