@@ -42,6 +42,15 @@ ExtractLaunchFn get_launcher(const Geometry &ge, int mode, bool hash, bool ragge
     return nullptr;
 }
 
+ExtractLaunchFn get_digest_launcher(const Geometry &ge, int mode, bool hash, bool ragged)
+{
+    switch (ge.n_limbs) {
+    case 1: return get_digest_launcher_n1(ge.nx, mode, hash, ragged);
+    case 2: return get_digest_launcher_n2(ge.nx, mode, hash, ragged);
+    }
+    return nullptr;
+}
+
 namespace {
 
 bool aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
@@ -208,7 +217,9 @@ int32_t extract_device(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode,
     st = bind_outputs(ctx, out, mode, flags, &p);
     if (st) return st;
 
-    ExtractLaunchFn fn = get_launcher(ge, kmode, hash, !L.uniform_len);
+    const bool fused_digest = known.digest && digest_fusable(s, ge.n_limbs, mode, flags);
+    if (fused_digest) p.digest = known.digest;
+    ExtractLaunchFn fn = fused_digest ? get_digest_launcher(ge, kmode, hash, !L.uniform_len) : get_launcher(ge, kmode, hash, !L.uniform_len);
     if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
     CU(fn(p, ctx->sm_count, stream));
     if (sync) {

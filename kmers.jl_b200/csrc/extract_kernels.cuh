@@ -71,6 +71,8 @@ struct ExtractParams {
     unsigned long long *err_flat;  // strict modes: atomicMin of the first flat window with an uncertain symbol
     // source prefetch in bursts (see burst_prefetch): tiles per chunk; 0 = off.  Set by launch_extract.
     uint32_t pf_tiles;
+    // DIGEST instantiations: xor / wrapping sum of the words written to out_a -> digest[0..1], of out_hash -> [2..3]
+    unsigned long long *digest;
 };
 
 // Validity bits of the slots [jlo, jhi) of one item: bit j set <=> window j has no uncertain symbol.
@@ -326,9 +328,12 @@ inline void set_iteration_strides(ExtractParams &p)
 
 
 
-template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false, int BPS = 2>
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false, int BPS = 2,
+          bool DIGEST = false>
 __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractParams p)
 {
+    static_assert(!DIGEST || (SINK == SINK_STREAMS && MODE != MODE_FWRV), "the fused fingerprint covers out_a and out_hash");
+    uint64_t dg_xa = 0, dg_sa = 0, dg_xh = 0, dg_sh = 0; // DIGEST: this thread's share of the fingerprint
     constexpr int G = GroupOf<N>::G;
     constexpr bool WANT_FW = true;
     constexpr bool WANT_RV = (MODE != MODE_FW);
@@ -377,6 +382,17 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
 #pragma unroll
                 for (int i = 0; i < N; ++i) a[j][i] = take_fw ? fw[j][i] : rv[j][i];
                 if (HASH) h[j] = fx_hash<N>(a[j], 0);
+                if (DIGEST && j >= jlo && j < jhi) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        dg_xa ^= a[j][i];
+                        dg_sa += a[j][i];
+                    }
+                    if (HASH) {
+                        dg_xh ^= h[j];
+                        dg_sh += h[j];
+                    }
+                }
             }
 
             if (SINK == SINK_IDS) {
@@ -460,13 +476,41 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     next_item:
         cur.advance(p);
     }
+    if (DIGEST) {
+        // one set of atomics per block (same-address atomics serialise in L2)
+        __shared__ uint64_t s_dg[4][kBlockThreads / 32];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            dg_xa ^= __shfl_xor_sync(0xffffffffu, dg_xa, d);
+            dg_sa += __shfl_xor_sync(0xffffffffu, dg_sa, d);
+            dg_xh ^= __shfl_xor_sync(0xffffffffu, dg_xh, d);
+            dg_sh += __shfl_xor_sync(0xffffffffu, dg_sh, d);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_dg[0][threadIdx.x >> 5] = dg_xa;
+            s_dg[1][threadIdx.x >> 5] = dg_sa;
+            s_dg[2][threadIdx.x >> 5] = dg_xh;
+            s_dg[3][threadIdx.x >> 5] = dg_sh;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            uint64_t v = 0;
+#pragma unroll
+            for (int w = 0; w < kBlockThreads / 32; ++w) v = (threadIdx.x & 1) ? v + s_dg[threadIdx.x][w] : v ^ s_dg[threadIdx.x][w];
+            if (threadIdx.x & 1)
+                atomicAdd(p.digest + threadIdx.x, static_cast<unsigned long long>(v));
+            else
+                atomicXor(p.digest + threadIdx.x, static_cast<unsigned long long>(v));
+        }
+    }
 }
 
 // Host-side launcher: one block per tile of kTileItems work items.  Defined per N in
 // extract_n*.cu so the instantiations compile in parallel.
 using ExtractLaunchFn = cudaError_t (*)(ExtractParams, int sm_count, cudaStream_t);
 
-template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false, int BPS = 2>
+template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false, int BPS = 2,
+          bool DIGEST = false>
 cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t stream)
 {
     const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
@@ -480,7 +524,8 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
         const uint64_t t = kPfChunkBytes / per_tile;
         p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
     }
-    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS>
+    if (DIGEST && !p.digest) return cudaErrorInvalidValue;
+    extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS, DIGEST>
         <<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -528,6 +573,39 @@ constexpr int MODE_BUCKET_IDS = -2; // canonical + fx_hash -> flat array of 32-b
         if (nx == NXMAX) return pick_mode_##N<NXMAX>(mode, hash, ragged);                           \
         if (nx == NXMAX - 1) return pick_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
         if (nx == NXMAX - 2) return pick_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
+        return nullptr;                                                                             \
+    }
+
+// The same kernels with the fingerprint of their output fused in (KMC_DIGEST of the host pipeline): FwKmers and
+// CanonicalKmers, SoA, N <= 2 (extract_n{1,2}.cu).
+ExtractLaunchFn get_digest_launcher_n1(int nx, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_digest_launcher_n2(int nx, int mode, bool hash, bool ragged);
+
+#define KMC_DEFINE_DIGEST_TABLE(FN, N)                                                              \
+    template <int NX, int MODE>                                                                     \
+    static ExtractLaunchFn pickdg_##N(bool hash, bool ragged)                                       \
+    {                                                                                               \
+        if (hash)                                                                                   \
+            return ragged ? &launch_extract<N, NX, MODE, true, true, SINK_STREAMS, false, 2, true>  \
+                          : &launch_extract<N, NX, MODE, true, false, SINK_STREAMS, false, 2, true>; \
+        return ragged ? &launch_extract<N, NX, MODE, false, true, SINK_STREAMS, false, 2, true>     \
+                      : &launch_extract<N, NX, MODE, false, false, SINK_STREAMS, false, 2, true>;   \
+    }                                                                                               \
+    template <int NX>                                                                               \
+    static ExtractLaunchFn pickdg_mode_##N(int mode, bool hash, bool ragged)                        \
+    {                                                                                               \
+        switch (mode) {                                                                             \
+        case MODE_FW: return pickdg_##N<NX, MODE_FW>(hash, ragged);                                 \
+        case MODE_CANON: return pickdg_##N<NX, MODE_CANON>(hash, ragged);                           \
+        }                                                                                           \
+        return nullptr;                                                                             \
+    }                                                                                               \
+    ExtractLaunchFn FN(int nx, int mode, bool hash, bool ragged)                                    \
+    {                                                                                               \
+        constexpr int NXMAX = (64 * N + 2 * GroupOf<N>::G - 2 + 31) / 32;                           \
+        if (nx == NXMAX) return pickdg_mode_##N<NXMAX>(mode, hash, ragged);                         \
+        if (nx == NXMAX - 1) return pickdg_mode_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(mode, hash, ragged); \
+        if (nx == NXMAX - 2) return pickdg_mode_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(mode, hash, ragged); \
         return nullptr;                                                                             \
     }
 

@@ -2,4 +2,5 @@
 #include "extract_kernels.cuh"
 namespace kmc {
 KMC_DEFINE_LAUNCHER_TABLE(get_extract_launcher_n1, 1)
+KMC_DEFINE_DIGEST_TABLE(get_digest_launcher_n1, 1)
 }

@@ -299,8 +299,10 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
     };
 
     // KMC_DIGEST: fingerprint the chunk's k-mers and hashes right behind the kernel that wrote them
+    // (the 2-bit SoA forms of FwKmers / CanonicalKmers fingerprint their output inside the extraction kernel)
+    const bool fused_digest = want_digest && digest_fusable(hs, ge.n_limbs, mode, flags);
     auto digest_chunk = [&](Chunk &c, Slot &sl, uint64_t n) -> int32_t {
-        if (!want_digest || !n) return KMC_OK;
+        if (!want_digest || !n || fused_digest) return KMC_OK;
         CU(launch_digest(c.dout.a, n * a_elems, ctx->dev_small, ctx->sm_count, sl.stream, false));
         if (hash) CU(launch_digest(c.dout.hash, n, ctx->dev_small + 2, ctx->sm_count, sl.stream, false));
         return KMC_OK;
@@ -382,6 +384,7 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
         scratch.used = 0;
         if (!four) {
             kmc_result r{};
+            if (fused_digest) known.digest = reinterpret_cast<unsigned long long *>(ctx->dev_small);
             st = kmer4 ? extract_device_kmer4(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch)
                        : extract_device(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch);
             if (st) return st;

@@ -59,7 +59,17 @@ struct KnownTotals {
     bool valid = false;
     uint64_t windows = 0;
     uint64_t items = 0;
+    // KMC_DIGEST of the host pipeline: if not NULL and digest_fusable(), the extraction kernel adds the xor / wrapping
+    // sum of what it writes to digest[0..1] (stream a) and digest[2..3] (hash stream) itself, instead of a second
+    // pass that re-reads both streams
+    unsigned long long *digest = nullptr;
 };
+
+// the fused fingerprint exists for the SoA forms of FwKmers / CanonicalKmers over 2-bit sources, K <= 64
+inline bool digest_fusable(const kmc_seqs *s, int n_limbs, int mode, uint32_t flags)
+{
+    return s->src_bits == 2 && !(flags & (KMC_AOS | KMC_KMER4)) && (mode == KMC_FW || mode == KMC_CANON) && n_limbs <= 2;
+}
 
 struct Layout {
     bool uniform_len, uniform_off;
@@ -98,6 +108,7 @@ int32_t bind_outputs(kmc_ctx *ctx, const kmc_out *out, int mode, uint32_t flags,
 cudaError_t fill_uniform_offsets(uint64_t *out, uint64_t n_plus_1, uint64_t step, cudaStream_t stream);
 
 ExtractLaunchFn get_launcher(const Geometry &ge, int mode, bool hash, bool ragged);
+ExtractLaunchFn get_digest_launcher(const Geometry &ge, int mode, bool hash, bool ragged); // MODE_FW / MODE_CANON, N <= 2
 
 // The device-resident extraction for 2-bit sources; everything is enqueued on `stream`.
 int32_t extract_device(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode, uint32_t flags, const kmc_out *out,

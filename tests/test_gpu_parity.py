@@ -346,6 +346,42 @@ def test_host_sequences_device_outputs_and_digest(kc, ctx):
         assert s == int(sl.sum(dtype=np.uint64)) if m else s == 0
 
 
+@pytest.mark.parametrize("mode,k,hash_,ragged", [("fw", 31, False, False), ("canon", 63, True, True), ("fw", 5, True, True),
+                                                 ("canon", 32, False, False)])
+def test_digest_fused_into_the_extraction_kernel(kc, ctx, mode, k, hash_, ragged):
+    """KMC_DIGEST for the SoA forms of FwKmers / CanonicalKmers over 2-bit sources comes out of the extraction kernel
+    itself (no second pass over the streams): one- and two-limb k-mers, with and without the hash stream, uniform and
+    ragged sets with partial groups at every read boundary."""
+    from kmerscuda import _abi
+    rng = np.random.default_rng(k + 7)
+    omode = ko.CANON if mode == "canon" else ko.FW
+    if ragged:
+        lens = rng.integers(0, 300, size=20_000).tolist()
+        seqs, words, off, ln = make_ragged(rng, [int(x) for x in lens])
+        n_seqs = len(lens)
+        a, _, h, _ = ko.batch_iterate(words, n_seqs, k, omode, word_off=off, seq_len=ln, want_hash=True)
+        desc = _abi.kmc_seqs(words.ctypes.data, words.size, n_seqs, off.ctypes.data, ln.ctypes.data, 0, 0, 2, 0)
+    else:
+        n_seqs, length, stride = 30_000, 150, 5
+        words = rng.integers(0, 2**64, size=n_seqs * stride, dtype=np.uint64)
+        a, _, h, _ = ko.batch_iterate(words, n_seqs, k, omode, uniform_len=length, uniform_stride=stride, want_hash=True)
+        desc = _abi.kmc_seqs(words.ctypes.data, words.size, n_seqs, None, None, length, stride, 2, 0)
+    n, limbs = a.shape
+    da, dh = ctx.alloc(max(n, 1) * limbs * 8), ctx.alloc(max(n, 1) * 8)
+    out = _abi.kmc_out(da.ptr, None, dh.ptr if hash_ else None, None, None, n, 0)
+    res = _abi.kmc_result()
+    flags = (_abi.KMC_HASH_FX if hash_ else 0) | _abi.KMC_OUT_DEVICE | _abi.KMC_DIGEST
+    ctx._check(ctx.lib.kmc_extract_host(ctx.handle, C.byref(desc), k, MODES[mode], flags, C.byref(out), C.byref(res)))
+    want = [int(np.bitwise_xor.reduce(a.reshape(-1))), int(a.sum(dtype=np.uint64)),
+            int(np.bitwise_xor.reduce(h)) if hash_ else 0, int(h.sum(dtype=np.uint64)) if hash_ else 0]
+    assert int(res.n_written) == n and list(res.digest) == want
+    assert np.array_equal(da.download(np.uint64, n * limbs).reshape(n, limbs), a)
+    if hash_:
+        assert np.array_equal(dh.download(np.uint64, n), h)
+    da.free()
+    dh.free()
+
+
 # ---------------------------------------------------------------------- bucket count table
 def test_bucket_count_binned_ragged(kc):
     """Tables beyond L2 take the binned path (ids -> bins -> apply); ragged set, one- and two-limb k-mers."""
