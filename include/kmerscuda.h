@@ -76,7 +76,9 @@ extern "C" {
                             or from a 2-bit source (TwoToFour, FwKmers.jl:96-102, CanonicalKmers.jl:122-129). */
 #define KMC_DIGEST 0x10u /* kmc_extract_host only: also fingerprint what was written -- xor and wrapping
                             sum of the out.a words and of the out.hash words -> result->digest[4].
-                            Computed chunk by chunk inside the pipeline, while the chunk is L2-hot. */
+                            For FwKmers / CanonicalKmers over 2-bit sources (SoA, K <= 64) the extraction
+                            kernel accumulates it from its own registers; other forms are fingerprinted
+                            chunk by chunk by a second kernel right behind the one that wrote the chunk. */
 
 typedef struct kmc_ctx kmc_ctx;
 
