@@ -33,7 +33,8 @@ const KMC_FW, KMC_FWRV, KMC_CANON, KMC_UNAMBIG = Int32(0), Int32(1), Int32(2), I
 const KMC_HASH_FX, KMC_AOS = UInt32(1), UInt32(2)
 const KMC_KMER4 = UInt32(0x40)   # k-mers over a 4-bit alphabet (Copyable 4 -> 4, TwoToFour)
 
-# struct kmc_seqs / kmc_out / kmc_result of include/kmerscuda.h (same field order and sizes)
+# struct kmc_seqs / kmc_out / kmc_result of include/kmerscuda.h (same field order and sizes).  KmcResult is
+# mutable and passed as Ref{KmcResult}: ccall hands the library the address of the object itself.
 struct KmcSeqs
     words::Ptr{UInt64}
     n_words::UInt64
@@ -113,7 +114,8 @@ mode_of(::Type{<:UnambiguousKmers}) = KMC_UNAMBIG
 function throw_status(ctx::Context, st::Int32, res::KmcResult, ::Type{A}) where {A}
     if st == KMC_E_AMBIGUOUS
         # what src/construction.jl:108-110 throws: EncodeError(Alphabet, symbol)
-        throw(BioSequences.EncodeError(A(), reinterpret(DNA, UInt8(res.err_sym))))
+        sym = A <: RNAAlphabet ? reinterpret(RNA, UInt8(res.err_sym)) : reinterpret(DNA, UInt8(res.err_sym))
+        throw(BioSequences.EncodeError(A(), sym))
     elseif st == KMC_E_BAD_K
         error("K must be at least 1")            # src/iterators/FwKmers.jl:32-33
     else
@@ -150,8 +152,8 @@ function collect(it::Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, 
         s = Ref(KmcSeqs(pointer(words), length(words), 1, C_NULL, C_NULL, len, length(words), src_bits(typeof(seq)), 0))
         o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, C_NULL, C_NULL, C_NULL, nwin, 0))
         st = ccall((:kmc_extract_host, LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
-            ctx.handle, s, K, mode, KMC_AOS | KMC_KMER4, o, pointer_from_objref(res))
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ref{KmcResult}),
+            ctx.handle, s, K, mode, KMC_AOS | KMC_KMER4, o, res)
         st == KMC_OK || throw_status(ctx, st, res, A)
     end
     return out
@@ -179,8 +181,8 @@ function collect(it::Union{FwKmers{A, K}, FwRvIterator{A, K}, CanonicalKmers{A, 
         s = Ref(KmcSeqs(pointer(words), length(words), 1, C_NULL, C_NULL, len, length(words), bits, 0))
         o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, C_NULL, C_NULL, C_NULL, cap, 0))
         st = ccall((:kmc_extract_host, LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
-            ctx.handle, s, K, mode, KMC_AOS, o, pointer_from_objref(res))
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ref{KmcResult}),
+            ctx.handle, s, K, mode, KMC_AOS, o, res)
         st == KMC_OK || throw_status(ctx, st, res, A)
     end
     resize!(out, res.n_written)
@@ -192,6 +194,9 @@ end
 const AsciiSource = Union{String, SubString{String}, Base.CodeUnits{UInt8, String}, Vector{UInt8}}
 ascii_bytes(s::Union{String, SubString{String}}) = codeunits(s)
 ascii_bytes(s) = s
+# first byte of the source (the caller holds the source with GC.@preserve)
+ascii_pointer(s::Union{String, SubString{String}, Vector{UInt8}}) = Ptr{UInt8}(pointer(s))
+ascii_pointer(s::Base.CodeUnits{UInt8, String}) = Ptr{UInt8}(pointer(s.s))
 
 function collect_ascii(it::AnyIter{A, K}, src::AsciiSource; ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
     T = derive_type(Kmer{A, K})
@@ -203,11 +208,11 @@ function collect_ascii(it::AnyIter{A, K}, src::AsciiSource; ctx::Context = defau
     res = KmcResult()
     flags = KMC_AOS | (A <: RNAAlphabet ? UInt32(0x20) : UInt32(0))   # KMC_RNA: U, not T, is the fourth letter
     GC.@preserve src out begin
-        s = Ref(KmcSeqs(Ptr{UInt64}(pointer(bytes)), len, 1, C_NULL, C_NULL, len, max(len, 1), UInt32(8), 0))
+        s = Ref(KmcSeqs(Ptr{UInt64}(ascii_pointer(src)), len, 1, C_NULL, C_NULL, len, max(len, 1), UInt32(8), 0))
         o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, C_NULL, C_NULL, C_NULL, length(out), 0))
         st = ccall((:kmc_extract_host, LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
-            ctx.handle, s, K, mode, flags, o, pointer_from_objref(res))
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ref{KmcResult}),
+            ctx.handle, s, K, mode, flags, o, res)
         if st == KMC_E_AMBIGUOUS   # FwKmers.jl:124-126 / UnambiguousKmers.jl:123-124
             throw(BioSequences.EncodeError(A(), repr(UInt8(res.err_sym))))
         end
@@ -275,8 +280,8 @@ function extract(::Type{I}, reads::Vector{S}; hash::Bool = false,
         o = Ref(KmcOut(Ptr{UInt64}(pointer(out)), C_NULL, hash ? pointer(hashes) : C_NULL, C_NULL,
             pointer(offsets), cap, 0))
         st = ccall((:kmc_extract_host, LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
-            ctx.handle, s, K, mode, KMC_AOS | (hash ? KMC_HASH_FX : UInt32(0)), o, pointer_from_objref(res))
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ref{KmcResult}),
+            ctx.handle, s, K, mode, KMC_AOS | (hash ? KMC_HASH_FX : UInt32(0)), o, res)
         st == KMC_OK || throw_status(ctx, st, res, A)
     end
     resize!(out, res.n_written)
@@ -369,8 +374,8 @@ function minhash_sketch(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}}, s::Integ
         dout = Ref{Ptr{Cvoid}}(C_NULL)
         ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 8 * s, dout)
         st = ccall((:kmc_minhash_sketch, LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt64, Ptr{Cvoid}, Ptr{KmcResult}),
-            ctx.handle, d, K, mode_of(typeof(it)), s, dout[], pointer_from_objref(res))
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt64, Ptr{Cvoid}, Ref{KmcResult}),
+            ctx.handle, d, K, mode_of(typeof(it)), s, dout[], res)
         st == KMC_OK && ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64),
             ctx.handle, out, dout[], 8 * res.n_written)
         device_free(ctx, dout[])
@@ -394,8 +399,8 @@ function composition(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}};
         ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(counts), dt)
         ccall((:kmc_memset, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, UInt64), ctx.handle, dt[], 0, sizeof(counts))
         st = ccall((:kmc_composition, LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Ptr{Cvoid}, Ptr{KmcResult}),
-            ctx.handle, d, K, mode_of(typeof(it)), dt[], pointer_from_objref(res))
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Ptr{Cvoid}, Ref{KmcResult}),
+            ctx.handle, d, K, mode_of(typeof(it)), dt[], res)
         st == KMC_OK && ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64),
             ctx.handle, counts, dt[], sizeof(counts))
         device_free(ctx, dt[])
@@ -425,8 +430,8 @@ function minimizers(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}}, W::Integer; 
         ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 8 * max(n, 1), di)
         o = Ref(KmcOut(Ptr{UInt64}(dk[]), C_NULL, C_NULL, Ptr{Int64}(di[]), C_NULL, n, 0))
         st = ccall((:kmc_minimizers, LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Int32, Int32, UInt32, Ptr{KmcOut}, Ptr{KmcResult}),
-            ctx.handle, d, K, W, step, mode_of(typeof(it)), UInt32(0), o, pointer_from_objref(res))
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Int32, Int32, UInt32, Ptr{KmcOut}, Ref{KmcResult}),
+            ctx.handle, d, K, W, step, mode_of(typeof(it)), UInt32(0), o, res)
         if st == KMC_OK
             ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, kmers, dk[], 8 * n)
             ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, starts, di[], 8 * n)
