@@ -18,7 +18,7 @@ using Kmers
 using Kmers: FwKmers, FwRvIterator, CanonicalKmers, UnambiguousKmers, Kmer, derive_type
 using Libdl
 
-export fx_hash_device, hash_device, extract, set_library!, minhash_sketch, composition, minimizers
+export fx_hash_device, hash_device, extract, set_library!, minhash_sketch, composition, minimizers, count_kmers, bucket_count
 
 # ---------------------------------------------------------------------------------------------
 # library handle
@@ -441,6 +441,79 @@ function minimizers(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}}, W::Integer; 
         st == KMC_OK || throw_status(ctx, st, res, A)
     end
     return kmers, starts
+end
+
+"""
+    count_kmers(FwKmers{A,K}(seq) | CanonicalKmers{A,K}(seq); log2_capacity) -> Dict{Kmer{A,K,1}, Int}
+
+Exact k-mer counts -- the `Dict` a loop over the iterator would build -- through `kmc_kmer_count` (open addressing
+in device memory keyed by the k-mer, K <= 31, or K = 32 for canonical k-mers) and `kmc_kmer_table_export`.
+`log2_capacity` defaults to twice the number of windows, rounded up to a power of two.
+"""
+function count_kmers(it::Union{FwKmers{A, K}, CanonicalKmers{A, K}};
+        log2_capacity::Integer = max(10, ceil(Int, log2(2 * max(1, length(source(it)))))),
+        ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
+    K <= 32 || throw(ArgumentError("count_kmers handles one-limb k-mers (K <= 32)"))
+    T = derive_type(Kmer{A, K})
+    slots = UInt64(1) << log2_capacity
+    res = KmcResult()
+    keys, vals = UInt64[], UInt32[]
+    with_device_sequence(ctx, source(it)) do d
+        dk, dv = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 8 * slots, dk)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 4 * slots, dv)
+        ccall((:kmc_memset, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, UInt64), ctx.handle, dk[], 0xff, 8 * slots)  # free slot = ~0
+        ccall((:kmc_memset, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, UInt64), ctx.handle, dv[], 0, 4 * slots)
+        st = ccall((:kmc_kmer_count, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, UInt32, Ref{KmcResult}),
+            ctx.handle, d, K, mode_of(typeof(it)), dk[], dv[], UInt32(log2_capacity), res)
+        if st == KMC_OK
+            n = res.digest[1]                      # keys this call added = every key of a fresh table
+            resize!(keys, n); resize!(vals, n)
+            ok, ov, nout = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL), Ref{UInt64}(0)
+            ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 8 * max(n, 1), ok)
+            ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, 4 * max(n, 1), ov)
+            st = ccall((:kmc_kmer_table_export, LIB[]), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt32, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Ptr{UInt64}),
+                ctx.handle, dk[], dv[], UInt32(log2_capacity), ok[], ov[], n, nout)
+            if st == KMC_OK && n > 0
+                ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, keys, ok[], 8 * n)
+                ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64), ctx.handle, vals, ov[], 4 * n)
+            end
+            device_free(ctx, ok[])
+            device_free(ctx, ov[])
+        end
+        device_free(ctx, dk[])
+        device_free(ctx, dv[])
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    kmers = reinterpret(T, keys)               # Kmer{A,K,1} is one UInt64 limb
+    return Dict{T, Int}(kmers[i] => Int(vals[i]) for i in eachindex(vals))
+end
+
+"""
+    bucket_count(CanonicalKmers{A,K}(seq), bits) -> Vector{UInt32}   (length 2^bits)
+
+`table[fx_hash(canonical k-mer) >> (64 - bits) + 1] += 1` for every window (`kmc_bucket_count`; the count table of
+the multi-GPU configuration, whose per-GPU tables a caller sums with its own collective).
+"""
+function bucket_count(it::CanonicalKmers{A, K}, bits::Integer;
+        ctx::Context = default_context()) where {A <: NucleicAcidAlphabet{2}, K}
+    table = zeros(UInt32, 1 << bits)
+    res = KmcResult()
+    with_device_sequence(ctx, source(it)) do d
+        dt = Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:kmc_malloc, LIB[]), Int32, (Ptr{Cvoid}, UInt64, Ptr{Ptr{Cvoid}}), ctx.handle, sizeof(table), dt)
+        ccall((:kmc_memset, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, UInt64), ctx.handle, dt[], 0, sizeof(table))
+        st = ccall((:kmc_bucket_count, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, Ptr{Cvoid}, Ref{KmcResult}),
+            ctx.handle, d, K, bits, dt[], res)
+        st == KMC_OK && ccall((:kmc_download, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64),
+            ctx.handle, table, dt[], sizeof(table))
+        device_free(ctx, dt[])
+        st == KMC_OK || throw_status(ctx, st, res, A)
+    end
+    return table
 end
 
 end # module

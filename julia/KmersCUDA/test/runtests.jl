@@ -24,3 +24,14 @@ end
     @test KmersCUDA.fx_hash_device(v) == fx_hash.(v)
     @test KmersCUDA.fx_hash_device([mer"TAGCTAG"d])[1] == 0xa76409341339d05a   # test/runtests.jl:907
 end
+
+@testset "count_kmers == Dict loop" begin
+    s = LongDNA{2}(randdnaseq(RNG, 5_000))
+    want = Dict{eltype(CanonicalDNAMers{11}(s)), Int}()
+    for m in CanonicalDNAMers{11}(s)
+        want[m] = get(want, m, 0) + 1
+    end
+    @test KmersCUDA.count_kmers(CanonicalDNAMers{11}(s)) == want
+    t = KmersCUDA.bucket_count(CanonicalDNAMers{11}(s), 12)
+    @test sum(t) == length(s) - 10
+end
