@@ -35,6 +35,13 @@ struct CompactParams {
 #define KMC_COMPACT_MIN_BLOCKS 5
 #endif
 
+// EXPERIMENT, off by default and not measured yet: the burst prefetch of extract_kernel for
+// this kernel's two sources -- the recoded 2-bit stream and the valid-start bits.  Build a variant with
+// EXTRA=-DKMC_COMPACT_PREFETCH=1 and compare it with ab/ab_modes.sh before switching it on.
+#ifndef KMC_COMPACT_PREFETCH
+#define KMC_COMPACT_PREFETCH 0
+#endif
+
 constexpr uint64_t kTileAggregate = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1;
 constexpr int kWarpsPerBlock = kBlockThreads / 32;
 
@@ -125,6 +132,25 @@ __global__ void __launch_bounds__(kBlockThreads, KMC_COMPACT_MIN_BLOCKS) compact
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t *stage = s_stage_all + static_cast<size_t>(warp) * stage_words(N);
     const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
+#if KMC_COMPACT_PREFETCH
+    if (p.pf_tiles) {
+        burst_prefetch<RAGGED, G, 2>(p, p.items);
+        // the valid-start bits of the same symbols: one bit per symbol, so byte = (stream bit / 2) / 8
+        const uint32_t T = p.pf_tiles, c = blockIdx.x / T, k = blockIdx.x - c * T;
+        const uint32_t lead = kPfLead < T ? kPfLead : T, k0 = T - lead;
+        const bool first = blockIdx.x < kPfBlocks;
+        if (first || (k >= k0 && k < k0 + kPfBlocks)) {
+            const uint64_t cc = first ? 0 : c + 1, kk = first ? blockIdx.x : k - k0;
+            const int64_t b0 = (tile_start_bit<RAGGED, G, 2>(p, cc * T, p.items) >> 4) & ~127ll;
+            int64_t b1 = (tile_start_bit<RAGGED, G, 2>(p, (cc + 1) * T, p.items) >> 4) + 256;
+            if (b1 > p.nw32 * 2) b1 = p.nw32 * 2; // the bit array covers the stream's nw32 * 16 symbols = nw32 * 2 bytes
+            const char *vb = reinterpret_cast<const char *>(p.vstart);
+            for (int64_t o = b0 + (static_cast<int64_t>(kk) * kBlockThreads + threadIdx.x) * 128; o < b1;
+                 o += static_cast<int64_t>(kPfBlocks) * kBlockThreads * 128)
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(vb + o));
+        }
+    }
+#endif
     TileCursor<RAGGED, G> cur;
     cur.init(p, tile_base, sh, threadIdx.x);
     const TileCursor<RAGGED, G> cur0 = cur;
@@ -278,6 +304,14 @@ cudaError_t launch_compact(ExtractParams p, CompactParams cp, cudaStream_t strea
     if (tiles == 0) return cudaSuccess;
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     set_iteration_strides(p);
+    p.pf_tiles = 0;
+#if KMC_COMPACT_PREFETCH
+    if (prefetch_enabled()) {
+        const uint64_t per_tile = static_cast<uint64_t>(p.nw32) * 4 / tiles + 1;
+        const uint64_t t = kPfChunkBytes / per_tile;
+        p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
+    }
+#endif
     constexpr size_t smem = static_cast<size_t>(kWarpsPerBlock) * stage_words(N) * sizeof(uint64_t);
     // (set on every launch: the attribute belongs to the function on the CURRENT device, and a process may hold
     // contexts on several devices; the call costs a few microseconds)
