@@ -39,6 +39,28 @@ constexpr uint64_t FX_CONSTANT = 0x517cc1b727220a95ull; // src/kmer.jl:218
 #endif
 constexpr int group_of(int n) { return n == 1 ? KMC_GROUP_1 : n == 2 ? KMC_GROUP_2 : n == 3 ? KMC_GROUP_3 : KMC_GROUP_4; }
 
+// The shape of a work item for K symbols of bps bits: limbs, windows per item, 32-bit words per block, and the
+// two constants block_kmers needs.  Plain host code (the launch planner, plan.h) -- here so that the CPU test of
+// these primitives (tests/host_core) takes the geometry from the same place as the kernels' launchers.
+struct Geometry {
+    int n_limbs, g, nx;
+    uint32_t s0;
+    uint64_t head_mask;
+};
+
+// src/kmer.jl:117-137 (N = cld(K * bps, 64)) and :603-605 (get_mask); bps = bits per symbol of the k-mer alphabet
+inline Geometry geometry(int k, int bps = 2)
+{
+    Geometry ge;
+    ge.n_limbs = (bps * k + 63) / 64;
+    ge.g = group_of(ge.n_limbs);
+    ge.nx = (bps * k + bps * ge.g - bps + 31) / 32;
+    ge.s0 = static_cast<uint32_t>(32 * ge.nx - bps * k - bps * (ge.g - 1));
+    int used = bps * k - 64 * (ge.n_limbs - 1); // bits used in the head limb, bps..64
+    ge.head_mask = used >= 64 ? ~0ull : ((1ull << used) - 1);
+    return ge;
+}
+
 // reversebits(x, BitsPerSymbol{2}) on a 32-bit word: reverse the order of the 16 two-bit groups.
 KMC_DEV uint32_t rev2_32(uint32_t x)
 {

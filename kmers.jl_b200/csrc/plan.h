@@ -18,24 +18,7 @@ int32_t fail(kmc_ctx *ctx, int32_t code, const char *msg);
         if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
     } while (0)
 
-struct Geometry {
-    int n_limbs, g, nx;
-    uint32_t s0;
-    uint64_t head_mask;
-};
-
-// src/kmer.jl:117-137 (N = cld(K * bps, 64)) and :603-605 (get_mask); bps = bits per symbol of the k-mer alphabet
-inline Geometry geometry(int k, int bps = 2)
-{
-    Geometry ge;
-    ge.n_limbs = (bps * k + 63) / 64;
-    ge.g = group_of(ge.n_limbs);
-    ge.nx = (bps * k + bps * ge.g - bps + 31) / 32;
-    ge.s0 = static_cast<uint32_t>(32 * ge.nx - bps * k - bps * (ge.g - 1));
-    int used = bps * k - 64 * (ge.n_limbs - 1); // bits used in the head limb, bps..64
-    ge.head_mask = used >= 64 ? ~0ull : ((1ull << used) - 1);
-    return ge;
-}
+// (Geometry / geometry(): kmer_core.cuh)
 
 inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 

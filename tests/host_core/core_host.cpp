@@ -1,0 +1,100 @@
+// core_host.cpp -- TEST INFRASTRUCTURE: kmers.jl_b200/csrc/kmer_core.cuh compiled for the host, so that the bit logic of
+// the device primitives (block load and alignment, block_kmers, limbs_less, fx_hash) can be checked against the
+// oracle without a GPU.  The CUDA intrinsics the header uses are given portable definitions here; nothing in the
+// product links or calls this file (the library has no CPU path).
+#include <cstdint>
+
+#define __device__
+#define __forceinline__ inline __attribute__((always_inline))
+
+static inline uint32_t __brev(uint32_t x)
+{
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+}
+// PRMT, default mode: byte i of the result is byte (selector nibble i) of the 8 bytes {b, a}
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s)
+{
+    const uint64_t v = (static_cast<uint64_t>(b) << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= static_cast<uint32_t>((v >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
+// SHF.R.WRAP: the low 32 bits of {hi, lo} >> (s & 31)
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s)
+{
+    s &= 31u;
+    return s ? (lo >> s) | (hi << (32u - s)) : lo;
+}
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+
+#include "../../kmers.jl_b200/csrc/kmer_core.cuh"
+
+namespace {
+
+using namespace kmc;
+
+template <int N, int NX, int BPS>
+void windows(const uint32_t *w32, int64_t nw32, int64_t bit, const Geometry &ge, uint64_t *fw, uint64_t *rv, uint64_t *canon,
+             uint64_t *hash)
+{
+    constexpr int G = group_of(N);
+    uint32_t x[NX];
+    load_block<NX>(w32, nw32, bit, x);
+    uint64_t f[G][N], r[G][N];
+    block_kmers<N, NX, G, true, true, BPS>(x, ge.s0, ge.head_mask, f, r);
+    for (int j = 0; j < G; ++j) {
+        const bool take_fw = limbs_less<N>(f[j], r[j]);
+        uint64_t a[N];
+        for (int i = 0; i < N; ++i) {
+            fw[j * N + i] = f[j][i];
+            rv[j * N + i] = r[j][i];
+            a[i] = take_fw ? f[j][i] : r[j][i];
+            canon[j * N + i] = a[i];
+        }
+        hash[j] = fx_hash<N>(a, 0);
+    }
+}
+
+template <int N, int BPS>
+int dispatch_nx(const uint32_t *w32, int64_t nw32, int64_t bit, const Geometry &ge, uint64_t *fw, uint64_t *rv, uint64_t *canon,
+                uint64_t *hash)
+{
+    constexpr int G = group_of(N);
+    constexpr int NXMAX = (64 * N + BPS * G - BPS + 31) / 32; // the launcher tables' range: NXMAX - 2 .. NXMAX
+    if (ge.nx == NXMAX) return windows<N, NXMAX, BPS>(w32, nw32, bit, ge, fw, rv, canon, hash), 0;
+    if (ge.nx == NXMAX - 1) return windows<N, (NXMAX - 1 > 0 ? NXMAX - 1 : 1), BPS>(w32, nw32, bit, ge, fw, rv, canon, hash), 0;
+    if (ge.nx == NXMAX - 2) return windows<N, (NXMAX - 2 > 0 ? NXMAX - 2 : 1), BPS>(w32, nw32, bit, ge, fw, rv, canon, hash), 0;
+    if (ge.nx == NXMAX - 3) return windows<N, (NXMAX - 3 > 0 ? NXMAX - 3 : 1), BPS>(w32, nw32, bit, ge, fw, rv, canon, hash), 0;
+    return -1;
+}
+
+template <int BPS>
+int dispatch_n(const uint32_t *w32, int64_t nw32, int64_t bit, const Geometry &ge, uint64_t *fw, uint64_t *rv, uint64_t *canon,
+               uint64_t *hash)
+{
+    switch (ge.n_limbs) {
+    case 1: return dispatch_nx<1, BPS>(w32, nw32, bit, ge, fw, rv, canon, hash);
+    case 2: return dispatch_nx<2, BPS>(w32, nw32, bit, ge, fw, rv, canon, hash);
+    case 3: return dispatch_nx<3, BPS>(w32, nw32, bit, ge, fw, rv, canon, hash);
+    case 4: return dispatch_nx<4, BPS>(w32, nw32, bit, ge, fw, rv, canon, hash);
+    }
+    return -1;
+}
+
+} // namespace
+
+// The G windows of the work item whose first window starts at stream bit `bit` (bps * symbol index), exactly as a
+// kernel thread computes them: fw / rv / canon are [G][N] limbs (head first), hash is [G].  Returns G, or -1.
+extern "C" int core_item_windows(const uint32_t *w32, int64_t nw32, int64_t bit, int k, int bps, uint64_t *fw, uint64_t *rv,
+                                 uint64_t *canon, uint64_t *hash, int *n_limbs)
+{
+    const kmc::Geometry ge = kmc::geometry(k, bps);
+    *n_limbs = ge.n_limbs;
+    const int rc = bps == 2 ? dispatch_n<2>(w32, nw32, bit, ge, fw, rv, canon, hash)
+                            : dispatch_n<4>(w32, nw32, bit, ge, fw, rv, canon, hash);
+    return rc < 0 ? rc : ge.g;
+}

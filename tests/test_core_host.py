@@ -1,0 +1,95 @@
+"""CPU check of the device primitives themselves: kmers.jl_b200/csrc/kmer_core.cuh (block load and alignment,
+block_kmers, limbs_less, fx_hash) compiled for the host with portable definitions of the CUDA intrinsics
+(tests/host_core/core_host.cpp) and compared, work item by work item, with the oracle -- the same closed form the
+kernels run, for every (limbs, block width) class of the launcher tables and both k-mer alphabets.  Test
+infrastructure only: the library has no CPU path and nothing in it links this code."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import kmertools as kt
+from oracle import oracle as ko
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def core(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    so = str(tmp_path_factory.mktemp("core_host") / "libcore_host.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-o", so,
+                    os.path.join(ROOT, "tests", "host_core", "core_host.cpp")], check=True)
+    lib = C.CDLL(so)
+    lib.core_item_windows.restype = C.c_int
+    lib.core_item_windows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.POINTER(C.c_int)]
+    return lib
+
+
+def item(core, words, bit, k, bps):
+    """(G, fw[G][N], rv[G][N], canon[G][N], hash[G]) of the work item starting at stream bit `bit`."""
+    w32 = np.ascontiguousarray(words).view(np.uint32)
+    fw, rv, ca = (np.zeros(8 * 4, dtype=np.uint64) for _ in range(3))
+    h = np.zeros(8, dtype=np.uint64)
+    n = C.c_int(0)
+    g = core.core_item_windows(w32.ctypes.data, w32.size, bit, k, bps, fw.ctypes.data, rv.ctypes.data, ca.ctypes.data,
+                               h.ctypes.data, C.byref(n))
+    assert g > 0, f"no instantiation for K={k}, bps={bps}"
+    N = n.value
+    return g, fw[:g * N].reshape(g, N), rv[:g * N].reshape(g, N), ca[:g * N].reshape(g, N), h[:g]
+
+
+def starts(rng, n_windows):
+    fixed = [0, 1, 2, 7, 15, 16, 17, 31, 32, 33, 63, 64, 65]
+    return sorted({p for p in fixed if p < n_windows} | {int(p) for p in rng.integers(0, max(n_windows, 1), size=24)})
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 15, 16, 17, 29, 31, 32, 33, 47, 48, 49, 63, 64, 65, 80, 95, 96, 97, 112, 127, 128])
+def test_two_bit_items_match_the_oracle(core, k):
+    rng = np.random.default_rng(1000 + k)
+    n = 700
+    words = rng.integers(0, 2**64, size=(n + 31) // 32 + 1, dtype=np.uint64)
+    fw, rv, _ = ko.iterate(words, n, k, ko.FWRV)
+    ca, _, h = ko.iterate(words, n, k, ko.CANON, want_hash=True)
+    nwin = n - k + 1
+    for p in starts(rng, nwin):
+        g, f, r, c, hh = item(core, words, 2 * p, k, 2)
+        m = min(g, nwin - p)
+        assert np.array_equal(f[:m], fw[p:p + m]) and np.array_equal(r[:m], rv[p:p + m]), (k, p)
+        assert np.array_equal(c[:m], ca[p:p + m]) and np.array_equal(hh[:m], h[p:p + m]), (k, p)
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 15, 16, 17, 24, 31, 32, 33, 40, 47, 48, 49, 63, 64])
+def test_four_bit_alphabet_items_match_the_oracle(core, k):
+    """Kmer{DNAAlphabet{4}}: rev4 / comp4 (any IUPAC symbol, N and gap are legal symbols of the k-mer)."""
+    rng = np.random.default_rng(2000 + k)
+    n = 400
+    codes = rng.integers(0, 16, size=n).astype(np.uint64)
+    words = np.concatenate([kt.pack_codes(codes, 4), np.zeros(1, dtype=np.uint64)])
+    fw, rv, _ = ko.iterate4(words, n, k, ko.FWRV)
+    ca, _, h = ko.iterate4(words, n, k, ko.CANON, want_hash=True)
+    nwin = n - k + 1
+    for p in starts(rng, nwin):
+        g, f, r, c, hh = item(core, words, 4 * p, k, 4)
+        m = min(g, nwin - p)
+        assert np.array_equal(f[:m], fw[p:p + m]) and np.array_equal(r[:m], rv[p:p + m]), (k, p)
+        assert np.array_equal(c[:m], ca[p:p + m]) and np.array_equal(hh[:m], h[p:p + m]), (k, p)
+
+
+def test_loads_near_the_ends_of_the_buffer_are_clamped(core):
+    """Items whose block reaches past the last word (or starts before the first) read clamped words; the windows
+    that exist are still exact."""
+    rng = np.random.default_rng(5)
+    k, n = 31, 64
+    words = rng.integers(0, 2**64, size=2, dtype=np.uint64)  # exactly the 64 symbols, no slack word
+    fw, rv, _ = ko.iterate(words, n, k, ko.FWRV)
+    nwin = n - k + 1
+    for p in range(nwin - 9, nwin):
+        g, f, r, _, _ = item(core, words, 2 * p, k, 2)
+        m = min(g, nwin - p)
+        assert np.array_equal(f[:m], fw[p:p + m]) and np.array_equal(r[:m], rv[p:p + m]), p
