@@ -11,39 +11,7 @@ namespace {
 constexpr uint64_t kNone = ~0ull;
 constexpr int kCountLayoutG = 32; // windows per work item when the survivors are only counted (valid_count.cu)
 
-// ---- bit-parallel recoding of one LongSequence{<:NucleicAcidAlphabet{4}} word (16 nibbles) ------
-// Everything is done on 32-bit halves (8 nibbles): the integer pipe is 32 bits wide, a 64-bit
-// formulation costs two instructions per operation.
-//   2-bit code of a one-hot nibble = trailing_zeros (A=1,C=2,G=4,T=8 -> 0,1,2,3;
-//   construction_utils.jl:51): bit0 = x1|x3, bit1 = x2|x3.
-//   flag <=> the nibble is not one-hot (count_ones(enc) != 1: the reference's uncertainty test,
-//   FwKmers.jl:112, UnambiguousKmers.jl:145; covers IUPAC ambiguity codes, N and gap): with the four
-//   bit planes a..d aligned at bit 0 of each nibble, exactly one is set iff
-//   ((a^b) ^ (c^d)) & ~(a&b) & ~(c&d).
-__device__ __forceinline__ void recode_half(uint32_t x, uint32_t &codes16, uint32_t &flags8)
-{
-    const uint32_t M = 0x11111111u;
-    const uint32_t t1 = x >> 1, t2 = x >> 2, t3 = x >> 3;
-    uint32_t c = ((t1 | t3) & M) | (((t2 | t3) & M) << 1); // nibble i holds its code in its low 2 bits
-    c = (c | (c >> 2)) & 0x0f0f0f0fu;
-    c = (c | (c >> 4)) & 0x00ff00ffu;
-    codes16 = __byte_perm(c, 0u, 0x4420); // bytes 0 and 2
-    const uint32_t one = ((x ^ t1) ^ (t2 ^ t3)) & ~(x & t1) & ~(t2 & t3);
-    uint32_t n = ~one & M;
-    n = (n | (n >> 3)) & 0x03030303u;
-    n = (n | (n >> 6)) & 0x000f000fu;
-    flags8 = (n | (n >> 12)) & 0xffu;
-}
-
-// one source word: 32 bits of 2-bit codes, 16 flags
-__device__ __forceinline__ void recode_word(uint64_t w, uint32_t &codes, uint32_t &flags)
-{
-    uint32_t c0, c1, f0, f1;
-    recode_half(static_cast<uint32_t>(w), c0, f0);
-    recode_half(static_cast<uint32_t>(w >> 32), c1, f1);
-    codes = c0 | (c1 << 16);
-    flags = f0 | (f1 << 8);
-}
+// (recode_word: fourbit_core.cuh)
 
 // One thread per PAIR of source words (= one group of 32 symbols): 2 x u32 of 2-bit codes, 1 x u32 of
 // uncertainty flags -- and, fused, the group's valid-start word: the block keeps its 256 flag words

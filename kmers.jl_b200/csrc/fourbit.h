@@ -15,6 +15,7 @@
 //     compacts the survivors in order, each k-mer with its 1-based start inside its read, in a
 //     single pass (decoupled look-back over the tiles; aligned 256-bit stores from a staging buffer).
 #pragma once
+#include "fourbit_core.cuh"
 #include "plan.h"
 
 namespace kmc {
@@ -46,57 +47,7 @@ struct FourBitState {
 // valid_count.cu: *total += survivors of the set laid out in groups of g windows (g = 2, 4, 8 or 32)
 cudaError_t count_valid(const ExtractParams &p, bool ragged, int g, unsigned long long *total, cudaStream_t stream);
 
-// Valid-start bits of one group of 32 symbols from the flag words a[0..4] of this and the next four
-// groups (a[5] = 0): bit t set <=> no flagged symbol in [t, t + K).  Sliding-window OR of length K by
-// doubling -- A_1 = flags, A_2L = A_L | A_L >> L while 2L <= K, then two windows of length L cover
-// [P, P+K): A_L | A_L >> (K - L).  Branch-free in the data (K is uniform).  Only the first
-// NW = (30 + K) / 32 + 1 words can reach the result (a window starting at bit 31 ends at bit 30 + K), so
-// the doubling runs on NW words: 2 for K <= 33 instead of 5.
-template <int NW>
-__device__ __forceinline__ uint32_t valid_start_word_n(const uint32_t (&a6)[6], int k)
-{
-    uint32_t a[NW + 1];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) a[w] = a6[w];
-    a[NW] = 0;
-    int L = 1;
-#pragma unroll
-    for (int step = 0; step < 7; ++step) {
-        const int s = 1 << step; // current window length
-        if (2 * s <= k) {
-            if (s < 32) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) a[w] |= __funnelshift_r(a[w], a[w + 1], s);
-            } else if (s == 32) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) a[w] |= a[w + 1];
-            } else {
-#pragma unroll
-                for (int w = 0; w + 1 < NW; ++w) a[w] |= a[w + 2 <= NW ? w + 2 : NW];
-            }
-            L = 2 * s;
-        }
-    }
-    const int r = k - L; // 0 <= r < L, r < 64
-    uint32_t v = a[0];
-    if (r) {
-        const int b = r & 31;
-        if (r < 32) v |= __funnelshift_r(a[0], a[NW >= 1 ? 1 : 0], b);
-        else v |= b ? __funnelshift_r(a[1 <= NW ? 1 : NW], a[2 <= NW ? 2 : NW], b) : a[1 <= NW ? 1 : NW];
-    }
-    return ~v;
-}
-
-__device__ __forceinline__ uint32_t valid_start_word(const uint32_t (&a)[6], int k)
-{
-    switch ((30 + k) / 32) { // warp-uniform
-    case 0: return valid_start_word_n<1>(a, k);
-    case 1: return valid_start_word_n<2>(a, k);
-    case 2: return valid_start_word_n<3>(a, k);
-    case 3: return valid_start_word_n<4>(a, k);
-    }
-    return valid_start_word_n<5>(a, k);
-}
+// (valid_start_word: fourbit_core.cuh)
 constexpr int kRecodeHalo = 5; // flag words beyond a group that its windows can reach (31 + K - 1 <= 158 bits)
 
 // ascii.cu: byte sources (AsciiEncode).  lut: 0 = strict DNAAlphabet{2}, 1 = strict RNAAlphabet{2},

@@ -31,6 +31,7 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s)
 }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 
+#include "../../kmers.jl_b200/csrc/fourbit_core.cuh"
 #include "../../kmers.jl_b200/csrc/kmer_core.cuh"
 
 namespace {
@@ -97,4 +98,15 @@ extern "C" int core_item_windows(const uint32_t *w32, int64_t nw32, int64_t bit,
     const int rc = bps == 2 ? dispatch_n<2>(w32, nw32, bit, ge, fw, rv, canon, hash)
                             : dispatch_n<4>(w32, nw32, bit, ge, fw, rv, canon, hash);
     return rc < 0 ? rc : ge.g;
+}
+
+// FourToTwo primitives (fourbit_core.cuh): one source word of 16 nibbles -> 32 bits of 2-bit codes + 16 flags
+extern "C" void core_recode_word(uint64_t w, uint32_t *codes, uint32_t *flags) { kmc::recode_word(w, *codes, *flags); }
+
+// valid-start bits of one group of 32 symbols from the flag words of this and the next four groups (a[5] = 0)
+extern "C" uint32_t core_valid_start_word(const uint32_t *a, int k)
+{
+    uint32_t b[6];
+    for (int i = 0; i < 6; ++i) b[i] = a[i];
+    return kmc::valid_start_word(b, k);
 }

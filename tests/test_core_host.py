@@ -28,6 +28,10 @@ def core(tmp_path_factory):
     lib.core_item_windows.restype = C.c_int
     lib.core_item_windows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.POINTER(C.c_int)]
+    lib.core_recode_word.restype = None
+    lib.core_recode_word.argtypes = [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.core_valid_start_word.restype = C.c_uint32
+    lib.core_valid_start_word.argtypes = [C.c_void_p, C.c_int]
     return lib
 
 
@@ -93,3 +97,42 @@ def test_loads_near_the_ends_of_the_buffer_are_clamped(core):
         g, f, r, _, _ = item(core, words, 2 * p, k, 2)
         m = min(g, nwin - p)
         assert np.array_equal(f[:m], fw[p:p + m]) and np.array_equal(r[:m], rv[p:p + m]), p
+
+
+def test_recode_word_is_trailing_zeros_and_the_uncertainty_flag(core):
+    """FourToTwo (construction_utils.jl:41-54): code = trailing_zeros(enc) for a one-hot nibble; flag <=>
+    count_ones(enc) != 1 (IUPAC sets, N = 15, gap = 0)."""
+    rng = np.random.default_rng(9)
+    words = [0, 2**64 - 1, 0x8421842184218421, 0x1248124812481248] + [int(x) for x in rng.integers(0, 2**64, size=2000, dtype=np.uint64)]
+    # half of the random words: only certain symbols, as real reads mostly are
+    words += [int(sum((1 << int(c)) << (4 * i) for i, c in enumerate(rng.integers(0, 4, size=16)))) for _ in range(500)]
+    for w in words:
+        codes, flags = C.c_uint32(0), C.c_uint32(0)
+        core.core_recode_word(w, C.byref(codes), C.byref(flags))
+        for i in range(16):
+            enc = (w >> (4 * i)) & 15
+            certain = bin(enc).count("1") == 1
+            assert ((flags.value >> i) & 1) == (0 if certain else 1), (hex(w), i)
+            if certain:
+                assert ((codes.value >> (2 * i)) & 3) == enc.bit_length() - 1, (hex(w), i)
+        assert flags.value >> 16 == 0
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 34, 47, 63, 64, 65, 66, 95, 96, 97, 98, 127, 128])
+def test_valid_start_word_is_the_sliding_window_of_the_flags(core, k):
+    """bit t set <=> none of the symbols [t, t + K) is flagged (UnambiguousKmers.jl:134-148: every symbol of an
+    emitted k-mer is certain), for every class of the word-count specialisation."""
+    rng = np.random.default_rng(300 + k)
+    for density in (0.0, 0.01, 0.05, 0.3, 1.0):
+        for _ in range(40):
+            bits = (rng.random(160) < density).astype(np.uint8)
+            a = np.zeros(6, dtype=np.uint32)
+            for i in range(160):
+                if bits[i]:
+                    a[i // 32] |= np.uint32(1) << np.uint32(i % 32)
+            got = core.core_valid_start_word(a.ctypes.data, k)
+            want = 0
+            for t in range(32):
+                if not bits[t:t + k].any():
+                    want |= 1 << t
+            assert got == want, (k, density, [hex(int(x)) for x in a])
