@@ -209,6 +209,24 @@ KMC_DEV void store_words(uint64_t *p, const uint64_t (&v)[CNT], int lo, int hi, 
     }
 }
 
+// Base.hash(x::Kmer, h) = hash(x.data, h ⊻ K) (src/kmer.jl:206) with the tuple / UInt64 hashing of Julia 1.10 and
+// 1.11 (misc_kernels.cu: base_hash_kernel folds the limbs from the last to the first):
+//   hash(::Tuple{}, h) = h + 0x77cfa1eef01bca90 ; hash(t::Tuple, h) = hash(t[1], hash(tail(t), h))   (tuple.jl)
+//   hash(x::UInt64, h) = hash_64_64(x) - 3h                                                          (hashing.jl)
+KMC_DEV uint64_t hash_64_64(uint64_t a)
+{
+    a = ~a + (a << 21);
+    a = a ^ (a >> 24);
+    a = a + (a << 3) + (a << 8);
+    a = a ^ (a >> 14);
+    a = a + (a << 2) + (a << 4);
+    a = a ^ (a >> 28);
+    a = a + (a << 31);
+    return a;
+}
+KMC_DEV uint64_t base_hash_seed(uint64_t h) { return h + 0x77cfa1eef01bca90ull; }
+KMC_DEV uint64_t base_hash_fold(uint64_t limb, uint64_t acc) { return hash_64_64(limb) - 3 * acc; }
+
 // ---- the window block ----------------------------------------------------------------------
 // Loads NX+1 words at 32-bit word index floor(bit/32) (clamped into [0, nw32) so that slots
 // outside the sequence buffer never fault; such bits only ever feed windows that are not

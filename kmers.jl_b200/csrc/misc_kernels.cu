@@ -48,17 +48,7 @@ cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint6
 // Pinned by the reference's documented value hash(mer"UGCUGUAC"r) == 0xe5057d38c8907b22
 // (docs/src/hashing.md:18-20).  Julia >= 1.12 hashes integers differently; the Julia binding checks
 // that value at load time before it trusts this kernel.
-__device__ __forceinline__ uint64_t hash_64_64(uint64_t a)
-{
-    a = ~a + (a << 21);
-    a = a ^ (a >> 24);
-    a = a + (a << 3) + (a << 8);
-    a = a ^ (a >> 14);
-    a = a + (a << 2) + (a << 4);
-    a = a ^ (a >> 28);
-    a = a + (a << 31);
-    return a;
-}
+// (hash_64_64, base_hash_seed, base_hash_fold: kmer_core.cuh)
 
 template <int N>
 __global__ void __launch_bounds__(256) base_hash_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t h,
@@ -66,9 +56,9 @@ __global__ void __launch_bounds__(256) base_hash_kernel(const uint64_t *__restri
 {
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t acc = h + 0x77cfa1eef01bca90ull; // the empty tail
+        uint64_t acc = base_hash_seed(h); // the empty tail
 #pragma unroll
-        for (int j = N - 1; j >= 0; --j) acc = hash_64_64(__ldg(kmers + i * N + j)) - 3 * acc;
+        for (int j = N - 1; j >= 0; --j) acc = base_hash_fold(__ldg(kmers + i * N + j), acc);
         st_u64(out + i, acc);
     }
 }

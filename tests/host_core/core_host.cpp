@@ -110,3 +110,24 @@ extern "C" uint32_t core_valid_start_word(const uint32_t *a, int k)
     for (int i = 0; i < 6; ++i) b[i] = a[i];
     return kmc::valid_start_word(b, k);
 }
+
+// Base.hash of one k-mer (n limbs, head first) with h already xor-ed with K, as base_hash_kernel folds it
+extern "C" uint64_t core_base_hash(const uint64_t *limbs, int n, uint64_t h)
+{
+    uint64_t acc = kmc::base_hash_seed(h);
+    for (int j = n - 1; j >= 0; --j) acc = kmc::base_hash_fold(limbs[j], acc);
+    return acc;
+}
+
+// fx_hash of one k-mer (n limbs, head first), src/kmer.jl:255-261
+extern "C" uint64_t core_fx_hash(const uint64_t *limbs, int n, uint64_t h)
+{
+    switch (n) {
+    case 0: return h;
+    case 1: return kmc::fx_hash<1>(*reinterpret_cast<const uint64_t(*)[1]>(limbs), h);
+    case 2: return kmc::fx_hash<2>(*reinterpret_cast<const uint64_t(*)[2]>(limbs), h);
+    case 3: return kmc::fx_hash<3>(*reinterpret_cast<const uint64_t(*)[3]>(limbs), h);
+    case 4: return kmc::fx_hash<4>(*reinterpret_cast<const uint64_t(*)[4]>(limbs), h);
+    }
+    return 0;
+}

@@ -32,6 +32,9 @@ def core(tmp_path_factory):
     lib.core_recode_word.argtypes = [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.core_valid_start_word.restype = C.c_uint32
     lib.core_valid_start_word.argtypes = [C.c_void_p, C.c_int]
+    for f in (lib.core_base_hash, lib.core_fx_hash):
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     return lib
 
 
@@ -136,3 +139,27 @@ def test_valid_start_word_is_the_sliding_window_of_the_flags(core, k):
                 if not bits[t:t + k].any():
                     want |= 1 << t
             assert got == want, (k, density, [hex(int(x)) for x in a])
+
+
+def test_hash_primitives_reproduce_the_reference_values(core):
+    """fx_hash (src/kmer.jl:255-261) and Base.hash (src/kmer.jl:206, Julia 1.10 / 1.11) as the device code computes
+    them: the reference's known answers (test/runtests.jl:903-910, docs/src/hashing.md:18-20) and the oracle."""
+    import json
+    kats = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kats.json")))
+    for e in kats["fx_hash"]:
+        limbs = [int(x, 16) for x in e["limbs"]] if "limbs" in e else (kt.kmer_limbs(e["kmer"].replace("U", "T")) if e["kmer"] else [])
+        a = np.array(limbs, dtype=np.uint64)
+        assert core.core_fx_hash(a.ctypes.data if a.size else None, a.size, 0) == int(e["hash"], 16), e
+    for e in kats["base_hash"]:
+        s = e["kmer"].replace("U", "T")
+        a = np.array(kt.kmer_limbs(s), dtype=np.uint64)
+        assert core.core_base_hash(a.ctypes.data, a.size, 0 ^ len(s)) == int(e["hash"], 16), e
+    rng = np.random.default_rng(77)
+    for n, k in ((1, 31), (2, 63), (3, 90), (4, 128)):
+        km = rng.integers(0, 2**64, size=(50, n), dtype=np.uint64)
+        for h0 in (0, 0x1234_5678_9ABC_DEF0):
+            want_fx, want_b = ko.fx_hash(km, h0), ko.base_hash(km, k, h0)
+            for i in range(km.shape[0]):
+                row = np.ascontiguousarray(km[i])
+                assert core.core_fx_hash(row.ctypes.data, n, h0) == int(want_fx[i])
+                assert core.core_base_hash(row.ctypes.data, n, h0 ^ k) == int(want_b[i])
