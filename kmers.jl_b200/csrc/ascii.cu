@@ -12,39 +12,14 @@
 //   UnambiguousKmers (UnambiguousKmers.jl:109-132): ASCII_SKIPPING_LUT (iterators/common.jl:22-32):
 //     Aa Cc Gg TtUu -> 0..3 for both alphabets, "-MRSVWYHKDBN" in either case -> skip and
 //     restart, every other byte -> EncodeError.
+#include "ascii_luts.h"
 #include "fourbit.h"
 
 namespace kmc {
 
 namespace {
 
-// LUT entry: bits 0-1 = 2-bit code, bit 6 = skip (ambiguity code / gap), bit 7 = error
-constexpr uint8_t kSkip = 0x40, kErr = 0x80;
-
-struct AsciiLuts {
-    uint8_t strict_dna[256], strict_rna[256], skipping[256];
-};
-
-AsciiLuts make_luts()
-{
-    AsciiLuts l;
-    for (int i = 0; i < 256; ++i) l.strict_dna[i] = l.strict_rna[i] = l.skipping[i] = kErr;
-    const char *dna = "ACGT", *rna = "ACGU";
-    for (int c = 0; c < 4; ++c) {
-        l.strict_dna[static_cast<uint8_t>(dna[c])] = l.strict_dna[static_cast<uint8_t>(dna[c] | 0x20)] = static_cast<uint8_t>(c);
-        l.strict_rna[static_cast<uint8_t>(rna[c])] = l.strict_rna[static_cast<uint8_t>(rna[c] | 0x20)] = static_cast<uint8_t>(c);
-    }
-    // iterators/common.jl:22-32
-    const char *codes[4] = {"Aa", "cC", "gG", "TtUu"};
-    for (int c = 0; c < 4; ++c)
-        for (const char *q = codes[c]; *q; ++q) l.skipping[static_cast<uint8_t>(*q)] = static_cast<uint8_t>(c);
-    for (const char *q = "-MRSVWYHKDBN"; *q; ++q) {
-        l.skipping[static_cast<uint8_t>(*q)] = kSkip;
-        const char lower = (*q >= 'A' && *q <= 'Z') ? static_cast<char>(*q | 0x20) : *q; // lowercase('-') == '-'
-        l.skipping[static_cast<uint8_t>(lower)] = kSkip;
-    }
-    return l;
-}
+// (LUT entry format, AsciiLuts, make_luts: ascii_luts.h)
 
 __constant__ uint8_t c_luts[3][256];
 

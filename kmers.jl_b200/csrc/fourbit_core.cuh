@@ -92,4 +92,16 @@ __device__ __forceinline__ uint32_t valid_start_word(const uint32_t (&a)[6], int
     }
     return valid_start_word_n<5>(a, k);
 }
+// TwoToFour (src/construction_utils.jl:35: enc4 = 1 << enc2)
+// 8 two-bit codes (16 bits) -> 8 one-hot nibbles
+__device__ __forceinline__ uint32_t onehot8(uint32_t s)
+{
+    s = (s | (s << 8)) & 0x00ff00ffu;
+    s = (s | (s << 4)) & 0x0f0f0f0fu;
+    s = (s | (s << 2)) & 0x33333333u; // nibble i holds code i in its low 2 bits
+    const uint32_t M = 0x11111111u;
+    const uint32_t b0 = s & M, b1 = (s >> 1) & M;
+    return (~b1 & ~b0 & M) | ((~b1 & b0) << 1) | ((b1 & ~b0) << 2) | ((b1 & b0) << 3);
+}
+
 } // namespace kmc

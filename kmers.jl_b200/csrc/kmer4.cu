@@ -10,22 +10,14 @@
 //       of 128 bits).
 //
 // UnambiguousKmers only exists for 2-bit k-mers (UnambiguousKmers{A<:TwoBit}, UnambiguousKmers.jl:29).
+#include "fourbit_core.cuh"
 #include "plan.h"
 
 namespace kmc {
 
 namespace {
 
-// 8 two-bit codes (16 bits) -> 8 one-hot nibbles
-__device__ __forceinline__ uint32_t onehot8(uint32_t s)
-{
-    s = (s | (s << 8)) & 0x00ff00ffu;
-    s = (s | (s << 4)) & 0x0f0f0f0fu;
-    s = (s | (s << 2)) & 0x33333333u; // nibble i holds code i in its low 2 bits
-    const uint32_t M = 0x11111111u;
-    const uint32_t b0 = s & M, b1 = (s >> 1) & M;
-    return (~b1 & ~b0 & M) | ((~b1 & b0) << 1) | ((b1 & ~b0) << 2) | ((b1 & b0) << 3);
-}
+// (onehot8: fourbit_core.cuh)
 
 __global__ void __launch_bounds__(256) expand_kernel(const uint64_t *__restrict__ words, uint64_t n_words,
                                                      uint4 *__restrict__ out)

@@ -31,6 +31,7 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s)
 }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 
+#include "../../kmers.jl_b200/csrc/ascii_luts.h"
 #include "../../kmers.jl_b200/csrc/fourbit_core.cuh"
 #include "../../kmers.jl_b200/csrc/kmer_core.cuh"
 
@@ -130,4 +131,18 @@ extern "C" uint64_t core_fx_hash(const uint64_t *limbs, int n, uint64_t h)
     case 4: return kmc::fx_hash<4>(*reinterpret_cast<const uint64_t(*)[4]>(limbs), h);
     }
     return 0;
+}
+
+// TwoToFour: 8 two-bit codes (16 bits) -> 8 one-hot nibbles
+extern "C" uint32_t core_onehot8(uint32_t s) { return kmc::onehot8(s); }
+
+// the three byte tables of the ASCII sources: strict DNA, strict RNA, the UnambiguousKmers skipping table
+extern "C" void core_ascii_luts(uint8_t *out)
+{
+    const kmc::AsciiLuts l = kmc::make_luts();
+    for (int i = 0; i < 256; ++i) {
+        out[i] = l.strict_dna[i];
+        out[256 + i] = l.strict_rna[i];
+        out[512 + i] = l.skipping[i];
+    }
 }

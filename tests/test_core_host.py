@@ -32,6 +32,10 @@ def core(tmp_path_factory):
     lib.core_recode_word.argtypes = [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.core_valid_start_word.restype = C.c_uint32
     lib.core_valid_start_word.argtypes = [C.c_void_p, C.c_int]
+    lib.core_onehot8.restype = C.c_uint32
+    lib.core_onehot8.argtypes = [C.c_uint32]
+    lib.core_ascii_luts.restype = None
+    lib.core_ascii_luts.argtypes = [C.c_void_p]
     for f in (lib.core_base_hash, lib.core_fx_hash):
         f.restype = C.c_uint64
         f.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
@@ -163,3 +167,34 @@ def test_hash_primitives_reproduce_the_reference_values(core):
                 row = np.ascontiguousarray(km[i])
                 assert core.core_fx_hash(row.ctypes.data, n, h0) == int(want_fx[i])
                 assert core.core_base_hash(row.ctypes.data, n, h0 ^ k) == int(want_b[i])
+
+
+def test_two_to_four_expansion(core):
+    """TwoToFour (src/construction_utils.jl:35): enc4 = 1 << enc2, eight symbols at a time, every input."""
+    for s in range(1 << 16):
+        want = 0
+        for i in range(8):
+            want |= (1 << ((s >> (2 * i)) & 3)) << (4 * i)
+        assert core.core_onehot8(s) == want, hex(s)
+
+
+def test_ascii_tables_follow_the_reference(core):
+    """Strict tables: BioSequences' ascii_encode for the 2-bit alphabets (ACGT / ACGU, either case, anything else is an
+    error).  Skipping table: ASCII_SKIPPING_LUT (src/iterators/common.jl:22-32) -- Aa, Cc, Gg, TtUu are 0..3, the
+    ambiguity letters and the gap (either case) are skipped, every other byte is an error."""
+    out = np.zeros(768, dtype=np.uint8)
+    core.core_ascii_luts(out.ctypes.data)
+    dna, rna, skip = out[:256], out[256:512], out[512:]
+    SKIP, ERR = 0x40, 0x80
+    want_skip = {}
+    for code, letters in enumerate(("Aa", "cC", "gG", "TtUu")):
+        for ch in letters:
+            want_skip[ord(ch)] = code
+    for ch in "-MRSVWYHKDBN":
+        want_skip[ord(ch)] = SKIP
+        want_skip[ord(ch.lower())] = SKIP
+    for b in range(256):
+        assert skip[b] == want_skip.get(b, ERR), b
+        c = chr(b)
+        assert dna[b] == ("ACGT".index(c.upper()) if c.upper() in "ACGT" and c.isalpha() else ERR), b
+        assert rna[b] == ("ACGU".index(c.upper()) if c.upper() in "ACGU" and c.isalpha() else ERR), b
