@@ -48,6 +48,8 @@ extern "C" {
 #define KMC_E_OUT_TOO_SMALL 4 /* kmc_out.capacity < number of elements to write */
 #define KMC_E_NO_DEVICE 5
 #define KMC_E_UNSUPPORTED 6
+#define KMC_E_NCCL 7          /* a multi-GPU entry point failed inside NCCL, or NCCL could not be loaded
+                                 (libnccl.so.2 is bound at run time); kmc_last_error says which */
 
 /* iterator selected (kmc_extract `mode`) */
 #define KMC_FW 0      /* FwKmers{A,K}            src/iterators/FwKmers.jl:28-59,88-115      */
@@ -81,6 +83,8 @@ extern "C" {
                             chunk by chunk by a second kernel right behind the one that wrote the chunk. */
 
 typedef struct kmc_ctx kmc_ctx;
+typedef struct kmc_group kmc_group; /* one process driving several GPUs: a context per device + one NCCL communicator */
+#define KMC_COMM_ID_BYTES 128       /* size of the communicator id of kmc_comm_unique_id (an ncclUniqueId) */
 
 /* A set of sequences resident in device memory.  n_seqs == 1 is a single LongSequence.
  * Ragged sets give word-aligned CSR offsets; uniform sets (every read the same length,
@@ -130,6 +134,9 @@ int32_t kmc_ctx_destroy(kmc_ctx *ctx);
  * stream) instead of the context's own.  NULL restores the context's own stream. */
 int32_t kmc_ctx_set_stream(kmc_ctx *ctx, void *cuda_stream);
 int32_t kmc_sync(kmc_ctx *ctx);
+/* Stream-ordered temporaries (the binned counts take 8-16 bytes per k-mer) are cached in a memory pool the
+ * context owns; this gives the cached memory back to the device.  Synchronises. */
+int32_t kmc_trim(kmc_ctx *ctx);
 const char *kmc_last_error(kmc_ctx *ctx);
 const char *kmc_status_string(int32_t status);
 int32_t kmc_device_info(kmc_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, char *name, int32_t name_len);
@@ -177,8 +184,8 @@ int32_t kmc_base_hash(kmc_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t n
 
 /* north_star extension (not in the reference): histogram of
  * fx_hash(canonical k-mer) >> (64 - bucket_bits) over the set, accumulated into
- * table[2^bucket_bits] (u32, device, caller-zeroed).  Tables of several GPUs are summed
- * by the caller's collective (torch.distributed / NCCL all-reduce). */
+ * table[2^bucket_bits] (u32, device, caller-zeroed).  Tables of several GPUs are summed by
+ * kmc_bucket_count_merge / kmc_group_bucket_count below (NCCL all-reduce over NVLink). */
 int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
                          uint32_t *table, kmc_result *result);
 
@@ -239,6 +246,63 @@ int32_t kmc_kmer_table_merge(kmc_ctx *ctx, uint64_t *keys, uint32_t *vals, uint3
 /* The table's entries as two dense device arrays (unordered); *n_out = how many. */
 int32_t kmc_kmer_table_export(kmc_ctx *ctx, const uint64_t *keys, const uint32_t *vals, uint32_t log2_capacity,
                               uint64_t *out_keys, uint32_t *out_vals, uint64_t capacity, uint64_t *n_out);
+
+/* ---- multi-GPU ---------------------------------------------------------------
+ * The reference has no collective (it is single-threaded Julia); north_star shards reads over the GPUs of a box
+ * by sequence and merges ONE thing: the optional canonical k-mer count table (the consumer discussed at
+ * src/iterators/CanonicalKmers.jl:183-185, docs/src/composition.md:28-39).  The k-mer / hash / index streams never
+ * cross GPUs.  Two ways to drive several GPUs, over the same code:
+ *   - one process, a kmc_group (what a Julia session is): kmc_group_create makes a context per device and an NCCL
+ *     communicator over them (ncclCommInitAll); per-device descriptors are passed as arrays indexed by device;
+ *   - one process per GPU (torchrun, MPI): rank 0 makes an id (kmc_comm_unique_id), the launcher broadcasts its
+ *     128 bytes, every rank attaches a communicator to its context (kmc_comm_init_rank).
+ * NCCL is loaded at run time; without it these entry points return KMC_E_NCCL (a group of ONE device needs none). */
+int32_t kmc_nccl_version(int32_t *version);
+int32_t kmc_comm_unique_id(void *id128);
+int32_t kmc_comm_init_rank(kmc_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id128);
+int32_t kmc_comm_destroy(kmc_ctx *ctx);
+int32_t kmc_comm_info(kmc_ctx *ctx, int32_t *rank, int32_t *n_ranks);
+/* in-place sum over the ranks of n counters in device memory, enqueued on the context's stream */
+int32_t kmc_allreduce_u32(kmc_ctx *ctx, uint32_t *buf, uint64_t n);
+int32_t kmc_allreduce_u64(kmc_ctx *ctx, uint64_t *buf, uint64_t n);
+/* kmc_bucket_count of this rank's reads + the sum over all ranks, the merge overlapping the count: every eighth of
+ * the table is all-reduced on a communication stream as soon as the count has finished it.  On return (it
+ * synchronises) every rank's table holds the merged counts; result->n_written = k-mers THIS rank counted,
+ * result->kernel_ms = device time from the first count kernel to the end of the last all-reduce.  Collective. */
+int32_t kmc_bucket_count_merge(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits, uint32_t *table,
+                               kmc_result *result);
+/* The exact k-mer table across GPUs.  Every key has one owner rank, kmc_kmer_owner(key, n_ranks) (a second mix of
+ * the key's fx_hash, independent of the bits that pick its slot).  The call sends every (key, count) of this
+ * rank's table (kmc_kmer_count) to its owner -- grouped ncclSend / ncclRecv, NVLink peer traffic -- and the owner
+ * adds what it receives, and its own share, into owned_keys / owned_vals (a table like kmc_kmer_count's,
+ * initialised by the caller).  *n_owned = keys added to the owned table.  Afterwards the union of the owned tables
+ * is the count of the whole input, each key on exactly one rank.  Collective. */
+uint32_t kmc_kmer_owner(uint64_t key, uint32_t n_ranks);
+int32_t kmc_kmer_table_exchange(kmc_ctx *ctx, const uint64_t *keys, const uint32_t *vals, uint32_t log2_capacity,
+                                uint64_t *owned_keys, uint32_t *owned_vals, uint32_t owned_log2_capacity, uint64_t *n_owned);
+
+/* devices == NULL selects devices 0 .. n-1 */
+int32_t kmc_group_create(int32_t n, const int32_t *devices, kmc_group **group);
+int32_t kmc_group_destroy(kmc_group *group);
+int32_t kmc_group_size(kmc_group *group, int32_t *n);
+int32_t kmc_group_ctx(kmc_group *group, int32_t i, kmc_ctx **ctx); /* device i's context (memory, uploads, single-GPU calls) */
+int32_t kmc_group_sync(kmc_group *group);
+/* bufs[i]: n counters on device i; in-place sum, enqueued on every context's stream */
+int32_t kmc_group_allreduce_u32(kmc_group *group, uint32_t *const *bufs, uint64_t n);
+int32_t kmc_group_allreduce_u64(kmc_group *group, uint64_t *const *bufs, uint64_t n);
+/* seqs[i] / tables[i] / results[i] belong to device i: kmc_bucket_count_merge on every device of the group (C5) */
+int32_t kmc_group_bucket_count(kmc_group *group, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
+                               uint32_t *const *tables, kmc_result *results);
+/* kmc_extract / kmc_extract_host on every device side by side (one host thread per device); shard i of a read
+ * set (or the i-th window range of one long sequence, out.index_base = its first window) goes to device i, and
+ * the concatenation of the outputs in device order is the single-GPU (= reference) order */
+int32_t kmc_group_extract(kmc_group *group, const kmc_seqs *seqs, int32_t k, int32_t mode, uint32_t flags,
+                          const kmc_out *outs, kmc_result *results);
+int32_t kmc_group_extract_host(kmc_group *group, const kmc_seqs *host_seqs, int32_t k, int32_t mode, uint32_t flags,
+                               const kmc_out *host_outs, kmc_result *results);
+int32_t kmc_group_kmer_table_exchange(kmc_group *group, const uint64_t *const *keys, const uint32_t *const *vals,
+                                      uint32_t log2_capacity, uint64_t *const *owned_keys, uint32_t *const *owned_vals,
+                                      uint32_t owned_log2_capacity, uint64_t *n_owned);
 
 /* XOR and wrapping sum of n u64 words in device memory -> out[0], out[1] (host).  A cheap
  * fingerprint of a device-resident stream: parity checks and result read-back at sizes where

@@ -293,11 +293,20 @@ int32_t kmc_ctx_create(int32_t device, kmc_ctx **out)
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
-        // temporaries of the binned bucket count come from the stream-ordered pool: keep them cached
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        // Stream-ordered temporaries (binned counts, sketch candidates) come from a pool this context owns.  It keeps
+        // what it has allocated (a binned count of 3 G k-mers takes 24 GB: re-allocating it per call costs
+        // milliseconds) until kmc_trim or kmc_ctx_destroy; the process's default pool is not touched.
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
             uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            ctx->pool = nullptr; // AsyncBuf falls back to the device's default pool
         }
         (void)cudaGetLastError();
     }
@@ -333,7 +342,9 @@ int32_t kmc_ctx_destroy(kmc_ctx *ctx)
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    if (ctx->comm) comm_detach(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
     return KMC_OK;
 }
@@ -353,6 +364,16 @@ int32_t kmc_sync(kmc_ctx *ctx)
     return KMC_OK;
 }
 
+int32_t kmc_trim(kmc_ctx *ctx)
+{
+    if (!ctx) return KMC_E_BAD_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) CU(cudaStreamSynchronize(ctx->pipe_streams[i]));
+    if (ctx->pool) CU(cudaMemPoolTrimTo(ctx->pool, 0));
+    return KMC_OK;
+}
+
 const char *kmc_last_error(kmc_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "kmc_ctx is NULL"; }
 
 const char *kmc_status_string(int32_t status)
@@ -365,6 +386,7 @@ const char *kmc_status_string(int32_t status)
     case KMC_E_OUT_TOO_SMALL: return "output buffer too small";
     case KMC_E_NO_DEVICE: return "no CUDA device";
     case KMC_E_UNSUPPORTED: return "unsupported configuration";
+    case KMC_E_NCCL: return "NCCL error (or NCCL could not be loaded)";
     }
     if (status < 0) return cudaGetErrorString(static_cast<cudaError_t>(-status));
     return "unknown status";
@@ -593,38 +615,34 @@ int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t
     // L2-sized tables) the kernel increments the table directly.
     const uint64_t table_bytes = 4ull << bucket_bits;
     bool binned = table_bytes > (96ull << 20) && bucket_bits <= 32;
-    uint32_t *ids = nullptr, *tmp_ids = nullptr;
-    uint64_t *matrix = nullptr, *offs = nullptr, *scan_tmp = nullptr;
+    AsyncBuf ids_buf, tmp_buf, matrix_buf, offs_buf, scan_buf; // freed (stream-ordered) on every way out
     const uint64_t n_ids = (L.items + 1) * static_cast<uint64_t>(ge.g); // flat windows, rounded up to whole groups
     if (binned) {
         const uint64_t cells = (static_cast<uint64_t>(1) << binned_count_bin_bits(bucket_bits)) * binned_count_blocks(n_ids);
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ids), round_up(n_ids * 4, 256), stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&tmp_ids), round_up(n_ids * 4, 256), stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&matrix), (cells + 1) * 8, stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&offs), (cells + 2) * 8, stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&scan_tmp), (scan_tmp_elems(cells) + 1) * 8, stream);
+        cudaError_t e = ids_buf.alloc(ctx, round_up(n_ids * 4, 256), stream);
+        if (e == cudaSuccess) e = tmp_buf.alloc(ctx, round_up(n_ids * 4, 256), stream);
+        if (e == cudaSuccess) e = matrix_buf.alloc(ctx, (cells + 1) * 8, stream);
+        if (e == cudaSuccess) e = offs_buf.alloc(ctx, (cells + 2) * 8, stream);
+        if (e == cudaSuccess) e = scan_buf.alloc(ctx, (scan_tmp_elems(cells) + 1) * 8, stream);
         if (e != cudaSuccess) { // not enough memory for the binned path: fall back to direct increments
             (void)cudaGetLastError();
-            for (void *q : {static_cast<void *>(ids), static_cast<void *>(tmp_ids), static_cast<void *>(matrix),
-                            static_cast<void *>(offs), static_cast<void *>(scan_tmp)})
-                if (q) cudaFreeAsync(q, stream);
             binned = false;
         }
     }
     if (binned) {
         // the flat id array is exactly the flat window array: every flat index < L.total is written
         // once (slots of partial groups that are not windows are not written and not binned)
-        p.out_a = reinterpret_cast<uint64_t *>(ids);
+        p.out_a = ids_buf.as<uint64_t>();
         p.vec_ok = 1;
         ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKET_IDS, true, !L.uniform_len);
         if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
         CU(fn(p, ctx->sm_count, stream));
-        CU(binned_count(ids, L.total, bucket_bits, table, tmp_ids, matrix, offs, scan_tmp, ctx->sm_count, stream, n_parts, events));
-        for (void *q : {static_cast<void *>(ids), static_cast<void *>(tmp_ids), static_cast<void *>(matrix),
-                        static_cast<void *>(offs), static_cast<void *>(scan_tmp)})
-            CU(cudaFreeAsync(q, stream));
+        CU(binned_count(ids_buf.as<uint32_t>(), L.total, bucket_bits, table, tmp_buf.as<uint32_t>(), matrix_buf.as<uint64_t>(),
+                        offs_buf.as<uint64_t>(), scan_buf.as<uint64_t>(), ctx->sm_count, stream, n_parts, events));
     } else {
         // a table that fits L2 is pulled into it first: increments that miss L2 serialise at DRAM latency
+        st = ensure_host_small(ctx); // allocates dev_small, where warm_table's sink lives
+        if (st) return st;
         if (table_bytes <= (96ull << 20)) CU(warm_table(table, 1ull << bucket_bits, ctx->sm_count, warm_sink(ctx), stream));
         p.bucket_table = table;
         ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKETS, true, !L.uniform_len);

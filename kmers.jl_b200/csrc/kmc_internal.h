@@ -6,6 +6,8 @@
 
 #include "../../include/kmerscuda.h"
 
+struct kmc_comm;
+
 struct kmc_ctx {
     int device = 0;
     int sm_count = 0;
@@ -25,12 +27,39 @@ struct kmc_ctx {
     // 16 u64 per pipeline slot, slot 3 = the context's own stream
     uint64_t *host_small = nullptr;
     uint64_t *dev_small = nullptr; // 128 bytes of device memory: KMC_DIGEST accumulators (first 64), warm_table's sink (byte 96)
+    // stream-ordered temporaries (binned counts, sketch candidates) come from a pool the context owns, so the
+    // process's default pool is left alone and kmc_trim / kmc_ctx_destroy give the memory back
+    cudaMemPool_t pool = nullptr;
+    kmc_comm *comm = nullptr; // comm.cu: the NCCL communicator attached to this context, if any
     std::string last_error;
 };
 
 namespace kmc {
 
+// stream-ordered temporary from the context's pool; freed (stream-ordered) when it goes out of scope
+struct AsyncBuf {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(kmc_ctx *ctx, uint64_t bytes, cudaStream_t stream)
+    {
+        s = stream;
+        return ctx->pool ? cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, ctx->pool, stream)
+                         : cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+    AsyncBuf() = default;
+    AsyncBuf(const AsyncBuf &) = delete;
+    AsyncBuf &operator=(const AsyncBuf &) = delete;
+    ~AsyncBuf()
+    {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+
 inline uint32_t *warm_sink(kmc_ctx *ctx) { return reinterpret_cast<uint32_t *>(ctx->dev_small) + 24; }
+
+// comm.cu: destroys the context's communicator (rank) and its stream / events
+void comm_detach(kmc_ctx *ctx);
 
 // scratch carving -------------------------------------------------------------------------
 int32_t ensure_scratch(kmc_ctx *ctx, uint64_t bytes);

@@ -265,20 +265,6 @@ __global__ void __launch_bounds__(256) table_export_kernel(const unsigned long l
     }
 }
 
-struct AsyncBuf { // stream-ordered temporary
-    void *p = nullptr;
-    cudaStream_t s = nullptr;
-    cudaError_t alloc(uint64_t bytes, cudaStream_t stream)
-    {
-        s = stream;
-        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
-    }
-    ~AsyncBuf()
-    {
-        if (p) cudaFreeAsync(p, s);
-    }
-};
-
 } // namespace
 
 } // namespace kmc
@@ -344,10 +330,10 @@ extern "C" int32_t kmc_minhash_sketch(kmc_ctx *ctx, const kmc_seqs *seqs, int32_
         const bool all = t >= kBuckets - 1;
         if (t >= kBuckets) t = kBuckets - 1;
         AsyncBuf cand, sorted, uniq, tmp, nsel;
-        CU(cand.alloc(cum * 8, stream));
-        CU(sorted.alloc(cum * 8, stream));
-        CU(uniq.alloc(cum * 8, stream));
-        CU(nsel.alloc(8, stream));
+        CU(cand.alloc(ctx, cum * 8, stream));
+        CU(sorted.alloc(ctx, cum * 8, stream));
+        CU(uniq.alloc(ctx, cum * 8, stream));
+        CU(nsel.alloc(ctx, 8, stream));
         c.limit = all ? ~0ull : (((t + 1) << (64 - kBits)) - 1);
         c.cand = static_cast<uint64_t *>(cand.p);
         c.cursor = cursor;
@@ -359,7 +345,7 @@ extern "C" int32_t kmc_minhash_sketch(kmc_ctx *ctx, const kmc_seqs *seqs, int32_
                                           64, stream));
         CU(cub::DeviceSelect::Unique(nullptr, b2, static_cast<uint64_t *>(sorted.p), static_cast<uint64_t *>(uniq.p),
                                      static_cast<uint64_t *>(nsel.p), cum, stream));
-        CU(tmp.alloc(b1 > b2 ? b1 : b2, stream));
+        CU(tmp.alloc(ctx, b1 > b2 ? b1 : b2, stream));
         CU(cub::DeviceRadixSort::SortKeys(tmp.p, b1, static_cast<uint64_t *>(cand.p), static_cast<uint64_t *>(sorted.p), cum, 0, 64,
                                           stream));
         CU(cub::DeviceSelect::Unique(tmp.p, b2, static_cast<uint64_t *>(sorted.p), static_cast<uint64_t *>(uniq.p),
@@ -481,11 +467,11 @@ extern "C" int32_t kmc_kmer_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k,
     const uint64_t n_flat = (L.items + 1) * static_cast<uint64_t>(ge.g); // flat windows, rounded up to whole groups
     if (binned) {
         const uint64_t cells = binning::matrix_cells<uint64_t>(L.total, bin_bits);
-        cudaError_t e = kmers_buf.alloc(round_up(n_flat * 8, 256), stream);
-        if (e == cudaSuccess) e = binned_buf.alloc(round_up(n_flat * 8, 256), stream);
-        if (e == cudaSuccess) e = matrix_buf.alloc((cells + 1) * 8, stream);
-        if (e == cudaSuccess) e = offs_buf.alloc((cells + 2) * 8, stream);
-        if (e == cudaSuccess) e = scan_buf.alloc((scan_tmp_elems(cells) + 1) * 8, stream);
+        cudaError_t e = kmers_buf.alloc(ctx, round_up(n_flat * 8, 256), stream);
+        if (e == cudaSuccess) e = binned_buf.alloc(ctx, round_up(n_flat * 8, 256), stream);
+        if (e == cudaSuccess) e = matrix_buf.alloc(ctx, (cells + 1) * 8, stream);
+        if (e == cudaSuccess) e = offs_buf.alloc(ctx, (cells + 2) * 8, stream);
+        if (e == cudaSuccess) e = scan_buf.alloc(ctx, (scan_tmp_elems(cells) + 1) * 8, stream);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             binned = false;

@@ -20,6 +20,8 @@ KMC_E_AMBIGUOUS = 3
 KMC_E_OUT_TOO_SMALL = 4
 KMC_E_NO_DEVICE = 5
 KMC_E_UNSUPPORTED = 6
+KMC_E_NCCL = 7
+KMC_COMM_ID_BYTES = 128
 
 KMC_FW, KMC_FWRV, KMC_CANON, KMC_UNAMBIG = 0, 1, 2, 3
 KMC_HASH_FX, KMC_AOS, KMC_NO_SYNC, KMC_OUT_DEVICE, KMC_DIGEST, KMC_RNA = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
@@ -73,6 +75,7 @@ SIGNATURES = {
     "kmc_ctx_destroy": (C.c_int32, [C.c_void_p]),
     "kmc_ctx_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "kmc_sync": (C.c_int32, [C.c_void_p]),
+    "kmc_trim": (C.c_int32, [C.c_void_p]),
     "kmc_last_error": (C.c_char_p, [C.c_void_p]),
     "kmc_status_string": (C.c_char_p, [C.c_int32]),
     "kmc_device_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_char_p, C.c_int32]),
@@ -108,6 +111,33 @@ SIGNATURES = {
                                          C.POINTER(C.c_uint64)]),
     "kmc_kmer_table_export": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
                                           C.POINTER(C.c_uint64)]),
+    "kmc_nccl_version": (C.c_int32, [C.POINTER(C.c_int32)]),
+    "kmc_comm_unique_id": (C.c_int32, [C.c_void_p]),
+    "kmc_comm_init_rank": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "kmc_comm_destroy": (C.c_int32, [C.c_void_p]),
+    "kmc_comm_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "kmc_allreduce_u32": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "kmc_allreduce_u64": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "kmc_bucket_count_merge": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p,
+                                           C.POINTER(kmc_result)]),
+    "kmc_kmer_owner": (C.c_uint32, [C.c_uint64, C.c_uint32]),
+    "kmc_kmer_table_exchange": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                            C.POINTER(C.c_uint64)]),
+    "kmc_group_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
+    "kmc_group_destroy": (C.c_int32, [C.c_void_p]),
+    "kmc_group_size": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "kmc_group_ctx": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "kmc_group_sync": (C.c_int32, [C.c_void_p]),
+    "kmc_group_allreduce_u32": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint64]),
+    "kmc_group_allreduce_u64": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint64]),
+    "kmc_group_bucket_count": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+                                           C.POINTER(kmc_result)]),
+    "kmc_group_extract": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint32, C.POINTER(kmc_out),
+                                      C.POINTER(kmc_result)]),
+    "kmc_group_extract_host": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint32, C.POINTER(kmc_out),
+                                           C.POINTER(kmc_result)]),
+    "kmc_group_kmer_table_exchange": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32,
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_uint64)]),
     "kmc_digest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "kmc_timer_begin": (C.c_int32, [C.c_void_p]),
     "kmc_timer_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),

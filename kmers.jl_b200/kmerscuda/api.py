@@ -223,8 +223,13 @@ class DeviceBuffer:
 class Context:
     """One kmc_ctx: a device, a stream, scratch.  Not thread-safe (one caller at a time)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self.lib = _abi.load()
+        self.device = device
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a context that belongs to a Group
+            self.handle = _borrowed
+            return
         h = C.c_void_p()
         st = self.lib.kmc_ctx_create(device, C.byref(h))
         if st != KMC_OK:
@@ -232,12 +237,57 @@ class Context:
                 f"kmc_ctx_create(device={device}) failed: {self.lib.kmc_status_string(st).decode()} "
                 "-- KmersCUDA needs a CUDA device; there is no CPU fallback")
         self.handle = h
-        self.device = device
 
     def close(self):
-        if self.handle:
+        if self.handle and self._owned:
             self.lib.kmc_ctx_destroy(self.handle)
-            self.handle = None
+        self.handle = None
+
+    # ---- one process per GPU: an NCCL communicator attached to this context (comm.cu) --------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes made by rank 0 and broadcast by the launcher (torch.distributed, MPI, a file)."""
+        lib = _abi.load()
+        buf = C.create_string_buffer(_abi.KMC_COMM_ID_BYTES)
+        st = lib.kmc_comm_unique_id(buf)
+        if st != KMC_OK:
+            raise KmersCUDAError(f"kmc_comm_unique_id: {lib.kmc_status_string(st).decode()}")
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == _abi.KMC_COMM_ID_BYTES
+        self._check(self.lib.kmc_comm_init_rank(self.handle, n_ranks, rank, C.c_char_p(unique_id)))
+
+    def comm_init_torch(self, group=None):
+        """Attach a communicator whose ranks are the ranks of an initialised torch.distributed group: the id
+        travels by broadcast_object_list; the collectives themselves then run inside libkmerscuda."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(world, rank, box[0])
+
+    def comm_info(self):
+        r, n = C.c_int32(), C.c_int32()
+        self._check(self.lib.kmc_comm_info(self.handle, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def comm_destroy(self):
+        self._check(self.lib.kmc_comm_destroy(self.handle))
+
+    def allreduce(self, dptr: int, n: int, dtype=np.uint32):
+        fn = self.lib.kmc_allreduce_u32 if np.dtype(dtype).itemsize == 4 else self.lib.kmc_allreduce_u64
+        self._check(fn(self.handle, dptr, n))
+
+    def bucket_count_merge(self, desc, K: int, bucket_bits: int, table_ptr: int):
+        """Count this rank's reads and sum the tables of all ranks, the merge overlapping the count
+        (kmc_bucket_count_merge).  Returns (k-mers this rank counted, device ms)."""
+        res = kmc_result()
+        self._check(self.lib.kmc_bucket_count_merge(self.handle, C.byref(desc), K, bucket_bits, table_ptr, C.byref(res)))
+        return int(res.n_written), float(res.kernel_ms)
+
+    def trim(self):
+        self._check(self.lib.kmc_trim(self.handle))
 
     def __del__(self):
         try:
@@ -704,6 +754,17 @@ class KmerTable:
                                                           other.keys.ptr, other.vals.ptr, 1 << other.log2_capacity, C.byref(n_new)))
         self.n_keys += int(n_new.value)
 
+    def exchange(self, owned_log2_capacity: int) -> "KmerTable":
+        """One process per GPU: send every (key, count) to the rank that owns the key (kmc_kmer_table_exchange over the
+        context's communicator) and return this rank's owned table.  Collective."""
+        owned = KmerTable(owned_log2_capacity, ctx=self.ctx)
+        self.ctx.sync()
+        n_owned = C.c_uint64(0)
+        self.ctx._check(self.ctx.lib.kmc_kmer_table_exchange(self.ctx.handle, self.keys.ptr, self.vals.ptr, self.log2_capacity,
+                                                             owned.keys.ptr, owned.vals.ptr, owned_log2_capacity, C.byref(n_owned)))
+        owned.n_keys = int(n_owned.value)
+        return owned
+
     def items(self):
         """(keys u64[n], counts u32[n]) sorted by key."""
         n = max(self.n_keys, 1)
@@ -720,6 +781,107 @@ class KmerTable:
     def free(self):
         self.keys.free()
         self.vals.free()
+
+
+class Group:
+    """One process driving several GPUs (kmc_group): a Context per device and one NCCL communicator over them.
+    Shard i of the input goes to device i; outputs concatenate in device order (= the reference's order)."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.lib = _abi.load()
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        st = self.lib.kmc_group_create(len(devices), devs, C.byref(h))
+        if st != KMC_OK:
+            raise KmersCUDAError(f"kmc_group_create({list(devices)}) failed: {self.lib.kmc_status_string(st).decode()}")
+        self.handle = h
+        self.ctx = []
+        for i, d in enumerate(devices):
+            c = C.c_void_p()
+            self.lib.kmc_group_ctx(self.handle, i, C.byref(c))
+            self.ctx.append(Context(d, _borrowed=c))
+
+    def __len__(self):
+        return len(self.ctx)
+
+    def close(self):
+        if self.handle:
+            for c in self.ctx:
+                c.handle = None
+            self.lib.kmc_group_destroy(self.handle)
+            self.handle = None
+
+    def _check(self, st: int):
+        if st != KMC_OK:
+            msgs = [self.lib.kmc_last_error(c.handle).decode() for c in self.ctx]
+            raise KmersCUDAError(f"libkmerscuda status {st}: {self.lib.kmc_status_string(st).decode()} {[m for m in msgs if m]}")
+
+    def sync(self):
+        self._check(self.lib.kmc_group_sync(self.handle))
+
+    def bucket_count(self, shards: Sequence["DeviceReadSet"], K: int, bucket_bits: int):
+        """C5: count every shard on its device and merge the tables with NCCL (kmc_group_bucket_count).
+        Returns (the merged table u32[2^bucket_bits] read from device 0, k-mers per device, device ms per device,
+        the device tables)."""
+        n = len(self.ctx)
+        assert len(shards) == n
+        tables = [c.alloc(4 << bucket_bits) for c in self.ctx]
+        for c, t in zip(self.ctx, tables):
+            c._check(self.lib.kmc_memset(c.handle, t.ptr, 0, 4 << bucket_bits))
+        descs = (kmc_seqs * n)(*[sh.desc for sh in shards])
+        ptrs = (C.c_void_p * n)(*[t.ptr for t in tables])
+        res = (kmc_result * n)()
+        self._check(self.lib.kmc_group_bucket_count(self.handle, descs, K, bucket_bits, ptrs, res))
+        merged = tables[0].download(np.uint32, 1 << bucket_bits)
+        return merged, [int(r.n_written) for r in res], [float(r.kernel_ms) for r in res], tables
+
+    def extract_host(self, mode: int, shards: Sequence[ReadSet], K: int, *, hash: bool = False, aos: bool = False,
+                     index_bases: Optional[Sequence[int]] = None):
+        """`collect` over host shards on all devices side by side (kmc_group_extract_host); returns one Extracted
+        per device (2-bit k-mer alphabets)."""
+        n = len(self.ctx)
+        assert len(shards) == n
+        N = n_limbs(K)
+        two, want_index = mode == KMC_FWRV, mode == KMC_UNAMBIG
+        a_elems = (2 * N if two else N + 1 if want_index else N) if aos else N
+        flags = (KMC_HASH_FX if hash else 0) | (KMC_AOS if aos else 0)
+        bufs, outs = [], (kmc_out * n)()
+        for i, rs in enumerate(shards):
+            cap = max(int(rs.window_counts(K).sum()), 1)
+            a = np.zeros(cap * a_elems, dtype=np.uint64)
+            b = np.zeros(cap * N, dtype=np.uint64) if (two and not aos) else None
+            h = np.zeros(cap, dtype=np.uint64) if hash else None
+            ix = np.zeros(cap, dtype=np.int64) if (want_index and not aos) else None
+            bufs.append((a, b, h, ix))
+            outs[i] = kmc_out(a.ctypes.data, None if b is None else b.ctypes.data, None if h is None else h.ctypes.data,
+                              None if ix is None else ix.ctypes.data, None, cap, 0 if index_bases is None else index_bases[i])
+        descs = (kmc_seqs * n)(*[_host_desc(rs) for rs in shards])
+        res = (kmc_result * n)()
+        st = self.lib.kmc_group_extract_host(self.handle, descs, K, mode, flags, outs, res)
+        self._check(st)
+        out = []
+        for (a, b, h, ix), r in zip(bufs, res):
+            m = int(r.n_written)
+            kmers = a[: m * a_elems].reshape(m, a_elems if aos else N)
+            out.append(Extracted(kmers=kmers, rv=None if b is None else b[: m * N].reshape(m, N), hash=None if h is None else h[:m],
+                                 index=None if ix is None else ix[:m], n=m, kernel_ms=float(r.kernel_ms)))
+        return out
+
+    def kmer_table_exchange(self, tables: Sequence["KmerTable"], owned_log2_capacity: int):
+        """Every (key, count) of the per-device tables to its owner device (kmc_group_kmer_table_exchange);
+        returns the owned tables, whose union is the count of the whole input."""
+        n = len(self.ctx)
+        owned = [KmerTable(owned_log2_capacity, ctx=c) for c in self.ctx]
+        for c in self.ctx:
+            c.sync()
+        P = C.c_void_p * n
+        n_owned = (C.c_uint64 * n)()
+        self._check(self.lib.kmc_group_kmer_table_exchange(
+            self.handle, P(*[t.keys.ptr for t in tables]), P(*[t.vals.ptr for t in tables]), tables[0].log2_capacity,
+            P(*[t.keys.ptr for t in owned]), P(*[t.vals.ptr for t in owned]), owned_log2_capacity, n_owned))
+        for t, m in zip(owned, n_owned):
+            t.n_keys = int(m)
+        return owned
 
 
 def bucket_count(rs, K: int, bucket_bits: int, ctx: Optional[Context] = None, table: Optional[DeviceBuffer] = None):

@@ -33,11 +33,18 @@ class ReadShard:
     n_words: int
 
 
+def symbols_per_unit(bits: int) -> int:
+    """Symbols per offset unit of a source: 32 / 16 per 64-bit LongSequence word (2- / 4-bit alphabets); ASCII
+    sources (bits == 8) count BYTES in every "word" quantity (include/kmerscuda.h, kmc_seqs), so one symbol per unit
+    -- the same rule as host_pipeline.cu and tiles_upper_bound."""
+    return 1 if bits == 8 else 64 // bits
+
+
 def plan_read_shards(rs: ReadSet, world: int) -> list[ReadShard]:
     """Contiguous read ranges, balanced by symbols (uniform sets: by reads)."""
     n = rs.n_seqs
     bits = rs.bits
-    spw = 64 // bits
+    spw = symbols_per_unit(bits)
     if rs.seq_len is None:
         bounds = [(n * g) // world for g in range(world + 1)]
     else:
@@ -93,7 +100,7 @@ class SequenceShard:
 
 def plan_sequence_shards(length: int, K: int, bits: int, world: int, first_symbol_offset: int = 0) -> list[SequenceShard]:
     """Window ranges of ONE long sequence with a K-1-symbol halo per rank."""
-    spw = 64 // bits
+    spw = symbols_per_unit(bits)
     n = max(0, length - K + 1)
     per = (n + world - 1) // world if n else 0
     out = []

@@ -99,6 +99,61 @@ def test_sequence_shards_with_halo(kc, sh, world, k):
     assert np.array_equal(np.concatenate(pk), km) and np.array_equal(np.concatenate(pp), pos)
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_ascii_read_shards_tile_and_concatenate(kc, sh, world):
+    """ASCII sets (bits = 8) count BYTES in every word quantity: one symbol per unit.  The planner used 64 // bits
+    = 8 symbols per unit and truncated the last read of every shard.  Ragged strings and the advisor's
+    own reproduction (8 x 'ACGT' * 25)."""
+    rng = np.random.default_rng(100 + world)
+    k = 31
+    sets = [kc.ReadSet.from_strings(["ACGT" * 25] * 8),
+            kc.ReadSet.from_strings(["".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(0, 300, size=200)])]
+    for rs in sets:
+        plan = sh.plan_read_shards(rs, world)
+        assert plan[0].seq0 == 0 and sum(p.n_seqs for p in plan) == rs.n_seqs
+        assert sum(p.n_words for p in plan) == int(rs.seq_len.sum())  # every byte belongs to exactly one shard
+        whole_a, whole_h = [], []
+        for r in range(rs.n_seqs):
+            o, n = int(rs.seq_word_offset[r]), int(rs.seq_len[r])
+            a, _, h = ko.ascii_iterate(bytes(rs.words[o:o + n]), k, ko.CANON, want_hash=True)
+            whole_a.append(a)
+            whole_h.append(h)
+        parts_a, parts_h = [], []
+        for g in range(world):
+            sub = sh.read_shard(rs, world, g)
+            for r in range(sub.n_seqs):
+                o, n = int(sub.seq_word_offset[r]), int(sub.seq_len[r])
+                assert o + n <= sub.words.size
+                a, _, h = ko.ascii_iterate(bytes(sub.words[o:o + n]), k, ko.CANON, want_hash=True)
+                parts_a.append(a)
+                parts_h.append(h)
+        assert np.array_equal(np.concatenate(parts_a), np.concatenate(whole_a))
+        assert np.array_equal(np.concatenate(parts_h), np.concatenate(whole_h))
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_ascii_sequence_shards_with_halo(kc, sh, world):
+    rng = np.random.default_rng(7 + world)
+    n, k = 1000, 31
+    s = "".join(rng.choice(list("ACGT"), size=n)).encode()
+    a, _, h = ko.ascii_iterate(s, k, ko.CANON, want_hash=True)
+    plan = sh.plan_sequence_shards(n, k, 8, world)
+    assert sum(p.n_windows for p in plan) == n - k + 1
+    if world == 2:  # the advisor's numbers: rank 1 starts at byte 485 and needs 515 bytes
+        assert (plan[1].word0, plan[1].n_words, plan[1].first_symbol_offset) == (485, 515, 0)
+    pa, ph = [], []
+    data = np.frombuffer(s, dtype=np.uint8)
+    for g in range(world):
+        rs, base = sh.sequence_shard(8, data, n, k, world, g)
+        assert base == plan[g].window0
+        view = bytes(rs.words[rs.first_symbol_offset: rs.first_symbol_offset + rs.uniform_len])
+        x, _, y = ko.ascii_iterate(view, k, ko.CANON, want_hash=True)
+        assert x.shape[0] == plan[g].n_windows
+        pa.append(x)
+        ph.append(y)
+    assert np.array_equal(np.concatenate(pa), a) and np.array_equal(np.concatenate(ph), h)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
