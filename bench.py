@@ -470,10 +470,11 @@ def run_ours(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout, which must carry exactly one JSON line (at N = 1 too:
+    # the c5 leg attaches a one-rank communicator inside libkmerscuda)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout, which must carry exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import kmerscuda as kc
