@@ -35,3 +35,49 @@ end
     t = KmersCUDA.bucket_count(CanonicalDNAMers{11}(s), 12)
     @test sum(t) == length(s) - 10
 end
+
+@testset "LongSubSeq views (reference: test/runtests.jl:154-169)" begin
+    s2 = LongDNA{2}(randdnaseq(RNG, 1000))
+    s4 = LongDNA{4}(s2); s4[500] = DNA_N
+    for rng in (2:1000, 33:900, 65:64, 17:48), K in (5, 31, 33)
+        v2, v4 = view(s2, rng), view(s4, rng)
+        @test KmersCUDA.collect(FwDNAMers{K}(v2)) == collect(FwDNAMers{K}(v2))
+        @test KmersCUDA.collect(CanonicalDNAMers{K}(v2)) == collect(CanonicalDNAMers{K}(v2))
+        @test KmersCUDA.collect(UnambiguousDNAMers{K}(v4)) == collect(UnambiguousDNAMers{K}(v4))
+    end
+end
+
+@testset "ASCII sources incl. StringView (reference: test/runtests.jl:892-899)" begin
+    str = "ATGCTGATGATCGTATGATGTCGAAA"
+    for src in (str, SubString(str, 3:20), codeunits(str), collect(codeunits(str)))
+        @test KmersCUDA.collect(FwRvIterator{DNAAlphabet{2}, 9}(src)) == collect(FwRvIterator{DNAAlphabet{2}, 9}(src))
+    end
+    if Base.find_package("StringViews") !== nothing
+        @eval using StringViews
+        sv = StringView(collect(codeunits(str)))
+        @test KmersCUDA.collect(FwRvIterator{DNAAlphabet{2}, 9}(sv)) == collect(FwRvIterator{DNAAlphabet{2}, 9}(sv))
+    end
+end
+
+@testset "device-resident extraction and groups" begin
+    reads = [LongDNA{2}(randdnaseq(RNG, rand(RNG, 0:300))) for _ in 1:2000]
+    want = reduce(vcat, [collect(CanonicalDNAMers{31}(r)) for r in reads])
+    km, h, off = KmersCUDA.extract(CanonicalDNAMers{31}, reads; hash = true)
+    @test km == want && h == fx_hash.(want) && off[end] == length(want)
+    dk, dh = KmersCUDA.extract(CanonicalDNAMers{31}, reads; hash = true, device = true)
+    @test Array(dk) == want && Array(dh) == fx_hash.(want)
+    @test Array(KmersCUDA.fx_hash_device(dk)) == fx_hash.(want)
+    g = KmersCUDA.Group()
+    parts = KmersCUDA.extract(CanonicalDNAMers{31}, reads; hash = true, group = g)
+    @test reduce(vcat, [p[1] for p in parts]) == want
+    t = KmersCUDA.bucket_count(CanonicalDNAMers{31}, reads, 16; group = g)
+    ref = zeros(UInt32, 1 << 16)
+    for m in want
+        ref[(fx_hash(m) >> 48) + 1] += 1
+    end
+    @test t == ref
+end
+
+@testset "LongSequence.data layout (what the device assumes; tests/golden pins it for the oracle)" begin
+    @test LongDNA{2}("TAGCTAGGACA").data == [0x000000000004a363]
+end

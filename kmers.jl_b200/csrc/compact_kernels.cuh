@@ -1,5 +1,8 @@
 // compact_kernels.cuh -- UnambiguousKmers over a recoded (4-bit or ASCII) source
-// (UnambiguousKmers.jl:109-148) as ONE ordered stream compaction.
+// (UnambiguousKmers.jl:109-148) as ONE ordered stream compaction over the FLAT WINDOW order of the set.
+// This is the general path: it handles any layout of the sequences in the buffer (overlapping views, any
+// order).  Sets whose sequences are ascending and disjoint in the buffer -- all the host mirrors build -- take
+// the cheaper source-order compaction of lincompact.cuh instead.
 //
 // The iterator emits, in order, every window whose K symbols are all certain, with its 1-based
 // start.  The recoding pass (fourbit.cu / ascii.cu) has left a 2-bit stream and one "valid start"
@@ -23,7 +26,8 @@
 namespace kmc {
 
 struct CompactParams {
-    unsigned long long *tile_state; // [tiles], zeroed before the launch: flag (2 bits) | count (62 bits)
+    unsigned long long *tile_state; // [tiles + 1], zeroed before the launch: flag (2 bits) | count (62 bits); the last
+                                    // entry is the ticket counter the blocks draw their tile from
     uint64_t *total_out;            // device: number of k-mers the set emits (written by the last tile)
     uint64_t capacity;              // elements the output buffers hold; nothing is written beyond
 };
@@ -33,13 +37,6 @@ struct CompactParams {
 // the 4 the compiler picks on its own (56 registers); 6 needs spills and is slower than 4.
 #ifndef KMC_COMPACT_MIN_BLOCKS
 #define KMC_COMPACT_MIN_BLOCKS 5
-#endif
-
-// EXPERIMENT, off by default and not measured yet: the burst prefetch of extract_kernel for
-// this kernel's two sources -- the recoded 2-bit stream and the valid-start bits.  Build a variant with
-// EXTRA=-DKMC_COMPACT_PREFETCH=1 and compare it with ab/ab_modes.sh before switching it on.
-#ifndef KMC_COMPACT_PREFETCH
-#define KMC_COMPACT_PREFETCH 0
 #endif
 
 constexpr uint64_t kTileAggregate = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1;
@@ -129,30 +126,19 @@ __global__ void __launch_bounds__(kBlockThreads, KMC_COMPACT_MIN_BLOCKS) compact
     __shared__ uint32_t s_cnt[kCells], s_base[kCells];
     __shared__ uint64_t s_tile_out;
 
+    __shared__ uint32_t s_tile;
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t *stage = s_stage_all + static_cast<size_t>(warp) * stage_words(N);
-    const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTileItems;
-#if KMC_COMPACT_PREFETCH
-    if (p.pf_tiles) {
-        burst_prefetch<RAGGED, G, 2>(p, p.items);
-        // the valid-start bits of the same symbols: one bit per symbol, so byte = (stream bit / 2) / 8
-        const uint32_t T = p.pf_tiles, c = blockIdx.x / T, k = blockIdx.x - c * T;
-        const uint32_t lead = kPfLead < T ? kPfLead : T, k0 = T - lead;
-        const bool first = blockIdx.x < kPfBlocks;
-        if (first || (k >= k0 && k < k0 + kPfBlocks)) {
-            const uint64_t cc = first ? 0 : c + 1, kk = first ? blockIdx.x : k - k0;
-            const int64_t b0 = (tile_start_bit<RAGGED, G, 2>(p, cc * T, p.items) >> 4) & ~127ll;
-            int64_t b1 = (tile_start_bit<RAGGED, G, 2>(p, (cc + 1) * T, p.items) >> 4) + 256;
-            if (b1 > p.nw32 * 2) b1 = p.nw32 * 2; // the bit array covers the stream's nw32 * 16 symbols = nw32 * 2 bytes
-            const char *vb = reinterpret_cast<const char *>(p.vstart);
-            for (int64_t o = b0 + (static_cast<int64_t>(kk) * kBlockThreads + threadIdx.x) * 128; o < b1;
-                 o += static_cast<int64_t>(kPfBlocks) * kBlockThreads * 128)
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(vb + o));
-        }
-    }
-#endif
+    // The tile comes from a ticket, not from blockIdx.x: the look-back below waits for the tiles before this one,
+    // and a ticket guarantees that they were STARTED before it whatever order the hardware dispatches blocks in
+    // (a block that has drawn its ticket publishes its aggregate without waiting for anything).
+    if (threadIdx.x == 0) s_tile = static_cast<uint32_t>(atomicAdd(cp.tile_state + gridDim.x, 1ull));
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_base = static_cast<uint64_t>(tile) * kTileItems;
     TileCursor<RAGGED, G> cur;
-    cur.init(p, tile_base, sh, threadIdx.x);
+    cur.init(p, tile_base, sh, threadIdx.x, tile);
     const TileCursor<RAGGED, G> cur0 = cur;
 
     // ---- phase 1: survivors of every item (G <= 8 bits each, kept for phase 2) ------------------
@@ -187,12 +173,12 @@ __global__ void __launch_bounds__(kBlockThreads, KMC_COMPACT_MIN_BLOCKS) compact
         s_base[lane] = i0 - v0;
         s_base[lane + 32] = i1 - v1;
         const uint64_t tile_total = __shfl_sync(0xffffffffu, i1, 31);
-        // decoupled look-back: tiles are dispatched in blockIdx order, so every tile before this one
-        // is running or done and publishes its aggregate without waiting for anything after it
+        // decoupled look-back: every tile before this one has drawn its ticket earlier, so it is running or done
+        // and publishes its aggregate without waiting for anything after it
         uint64_t excl = 0;
-        if (blockIdx.x > 0) {
-            if (lane == 0) st_relaxed_u64(cp.tile_state + blockIdx.x, kTileAggregate | tile_total);
-            int64_t top = static_cast<int64_t>(blockIdx.x) - 1;
+        if (tile > 0) {
+            if (lane == 0) st_relaxed_u64(cp.tile_state + tile, kTileAggregate | tile_total);
+            int64_t top = static_cast<int64_t>(tile) - 1;
             for (;;) {
                 const int64_t idx = top - lane;
                 uint64_t s;
@@ -207,9 +193,9 @@ __global__ void __launch_bounds__(kBlockThreads, KMC_COMPACT_MIN_BLOCKS) compact
             }
         }
         if (lane == 0) {
-            st_relaxed_u64(cp.tile_state + blockIdx.x, kTilePrefix | (excl + tile_total));
+            st_relaxed_u64(cp.tile_state + tile, kTilePrefix | (excl + tile_total));
             s_tile_out = excl;
-            if (blockIdx.x == gridDim.x - 1) *cp.total_out = excl + tile_total;
+            if (tile == gridDim.x - 1) *cp.total_out = excl + tile_total;
         }
     }
     __syncthreads();
@@ -305,13 +291,6 @@ cudaError_t launch_compact(ExtractParams p, CompactParams cp, cudaStream_t strea
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     set_iteration_strides(p);
     p.pf_tiles = 0;
-#if KMC_COMPACT_PREFETCH
-    if (prefetch_enabled()) {
-        const uint64_t per_tile = static_cast<uint64_t>(p.nw32) * 4 / tiles + 1;
-        const uint64_t t = kPfChunkBytes / per_tile;
-        p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
-    }
-#endif
     constexpr size_t smem = static_cast<size_t>(kWarpsPerBlock) * stage_words(N) * sizeof(uint64_t);
     // (set on every launch: the attribute belongs to the function on the CURRENT device, and a process may hold
     // contexts on several devices; the call costs a few microseconds)

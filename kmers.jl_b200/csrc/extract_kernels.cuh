@@ -47,6 +47,7 @@ struct ExtractParams {
     uint64_t gprm;       // group slots per read
     uint64_t it_dq, it_dr; // divmod(kBlockThreads, gprm): per-iteration advance of (r, gi)
     uint64_t read_bits;    // stride_units * unit_bits: stream bits from one read to the next (uniform offsets)
+    uint32_t aligned;      // uniform set whose windows per read are a multiple of G: item i IS flat group i (set_iteration_strides)
     // ragged locator
     const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
     const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
@@ -130,8 +131,13 @@ struct TileCursor {
         return p.seq_unit_off ? __ldg(p.seq_unit_off + rr) - p.unit_bias : rr * p.stride_units;
     }
 
-    // li0 = this thread's first local item of the tile (threadIdx.x for the strided item order)
+    // li0 = this thread's first local item of the tile (threadIdx.x for the strided item order);
+    // tile = index of the tile (blockIdx.x, except in compact_kernel, which takes its tiles from a ticket counter)
     KMC_DEV void init(const ExtractParams &p, uint64_t tile_base, TileShared<RAGGED> &sh, uint32_t li0)
+    {
+        init(p, tile_base, sh, li0, blockIdx.x);
+    }
+    KMC_DEV void init(const ExtractParams &p, uint64_t tile_base, TileShared<RAGGED> &sh, uint32_t li0, uint32_t tile)
     {
         seq_ibase = 0;
         if constexpr (!RAGGED) {
@@ -154,8 +160,8 @@ struct TileCursor {
                 r += d;
             }
         } else {
-            r_first = __ldg(p.tile_first + blockIdx.x);
-            const uint64_t r_last = __ldg(p.tile_first + blockIdx.x + 1);
+            r_first = __ldg(p.tile_first + tile);
+            const uint64_t r_last = __ldg(p.tile_first + tile + 1);
             const uint64_t n_meta = r_last - r_first + 1;
             const bool staged = n_meta <= kTileMetaCap;
             if (staged) {
@@ -218,6 +224,17 @@ struct TileCursor {
             }
             ubit = unit_off * p.unit_bits;
         } else {
+            if (p.aligned) {
+                // windows per read are a multiple of G (C2: 120 = 15 x 8): every group lies wholly inside one read, item i
+                // is flat group i and all G slots are windows.  One 32 x 32 -> 64-bit product instead of the two 64-bit
+                // products and the divisions-by-G bookkeeping below (60 of the 314 instructions per item, ncu r01).
+                q = item;
+                wbase = static_cast<int64_t>(static_cast<uint32_t>(gi) * static_cast<uint32_t>(G));
+                jlo = 0;
+                jhi = G;
+                ubit = static_cast<uint64_t>(static_cast<uint32_t>(r)) * static_cast<uint32_t>(p.read_bits);
+                return;
+            }
             // (recomputed per item: carrying f0 / ubit incrementally across the iterations measured 2 % slower
             // on the ALU-bound modes -- two more live 64-bit values per thread)
             f0 = r * p.wpr;
@@ -319,11 +336,16 @@ inline bool prefetch_enabled()
 }
 
 // per-iteration strides of the uniform locator (every launcher calls this before the launch)
-inline void set_iteration_strides(ExtractParams &p)
+// g = windows per work item of a uniform-layout launch (0: ragged, or a kernel that does not use the aligned form)
+inline void set_iteration_strides(ExtractParams &p, int g = 0)
 {
     p.it_dq = kBlockThreads / p.gprm;
     p.it_dr = kBlockThreads % p.gprm;
     p.read_bits = p.stride_units * p.unit_bits;
+    p.aligned = (g > 0 && !p.seq_unit_off && p.wpr > 0 && p.wpr % static_cast<uint64_t>(g) == 0 && p.gprm == p.wpr / g &&
+                 p.n_seqs < 0xffffffffull && p.read_bits < 0xffffffffull && p.gprm < 0xffffffffull)
+                    ? 1u
+                    : 0u;
 }
 
 
@@ -419,9 +441,8 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             }
 
             const uint64_t fbase = q * G; // flat index of slot 0
-            int64_t ibase = 0;            // 1-based start (within its sequence) of slot 0's window
-            if (p.out_index)
-                ibase = wbase + 1 + p.index_base + static_cast<int64_t>(cur.seq_ibase);
+            // 1-based start (within its sequence) of slot 0's window -- only the index-emitting branches evaluate it
+            auto ibase_of = [&]() -> int64_t { return wbase + 1 + p.index_base + static_cast<int64_t>(cur.seq_ibase); };
             const bool full = (jlo == 0) && (jhi == G);
             const bool tuple_rv = (MODE == MODE_FWRV) && p.aos;
             const bool tuple_ix = (p.out_index != nullptr) && p.aos;
@@ -442,6 +463,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             } else if (tuple_ix) {
                 // Tuple{Kmer,Int} = {u64[N]; i64} elements
                 uint64_t buf[G * (N + 1)];
+                const int64_t ibase = ibase_of();
 #pragma unroll
                 for (int j = 0; j < G; ++j) {
 #pragma unroll
@@ -465,6 +487,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
                 }
                 if (p.out_index) {
                     uint64_t ib[G];
+                    const int64_t ibase = ibase_of();
 #pragma unroll
                     for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(ibase + j);
                     store_words<G>(reinterpret_cast<uint64_t *>(p.out_index) + fbase, ib, jlo, jhi, fast, p.vec_ok);
@@ -516,7 +539,7 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
     const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
     if (tiles == 0) return cudaSuccess;
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    set_iteration_strides(p);
+    set_iteration_strides(p, RAGGED ? 0 : GroupOf<N>::G);
     p.pf_tiles = 0;
     if (SINK != SINK_BUCKETS && prefetch_enabled()) {
         // chunks of about kPfChunkBytes of source: tiles per chunk from the average source bytes per tile

@@ -149,6 +149,17 @@ ExtractLaunchFn strict_launcher(const Geometry &ge, int mode, bool hash, bool ra
     return nullptr;
 }
 
+LinLaunchFn lin_launcher(const Geometry &ge, bool hash, bool offsets)
+{
+    switch (ge.n_limbs) {
+    case 1: return get_lin_launcher_n1(ge.nx, hash, offsets);
+    case 2: return get_lin_launcher_n2(ge.nx, hash, offsets);
+    case 3: return get_lin_launcher_n3(ge.nx, hash, offsets);
+    case 4: return get_lin_launcher_n4(ge.nx, hash, offsets);
+    }
+    return nullptr;
+}
+
 CompactLaunchFn compact_launcher(const Geometry &ge, bool hash, bool ragged)
 {
     switch (ge.n_limbs) {
@@ -170,6 +181,8 @@ uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
     uint64_t need = 0;
     need += round_up(8 * (nb + 2), 256);     // rec32
     need += 3 * round_up(4 * (nb + 8), 256); // bad, vstart, err
+    need += 4 * kLinChunkWords + 256;        // vstart rounded up to whole chunks of the source-order compaction
+    if (mode == KMC_UNAMBIG) need += lin_scratch_bytes(32 * (nb + 2), s->n_seqs);
     need += 3 * 256;                         // err_flat, err_out, total
     need += layout_scratch_bytes(s);
     if (mode == KMC_UNAMBIG) {
@@ -203,7 +216,7 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     const uint64_t nb = ascii ? (s->n_words + 31) / 32 : (s->n_words + 1) / 2;
     uint32_t *rec = static_cast<uint32_t *>(scratch.take(8 * (nb + 2)));
     uint32_t *bad = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
-    uint32_t *vstart = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
+    uint32_t *vstart = static_cast<uint32_t *>(scratch.take(4 * (lin_chunks(32 * (nb + 2)) * kLinChunkWords + 8)));
     uint32_t *err = (ascii && st->unambig) ? static_cast<uint32_t *>(scratch.take(4 * (nb + 8))) : nullptr;
     if (ascii && st->unambig && !err) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
     st->err = err;
@@ -261,17 +274,30 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
         return KMC_OK;
     }
 
-    // UnambiguousKmers: the compaction kernel places its tiles itself; the survivors are counted up
-    // front only for callers that need the number before the k-mers exist
-    const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
-    st->total_dev = static_cast<unsigned long long *>(scratch.take(8));
-    st->tile_state = static_cast<unsigned long long *>(scratch.take(8 * (tiles + 1)));
-    if (!st->total_dev || !st->tile_state) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
-    if (count_first || !out) {
-        CU(cudaMemsetAsync(st->total_dev, 0, 8, stream));
-        CU(count_valid(st->p, !L.uniform_len, lay.g, st->total_dev, stream));
-        CU(cudaMemcpyAsync(&host_small[0], st->total_dev, 8, cudaMemcpyDeviceToHost, stream));
-        st->counted = true;
+    // UnambiguousKmers.  Sets whose sequences are ascending and disjoint in the buffer are compacted in source
+    // order (lincompact.cuh): the preparation masks the valid-start bits down to window starts and scans the
+    // survivors per chunk, so the total is known before the k-mers exist.  Any other layout goes through
+    // compact_kernel, which places its tiles itself (the survivors are then counted up front only for callers that
+    // need the number before the k-mers exist).
+    rc = lin_prepare(ctx, st->p, s, k, ge.g, nb + 2, known.linear, &host_small[8], stream, scratch, &st->lin);
+    if (rc) return rc;
+    if (st->lin.linear) {
+        st->total_dev = const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(st->lin.total_dev));
+        if (count_first || !out) {
+            CU(cudaMemcpyAsync(&host_small[0], st->total_dev, 8, cudaMemcpyDeviceToHost, stream));
+            st->counted = true;
+        }
+    } else {
+        const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
+        st->total_dev = static_cast<unsigned long long *>(scratch.take(8));
+        st->tile_state = static_cast<unsigned long long *>(scratch.take(8 * (tiles + 2)));
+        if (!st->total_dev || !st->tile_state) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+        if (count_first || !out) {
+            CU(cudaMemsetAsync(st->total_dev, 0, 8, stream));
+            CU(count_valid(st->p, !L.uniform_len, lay.g, st->total_dev, stream));
+            CU(cudaMemcpyAsync(&host_small[0], st->total_dev, 8, cudaMemcpyDeviceToHost, stream));
+            st->counted = true;
+        }
     }
     if (out && out->seq_out_offset) {
         uint64_t *cnt = static_cast<uint64_t *>(scratch.take(8 * (s->n_seqs + 1)));
@@ -331,12 +357,21 @@ int32_t fourbit_phase_b(kmc_ctx *ctx, FourBitState *st, const kmc_out *out, cuda
     ExtractParams p = st->p;
     int32_t rc = bind_outputs(ctx, out, KMC_UNAMBIG, st->flags, &p);
     if (rc) return rc;
-    const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
-    CompactParams cp{st->tile_state, reinterpret_cast<uint64_t *>(st->total_dev), out->capacity};
-    CU(cudaMemsetAsync(st->tile_state, 0, 8 * tiles, stream));
-    CompactLaunchFn fn = compact_launcher(st->ge, (st->flags & KMC_HASH_FX) != 0, !L.uniform_len);
-    if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
-    CU(fn(p, cp, stream));
+    const bool hash = (st->flags & KMC_HASH_FX) != 0;
+    if (st->lin.linear) {
+        LinParams lp = st->lin.lp;
+        lp.capacity = out->capacity;
+        LinLaunchFn fn = lin_launcher(st->ge, hash, st->lin.offsets);
+        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+        CU(fn(p, lp, stream));
+    } else {
+        const uint64_t tiles = (L.items + kTileItems - 1) / kTileItems;
+        CompactParams cp{st->tile_state, reinterpret_cast<uint64_t *>(st->total_dev), out->capacity};
+        CU(cudaMemsetAsync(st->tile_state, 0, 8 * (tiles + 1), stream)); // the look-back descriptors and the ticket counter
+        CompactLaunchFn fn = compact_launcher(st->ge, hash, !L.uniform_len);
+        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+        CU(fn(p, cp, stream));
+    }
     if (!st->counted) CU(cudaMemcpyAsync(&st->host_small[0], st->total_dev, 8, cudaMemcpyDeviceToHost, stream));
     return KMC_OK;
 }

@@ -16,9 +16,23 @@
 //     single pass (decoupled look-back over the tiles; aligned 256-bit stores from a staging buffer).
 #pragma once
 #include "fourbit_core.cuh"
+#include "lincompact.cuh"
 #include "plan.h"
 
 namespace kmc {
+
+// The source-order compaction's layout (lincompact.cuh, lin_prepare in valid_count.cu)
+struct LinPlan {
+    bool linear = false;  // the set's sequences are ascending and disjoint in the buffer: lin_compact_kernel runs
+    bool offsets = false; // the set gives per-sequence offsets
+    LinParams lp{};
+    const uint64_t *total_dev = nullptr; // device: the number of k-mers the set emits (last entry of the chunk scan)
+};
+bool lin_enabled();
+uint64_t lin_chunks(uint64_t n_positions);
+uint64_t lin_scratch_bytes(uint64_t n_symbols, uint64_t n_seqs);
+int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int k, int g_windows, uint64_t n_vstart_words,
+                    int known_linear, uint64_t *host_flag, cudaStream_t stream, Scratch &scratch, LinPlan *plan);
 
 // What one 4-bit extraction needs between its two phases.  Phase A enqueues the recoding (and, for
 // strict modes, the extraction) and leaves two words in `host_small` (pinned): [0] = number of k-mers
@@ -37,6 +51,7 @@ struct FourBitState {
     uint32_t *err = nullptr; // ASCII UnambiguousKmers: hard-error flags (bytes outside the skipping table)
     unsigned long long *tile_state = nullptr; // UnambiguousKmers: look-back descriptors of compact_kernel
     unsigned long long *total_dev = nullptr;  // UnambiguousKmers: emitted k-mers (device)
+    LinPlan lin;                              // UnambiguousKmers: the source-order compaction, when the layout allows it
     bool counted = false;                     // host_small[0] holds the count when phase A has completed
     uint64_t *err_out = nullptr; // device u64[3]: seq, 1-based pos, encoding
     uint64_t *host_small = nullptr;

@@ -202,6 +202,20 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
     if (hash && !ho->hash) return fail(ctx, KMC_E_BAD_ARG, "out.hash is NULL (KMC_HASH_FX)");
     if (want_index && !aos && !ho->index) return fail(ctx, KMC_E_BAD_ARG, "out.index is NULL (UNAMBIG, SoA)");
 
+    // UnambiguousKmers over a recoded source: are the sequences ascending and disjoint in the buffer?  (The device
+    // path would have to check its device-resident offsets and synchronise; here the offsets are host arrays.)
+    int host_linear = -1;
+    if (compacting && ragged_off && !single) {
+        host_linear = 1;
+        uint64_t prev_end = 0;
+        for (uint64_t r = 0; r < hs->n_seqs && host_linear; ++r) {
+            const uint64_t len = ragged_len ? hs->seq_len[r] : hs->uniform_len;
+            const uint64_t start = hs->seq_word_offset[r] * spw;
+            if (r && start < prev_end) host_linear = 0;
+            prev_end = start + (len >= K ? len - K + 1 : 0);
+        }
+    }
+
     // ---- slot buffers --------------------------------------------------------------------------
     uint64_t max_words = 0, max_out = 0, max_seq = 0;
     for (const Chunk &c : chunks) {
@@ -358,6 +372,7 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
         ds.seq_len = nullptr;
         uint64_t bias = 0;
         KnownTotals known;
+        known.linear = host_linear;
         if (single) {
             ds.uniform_len = c.len;
             ds.uniform_stride_words = c.nwords;

@@ -46,6 +46,9 @@ struct KnownTotals {
     // sum of what it writes to digest[0..1] (stream a) and digest[2..3] (hash stream) itself, instead of a second
     // pass that re-reads both streams
     unsigned long long *digest = nullptr;
+    // UnambiguousKmers over a recoded source: whether the sequences are ascending and disjoint in the buffer
+    // (1 / 0), or -1 when the caller does not know (device-resident offsets are then checked on the device)
+    int linear = -1;
 };
 
 // the fused fingerprint exists for the SoA forms of FwKmers / CanonicalKmers over 2-bit sources, K <= 64

@@ -106,20 +106,22 @@ def test_no_cpu_fallback_without_a_device():
         kc.CanonicalDNAMers(3, kc.LongDNA2("ACGTACGT")).collect()
 
 
-def test_header_is_plain_c_and_the_c_example_links(tmp_path):
-    """include/kmerscuda.h is C99 (what a cgo / ccall / ctypes binding needs), and examples/collect_canonical.c
-    builds against the shared library with gcc alone; without a device it reports that there is no CPU fallback."""
+def test_header_is_plain_c_and_the_c_examples_link(tmp_path):
+    """include/kmerscuda.h is C99 (what a cgo / ccall / ctypes binding needs), and the examples -- collect_canonical.c
+    (one kmc_extract_host call) and c5_group_count.c (the multi-GPU count + NCCL merge, no Python in the loop) -- build
+    against the shared library with gcc alone; without a device they report that there is no CPU fallback."""
     import shutil
     import subprocess
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     lib_dir = os.path.join(ROOT, "kmers.jl_b200")
-    exe = str(tmp_path / "collect_canonical")
-    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
-                    os.path.join(ROOT, "examples", "collect_canonical.c"), "-L", lib_dir, "-lkmerscuda",
-                    "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
-    if __import__("torch").cuda.is_available():
-        pytest.skip("the device path of the example is exercised by hand on the GPU box")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
-    assert r.returncode == 0
-    assert "ABI version 100" in r.stdout and "no CPU fallback" in r.stdout
+    for name in ("collect_canonical", "c5_group_count"):
+        exe = str(tmp_path / name)
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", name + ".c"), "-L", lib_dir, "-lkmerscuda",
+                        "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+        if __import__("torch").cuda.is_available():
+            continue  # the device path of the examples is exercised by tests/test_gpu_multi.py
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0
+        assert "ABI version 100" in r.stdout and "no CPU fallback" in r.stdout

@@ -232,3 +232,21 @@ def test_group_two_gpus_single_process():
         gk, gv = owned[r].items()
         assert np.array_equal(gk, uk[own == r]) and np.array_equal(gv.astype(np.int64), uc[own == r])
     g.close()
+
+
+def test_c_example_counts_and_merges_without_python(tmp_path):
+    """examples/c5_group_count.c: the C5 job (count on every GPU + NCCL merge inside the library) from plain C, on all
+    the GPUs of the box, at a small size; it checks the merged total and the equality of the tables itself."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "kmers.jl_b200")
+    exe = str(tmp_path / "c5_group_count")
+    subprocess.run(["gcc", "-std=c99", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c5_group_count.c"),
+                    "-L", lib_dir, "-lkmerscuda", "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    for bits in ("20", "27"):
+        r = subprocess.run([exe, "200000", bits], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "ok; identical on all" in r.stdout
