@@ -74,8 +74,11 @@ extern "C" {
                             where U (not T) is the fourth valid letter. */
 #define KMC_KMER4 0x40u  /* the k-mers are over a 4-bit alphabet, Kmer{DNAAlphabet{4},K,N} / Kmer{RNAAlphabet{4},K,N}
                             with N = cld(4K, 64) limbs, K <= KMC_MAX_K4: FW / FWRV / CANON from a 4-bit source
-                            (Copyable, FwKmers.jl:88-94, CanonicalKmers.jl:107-120; every symbol is allowed)
-                            or from a 2-bit source (TwoToFour, FwKmers.jl:96-102, CanonicalKmers.jl:122-129). */
+                            (Copyable, FwKmers.jl:88-94, CanonicalKmers.jl:107-120; every symbol is allowed),
+                            from a 2-bit source (TwoToFour, FwKmers.jl:96-102, CanonicalKmers.jl:122-129) or from
+                            ASCII bytes (AsciiEncode, FwKmers.jl:117-129, CanonicalKmers.jl:146-174: every IUPAC
+                            letter and the gap '-' in either case, T for DNA / U with KMC_RNA; any other byte in
+                            a sequence of at least K symbols is KMC_E_AMBIGUOUS). */
 #define KMC_DIGEST 0x10u /* kmc_extract_host only: also fingerprint what was written -- xor and wrapping
                             sum of the out.a words and of the out.hash words -> result->digest[4].
                             For FwKmers / CanonicalKmers over 2-bit sources (SoA, K <= 64) the extraction
@@ -168,6 +171,17 @@ int32_t kmc_extract(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t mode,
  * internal streams.  This is the call a Julia `collect(it)` replacement makes. */
 int32_t kmc_extract_host(kmc_ctx *ctx, const kmc_seqs *host_seqs, int32_t k, int32_t mode, uint32_t flags,
                          const kmc_out *host_out, kmc_result *result);
+
+/* collect(SpacedKmers{A,K,J}(seq)) for every sequence of the set (src/iterators/SpacedKmers.jl:22-139; each_codon =
+ * SpacedKmers{A,3,3}, :78-82): the k-mers at the 1-based starts 1, 1+J, 1+2J, ... -- div(L - K, J) + 1 per sequence
+ * of L >= K symbols (:36-40) -- concatenated in order into out.a (N limbs each), out.hash (KMC_HASH_FX) and
+ * optionally out.seq_out_offset.  Device buffers.  Every recoding scheme of the nucleotide alphabets
+ * (construction.jl:75-100): 2-bit / 4-bit / ASCII sources into 2-bit k-mers (K <= KMC_MAX_K) or, with KMC_KMER4,
+ * 4-bit k-mers (K <= KMC_MAX_K4); KMC_RNA as for kmc_extract.  A symbol that cannot be encoded INSIDE a sampled
+ * window is KMC_E_AMBIGUOUS (result->err_*); symbols between the windows of a step J > K are not read, as in the
+ * reference.  step < 1 is KMC_E_BAD_K ("J must be at least 1", SpacedKmers.jl:30). */
+int32_t kmc_extract_spaced(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t step, uint32_t flags,
+                           const kmc_out *out, kmc_result *result);
 
 /* fx_hash.(v, h0) over n k-mers of n_limbs limbs each already in device memory
  * (src/kmer.jl:255-261). */

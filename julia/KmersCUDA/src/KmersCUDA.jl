@@ -28,7 +28,7 @@ module KmersCUDA
 
 using BioSequences
 using Kmers
-using Kmers: FwKmers, FwRvIterator, CanonicalKmers, UnambiguousKmers, Kmer, derive_type
+using Kmers: FwKmers, FwRvIterator, CanonicalKmers, UnambiguousKmers, SpacedKmers, Kmer, derive_type
 using Libdl
 
 export fx_hash_device, hash_device, extract, set_library!, minhash_sketch, composition, minimizers, count_kmers,
@@ -331,6 +331,50 @@ function collect_ascii(it::AnyIter{A, K}, bytes::DenseBytes; ctx::Context = defa
     end
     resize!(out, res.n_written)
     return out
+end
+
+"""
+    KmersCUDA.collect(it::SpacedKmers{A,K,J}) -> Vector{Kmer{A,K,N}}
+
+`collect(SpacedKmers{A,K,J}(seq))` / `collect(each_codon(seq))` (src/iterators/SpacedKmers.jl:22-139): the k-mers at the
+starts 1, 1+J, 1+2J, ... through `kmc_extract_spaced`, for 2-bit and 4-bit k-mer alphabets over `LongSequence`,
+`LongSubSeq` and ASCII sources.  A symbol that cannot be encoded inside a sampled window throws the reference's
+`EncodeError`; symbols between the windows of a step J > K are never read (test/runtests.jl:866-867).
+"""
+function collect(it::SpacedKmers{A, K, J}; ctx::Context = default_context()) where {A <: NucleicAcidAlphabet, K, J}
+    T = derive_type(Kmer{A, K})
+    seq = it.seq
+    flags = (A <: NucleicAcidAlphabet{4} ? KMC_KMER4 : UInt32(0)) | (A <: RNAAlphabet ? KMC_RNA : UInt32(0))
+    res = KmcResult()
+    if seq isa NucSeq
+        data, wptr, nwords, len, first = seq_words(seq)
+        bits = src_bits(typeof(seq))
+        keep, host, unit_count = data, unsafe_wrap(Array, wptr, nwords), nwords
+    else
+        bytes = ascii_source(seq)
+        len, first, bits = length(bytes), UInt32(0), UInt32(8)
+        keep, host, unit_count = bytes, bytes, length(bytes)
+    end
+    n = len < K ? 0 : (len - K) ÷ J + 1                      # SpacedKmers.jl:36-40
+    out = DeviceVector{T}(ctx, n)
+    GC.@preserve keep begin
+        dsrc = upload(ctx, host isa Vector ? host : Vector{UInt8}(host))
+        try
+            s = Ref(KmcSeqs(Ptr{UInt64}(dsrc.ptr), unit_count, 1, C_NULL, C_NULL, len, max(unit_count, 1), bits, first))
+            o = Ref(KmcOut(Ptr{UInt64}(out.ptr), C_NULL, C_NULL, C_NULL, C_NULL, n, 0))
+            st = ccall((:kmc_extract_spaced, LIB[]), Int32,
+                (Ptr{Cvoid}, Ptr{KmcSeqs}, Int32, Int32, UInt32, Ptr{KmcOut}, Ref{KmcResult}), ctx.handle, s, K, J, flags, o, res)
+            if st == KMC_E_AMBIGUOUS && bits == UInt32(8)
+                throw(BioSequences.EncodeError(A(), repr(UInt8(res.err_sym))))
+            end
+            st == KMC_OK || throw_status(ctx, st, res, A)
+        finally
+            free!(dsrc)
+        end
+    end
+    v = Array(truncate!(out, res.n_written))
+    free!(out)
+    return v
 end
 
 "Number of elements `collect(it)` returns (runs the device count pass for 4-bit UnambiguousKmers)."

@@ -81,3 +81,15 @@ end
 @testset "LongSequence.data layout (what the device assumes; tests/golden pins it for the oracle)" begin
     @test LongDNA{2}("TAGCTAGGACA").data == [0x000000000004a363]
 end
+
+@testset "SpacedKmers / each_codon (reference: test/runtests.jl:849-889)" begin
+    for (s, A) in Any[("TA-NGAKATCGAWTAGA", DNAAlphabet{4}), ("AUGCUGAUGAGUCGUAG", RNAAlphabet{2})]
+        for (k, j) in ((3, 2), (2, 4), (3, 3)), src in (s, codeunits(s))
+            @test KmersCUDA.collect(SpacedKmers{A, k, j}(src)) == collect(SpacedKmers{A, k, j}(src))
+        end
+    end
+    @test KmersCUDA.collect(SpacedKmers{DNAAlphabet{2}, 4, 3}(rna"UAGUCGUAGUAG")) == collect(SpacedKmers{DNAAlphabet{2}, 4, 3}(rna"UAGUCGUAGUAG"))
+    @test KmersCUDA.collect(SpacedKmers{RNAAlphabet{4}, 2, 3}(dna"TAGCCWKMMNAGCTV")) == collect(SpacedKmers{RNAAlphabet{4}, 2, 3}(dna"TAGCCWKMMNAGCTV"))
+    @test_throws BioSequences.EncodeError KmersCUDA.collect(SpacedDNAMers{3, 4}("TAGAWWWW"))
+    @test KmersCUDA.collect(each_codon(DNA, "TGACGATCGAC")) == collect(each_codon(DNA, "TGACGATCGAC"))
+end

@@ -21,7 +21,7 @@ namespace {
 
 // (LUT entry format, AsciiLuts, make_luts: ascii_luts.h)
 
-__constant__ uint8_t c_luts[3][256];
+__constant__ uint8_t c_luts[5][256]; // strict DNA, strict RNA, skipping, 4-bit DNA, 4-bit RNA (ascii_luts.h)
 
 // 32 bytes -> 64 bits of 2-bit codes, 32 "not a base" flags, 32 error flags
 __device__ __forceinline__ void ascii_group(const uint8_t *__restrict__ bytes, uint64_t n_bytes, bool aligned, uint64_t g,
@@ -63,10 +63,11 @@ __device__ __forceinline__ void ascii_group(const uint8_t *__restrict__ bytes, u
 
 // One thread per group of 32 bytes: 2 x u32 of 2-bit codes, 1 x u32 of "not a base" flags, 1 x u32 of
 // error flags and, fused through shared memory (+ a recomputed 5-group halo), the valid-start word.
+// (rev: the codes once more in reversed symbol order, see recode_vstart_kernel in fourbit.cu)
 __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut, int k,
                                                            uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
                                                            uint32_t *__restrict__ err, uint32_t *__restrict__ vstart,
-                                                           uint64_t n_groups, uint64_t n_vstart)
+                                                           uint64_t n_groups, uint64_t n_vstart, uint32_t *__restrict__ rev)
 {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_bad[256 + 8];
@@ -80,8 +81,11 @@ __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__rest
         if (g < n_groups) {
             uint64_t codes;
             ascii_group(bytes, n_bytes, aligned, g, s_lut, codes, fb, fe);
-            reinterpret_cast<uint2 *>(rec)[g] = make_uint2(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32));
-            bad[g] = fb;
+            if (rec) reinterpret_cast<uint2 *>(rec)[g] = make_uint2(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32));
+            if (rev)
+                reinterpret_cast<uint2 *>(rev)[n_groups - 1 - g] =
+                    make_uint2(rev2_32(static_cast<uint32_t>(codes >> 32)), rev2_32(static_cast<uint32_t>(codes)));
+            if (bad) bad[g] = fb;
             if (err) err[g] = fe;
         }
         s_bad[threadIdx.x] = fb;
@@ -104,17 +108,72 @@ __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__rest
     }
 }
 
+// k-mers over a 4-bit alphabet from ASCII bytes (FwKmers.jl:117-129, CanonicalKmers.jl:146-174 with the FourBit branch
+// :160-162, SpacedKmers.jl:110-119): one thread per group of 32 bytes writes 2 x u64 of nibbles -- the layout of a
+// LongSequence{DNAAlphabet{4}}, which the Copyable 4 -> 4 kernels then read -- 32 error flags and, fused through shared
+// memory as above, the "K encodable symbols from here on" word.
+__global__ void __launch_bounds__(256) ascii4_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut, int k,
+                                                            uint64_t *__restrict__ nib, uint32_t *__restrict__ bad,
+                                                            uint32_t *__restrict__ vstart, uint64_t n_groups, uint64_t n_vstart)
+{
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_bad[256 + 8];
+    s_lut[threadIdx.x] = c_luts[lut][threadIdx.x];
+    __syncthreads();
+    const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * 256;
+    auto group = [&](uint64_t g, uint64_t &w0, uint64_t &w1) -> uint32_t {
+        uint32_t fe = 0;
+        w0 = w1 = 0;
+#pragma unroll 4
+        for (int t = 0; t < 32; ++t) {
+            const uint64_t b = 32 * g + t;
+            const uint32_t e = s_lut[b < n_bytes ? bytes[b] : 'A']; // past the end: never part of a window
+            const uint64_t code = e & 15u;
+            if (t < 16) w0 |= code << (4 * t); else w1 |= code << (4 * (t - 16));
+            fe |= (e >> 7) << t;
+        }
+        return fe;
+    };
+    {
+        const uint64_t g = g0 + threadIdx.x;
+        uint32_t fe = 0;
+        if (g < n_groups) {
+            uint64_t w0, w1;
+            fe = group(g, w0, w1);
+            nib[2 * g] = w0;
+            nib[2 * g + 1] = w1;
+            bad[g] = fe;
+        }
+        s_bad[threadIdx.x] = fe;
+    }
+    if (threadIdx.x < kRecodeHalo) {
+        const uint64_t g = g0 + 256 + threadIdx.x;
+        uint64_t w0, w1;
+        s_bad[256 + threadIdx.x] = g < n_groups ? group(g, w0, w1) : 0u;
+    }
+    __syncthreads();
+    const uint64_t g = g0 + threadIdx.x;
+    if (g < n_vstart) {
+        uint32_t a[6];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) a[d] = s_bad[threadIdx.x + d];
+        a[5] = 0;
+        vstart[g] = valid_start_word(a, k);
+    }
+}
+
 // UnambiguousKmers over ASCII reads EVERY byte of every sequence (even sequences shorter than K),
 // so any error byte fails the call: the first sequence that holds one.  One warp per sequence.
+// (min_len: the strict iterators never touch a sequence shorter than K, FwKmers.jl:62-66)
 __global__ void __launch_bounds__(256) seq_first_error_kernel(ExtractParams p, const uint32_t *__restrict__ err,
                                                               const uint64_t *__restrict__ seq_len, uint64_t uniform_len,
-                                                              unsigned long long *__restrict__ err_seq)
+                                                              uint64_t min_len, unsigned long long *__restrict__ err_seq)
 {
     const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p.n_seqs == 1) { // one long sequence: the whole grid strides over its flag words
         const uint64_t len = seq_len ? seq_len[0] : uniform_len;
-        if (len == 0) return;
+        if (len == 0 || len < min_len) return;
         const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[0] - p.unit_bias : 0;
         const uint64_t a = unit_off * (p.unit_bits >> 1) + p.first, b = a + len;
         const uint64_t threads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
@@ -131,7 +190,7 @@ __global__ void __launch_bounds__(256) seq_first_error_kernel(ExtractParams p, c
     }
     for (uint64_t r = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < p.n_seqs; r += warps) {
         const uint64_t len = seq_len ? seq_len[r] : uniform_len;
-        if (len == 0) continue;
+        if (len == 0 || len < min_len) continue;
         const uint64_t unit_off = p.seq_unit_off ? p.seq_unit_off[r] - p.unit_bias : r * p.stride_units;
         const uint64_t a = unit_off * (p.unit_bits >> 1) + p.first, b = a + len; // error bits [a, b)
         bool found = false;
@@ -177,8 +236,7 @@ __global__ void __launch_bounds__(256) resolve_ascii_error_kernel(ExtractParams 
 
 } // namespace
 
-cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k, uint32_t *rec, uint32_t *bad, uint32_t *err,
-                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream)
+static cudaError_t upload_luts()
 {
     static bool uploaded[64] = {};
     int dev = 0;
@@ -186,22 +244,42 @@ cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k,
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64 && !uploaded[dev]) {
         const AsciiLuts l = make_luts();
+        static_assert(sizeof(AsciiLuts) == sizeof(c_luts), "the constant-memory copy holds every table");
         e = cudaMemcpyToSymbol(c_luts, &l, sizeof l);
         if (e != cudaSuccess) return e;
         uploaded[dev] = true;
     }
+    return cudaSuccess;
+}
+
+// rna: U (not T) is the fourth base.  nib: 2 u64 per group of 32 bytes; bad / vstart as in ascii_recode.
+cudaError_t ascii4_recode(const uint8_t *bytes, uint64_t n_bytes, bool rna, int k, uint64_t *nib, uint32_t *bad, uint32_t *vstart,
+                          uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream)
+{
+    cudaError_t e = upload_luts();
+    if (e != cudaSuccess) return e;
+    ascii4_recode_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, rna ? 4 : 3, k, nib, bad,
+                                                                                           vstart, n_groups, n_vstart);
+    return cudaGetLastError();
+}
+
+cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k, uint32_t *rec, uint32_t *bad, uint32_t *err,
+                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev)
+{
+    cudaError_t e = upload_luts();
+    if (e != cudaSuccess) return e;
     ascii_recode_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, lut, k, rec, bad, err,
-                                                                                          vstart, n_groups, n_vstart);
+                                                                                          vstart, n_groups, n_vstart, rev);
     return cudaGetLastError();
 }
 
 cudaError_t ascii_first_error_seq(const ExtractParams &p, const uint32_t *err, const uint64_t *seq_len, uint64_t uniform_len,
-                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream)
+                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream, uint64_t min_len)
 {
     if (p.n_seqs == 0) return cudaSuccess;
     const uint64_t want = p.n_seqs == 1 ? static_cast<uint64_t>(sm_count) * 32 : (p.n_seqs * 32 + 255) / 256;
     const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 32 ? want : static_cast<uint64_t>(sm_count) * 32);
-    seq_first_error_kernel<<<grid, 256, 0, stream>>>(p, err, seq_len, uniform_len, err_seq);
+    seq_first_error_kernel<<<grid, 256, 0, stream>>>(p, err, seq_len, uniform_len, min_len, err_seq);
     return cudaGetLastError();
 }
 

@@ -8,14 +8,28 @@ namespace kmc {
 // LUT entry: bits 0-1 = 2-bit code, bit 6 = skip (ambiguity code / gap), bit 7 = error
 constexpr uint8_t kSkip = 0x40, kErr = 0x80;
 
+// the 4-bit tables (k-mers over DNAAlphabet{4} / RNAAlphabet{4} from ASCII sources): bits 0-3 = the 4-bit encoding,
+// bit 7 = error
 struct AsciiLuts {
-    uint8_t strict_dna[256], strict_rna[256], skipping[256];
+    uint8_t strict_dna[256], strict_rna[256], skipping[256], dna4[256], rna4[256];
 };
 
 inline AsciiLuts make_luts()
 {
     AsciiLuts l;
-    for (int i = 0; i < 256; ++i) l.strict_dna[i] = l.strict_rna[i] = l.skipping[i] = kErr;
+    for (int i = 0; i < 256; ++i) l.strict_dna[i] = l.strict_rna[i] = l.skipping[i] = l.dna4[i] = l.rna4[i] = kErr;
+    // BioSequences.ascii_encode of a 4-bit alphabet (restated, BioSequences v3 / BioSymbols): every symbol of the
+    // alphabet -- the gap, A C M G R S V T/U W Y H K D B N in encoding order 0..15 -- in either case
+    {
+        const char *sym4 = "-ACMGRSVTWYHKDBN";
+        for (int e = 0; e < 16; ++e) {
+            const char c = sym4[e];
+            const char lower = (c >= 'A' && c <= 'Z') ? static_cast<char>(c | 0x20) : c;
+            const char cr = c == 'T' ? 'U' : c, lr = c == 'T' ? 'u' : lower;
+            l.dna4[static_cast<uint8_t>(c)] = l.dna4[static_cast<uint8_t>(lower)] = static_cast<uint8_t>(e);
+            l.rna4[static_cast<uint8_t>(cr)] = l.rna4[static_cast<uint8_t>(lr)] = static_cast<uint8_t>(e);
+        }
+    }
     const char *dna = "ACGT", *rna = "ACGU";
     for (int c = 0; c < 4; ++c) {
         l.strict_dna[static_cast<uint8_t>(dna[c])] = l.strict_dna[static_cast<uint8_t>(dna[c] | 0x20)] = static_cast<uint8_t>(c);

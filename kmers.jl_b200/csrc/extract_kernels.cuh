@@ -29,6 +29,22 @@ constexpr int kBlockThreads = 256;
 constexpr int kTileIters = 8;                                // work items per thread per tile
 constexpr int kTileItems = kBlockThreads * kTileIters;       // work items per block
 
+// EXPERIMENT ("measure a TMA bulk store, do not argue it"): with -DKMC_TMA_STORE=1 the SoA streams
+// of aligned uniform sets (C2) leave the kernel as 1-D bulk copies, cp.async.bulk.global.shared::cta: every warp stages
+// the 256 elements of a step in shared memory (2 KB per stream, double-buffered) and one lane issues one bulk store per
+// stream.  Off by default: the measured A/B is in profiles/r02_ab_tma_store.txt and DESIGN.md 3.1.
+#ifndef KMC_TMA_STORE
+#define KMC_TMA_STORE 0
+#endif
+constexpr int kTmaStageBytes = 2 /*buffers*/ * 2 /*streams*/ * 32 * 8 * 8; // per warp, one-limb k-mers (G = 8)
+
+KMC_DEV void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(static_cast<uint32_t>(__cvta_generic_to_shared(ssrc))), "r"(bytes), "l"(0x12F0000000000000ull)
+                 : "memory");
+}
+
 struct ExtractParams {
     const uint32_t *w32; // sequence stream viewed as 32-bit words
     int64_t nw32;        // addressable 32-bit words (loads are clamped into it)
@@ -441,6 +457,34 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
             }
 
             const uint64_t fbase = q * G; // flat index of slot 0
+#if KMC_TMA_STORE
+            // (a warp whose last lane is past the end takes the ordinary stores: its lanes have left the loop)
+            const bool warp_full = tile_base + static_cast<uint64_t>(it) * kBlockThreads + (threadIdx.x | 31u) < n_items;
+            if (N == 1 && SINK == SINK_STREAMS && MODE != MODE_FWRV && p.aligned && p.vec_ok && !p.out_index && warp_full) {
+                // the warp's 32 items are 256 consecutive elements of every stream: lane l's 8 go to bytes [64 l, 64 l + 64)
+                extern __shared__ __align__(128) unsigned char s_tma[];
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                unsigned char *buf = s_tma + warp * kTmaStageBytes + (it & 1) * (kTmaStageBytes / 2);
+                if (it >= 2) { // the bulk copies of step it - 2 have finished reading this buffer
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
+                uint64_t *sa = reinterpret_cast<uint64_t *>(buf) + lane * G, *sh = sa + 32 * G;
+#pragma unroll
+                for (int j = 0; j < G; j += 2) {
+                    *reinterpret_cast<ulonglong2 *>(sa + j) = make_ulonglong2(a[j][0], a[j + 1][0]);
+                    if (HASH) *reinterpret_cast<ulonglong2 *>(sh + j) = make_ulonglong2(h[j], h[j + 1]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the bulk copy
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(p.out_a + fbase, buf, 32 * G * 8); // lane 0's fbase is the warp's first element
+                    if (HASH) bulk_store(p.out_hash + fbase, buf + 32 * G * 8, 32 * G * 8);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                goto next_item;
+            }
+#endif
             // 1-based start (within its sequence) of slot 0's window -- only the index-emitting branches evaluate it
             auto ibase_of = [&]() -> int64_t { return wbase + 1 + p.index_base + static_cast<int64_t>(cur.seq_ibase); };
             const bool full = (jlo == 0) && (jhi == G);
@@ -499,6 +543,9 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     next_item:
         cur.advance(p);
     }
+#if KMC_TMA_STORE
+    if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory stays valid until read
+#endif
     if (DIGEST) {
         // one set of atomics per block (same-address atomics serialise in L2)
         __shared__ uint64_t s_dg[4][kBlockThreads / 32];
@@ -548,8 +595,17 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
         p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
     }
     if (DIGEST && !p.digest) return cudaErrorInvalidValue;
+    size_t smem = 0;
+#if KMC_TMA_STORE
+    if (N == 1 && SINK == SINK_STREAMS && MODE != MODE_FWRV) {
+        smem = static_cast<size_t>(kBlockThreads / 32) * kTmaStageBytes;
+        cudaError_t e = cudaFuncSetAttribute(extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS, DIGEST>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
+#endif
     extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS, DIGEST>
-        <<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
+        <<<static_cast<unsigned>(tiles), kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -17,10 +17,12 @@ constexpr int kCountLayoutG = 32; // windows per work item when the survivors ar
 // uncertainty flags -- and, fused, the group's valid-start word: the block keeps its 256 flag words
 // (+ a 5-word halo recomputed from the neighbouring block's source words) in shared memory, so the
 // flags are never re-read from global memory and no second pass is launched.
+// rev (optional): the same codes as one stream in REVERSED symbol order -- group g goes, its 32 symbols reversed, to
+// 64-bit word n_groups - 1 - g -- in which the forward k-mer of every window is a plain run of 2K bits (lincompact.cuh).
 __global__ void __launch_bounds__(256) recode_vstart_kernel(const uint64_t *__restrict__ words, uint64_t n_words, int k,
                                                             uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
                                                             uint32_t *__restrict__ vstart, uint64_t n_groups,
-                                                            uint64_t n_vstart)
+                                                            uint64_t n_vstart, uint32_t *__restrict__ rev)
 {
     __shared__ uint32_t s_bad[256 + 8];
     const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * 256;
@@ -44,9 +46,10 @@ __global__ void __launch_bounds__(256) recode_vstart_kernel(const uint64_t *__re
             uint32_t c0, c1, f0, f1;
             recode_word(w0, c0, f0);
             recode_word(w1, c1, f1);
-            reinterpret_cast<uint2 *>(rec)[g] = make_uint2(c0, c1);
+            if (rec) reinterpret_cast<uint2 *>(rec)[g] = make_uint2(c0, c1);
+            if (rev) reinterpret_cast<uint2 *>(rev)[n_groups - 1 - g] = make_uint2(rev2_32(c1), rev2_32(c0));
             f = f0 | (f1 << 16);
-            bad[g] = f;
+            if (bad) bad[g] = f;
         }
         s_bad[threadIdx.x] = f;
     }
@@ -152,10 +155,10 @@ ExtractLaunchFn strict_launcher(const Geometry &ge, int mode, bool hash, bool ra
 LinLaunchFn lin_launcher(const Geometry &ge, bool hash, bool offsets)
 {
     switch (ge.n_limbs) {
-    case 1: return get_lin_launcher_n1(ge.nx, hash, offsets);
-    case 2: return get_lin_launcher_n2(ge.nx, hash, offsets);
-    case 3: return get_lin_launcher_n3(ge.nx, hash, offsets);
-    case 4: return get_lin_launcher_n4(ge.nx, hash, offsets);
+    case 1: return get_lin_launcher_n1(hash, offsets);
+    case 2: return get_lin_launcher_n2(hash, offsets);
+    case 3: return get_lin_launcher_n3(hash, offsets);
+    case 4: return get_lin_launcher_n4(hash, offsets);
     }
     return nullptr;
 }
@@ -173,6 +176,14 @@ CompactLaunchFn compact_launcher(const Geometry &ge, bool hash, bool ragged)
 
 } // namespace
 
+cudaError_t fourbit_recode(const uint64_t *words, uint64_t n_words, int k, uint32_t *rec, uint32_t *bad, uint32_t *vstart,
+                           uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev)
+{
+    recode_vstart_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(words, n_words, k, rec, bad, vstart, n_groups,
+                                                                                           n_vstart, rev);
+    return cudaGetLastError();
+}
+
 uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
 {
     (void)k;
@@ -182,7 +193,7 @@ uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
     need += round_up(8 * (nb + 2), 256);     // rec32
     need += 3 * round_up(4 * (nb + 8), 256); // bad, vstart, err
     need += 4 * kLinChunkWords + 256;        // vstart rounded up to whole chunks of the source-order compaction
-    if (mode == KMC_UNAMBIG) need += lin_scratch_bytes(32 * (nb + 2), s->n_seqs);
+    if (mode == KMC_UNAMBIG) need += lin_scratch_bytes(32 * (nb + 2), s->n_seqs) + round_up(8 * (nb + 2), 256); // + the reversed stream
     need += 3 * 256;                         // err_flat, err_out, total
     need += layout_scratch_bytes(s);
     if (mode == KMC_UNAMBIG) {
@@ -214,25 +225,29 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     const bool ascii = s->src_bits == 8;
     // groups of 32 symbols = u32 words of flag bits (4-bit: pairs of source words; ASCII: 32 bytes)
     const uint64_t nb = ascii ? (s->n_words + 31) / 32 : (s->n_words + 1) / 2;
-    uint32_t *rec = static_cast<uint32_t *>(scratch.take(8 * (nb + 2)));
-    uint32_t *bad = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
+    // UnambiguousKmers over a uniform set that the source-order compaction will take for certain (lin_uniform_ok: no
+    // device-side check is needed) reads neither the forward stream nor the flags: the recoding pass then writes only
+    // the reversed stream and the valid-start bits -- a third of its traffic less
+    const bool rev_only = st->unambig && out && lin_enabled() && known.linear != 0 && lin_uniform_ok(s, k);
+    uint32_t *rec = rev_only ? nullptr : static_cast<uint32_t *>(scratch.take(8 * (nb + 2)));
+    uint32_t *bad = rev_only ? nullptr : static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
     uint32_t *vstart = static_cast<uint32_t *>(scratch.take(4 * (lin_chunks(32 * (nb + 2)) * kLinChunkWords + 8)));
     uint32_t *err = (ascii && st->unambig) ? static_cast<uint32_t *>(scratch.take(4 * (nb + 8))) : nullptr;
     if (ascii && st->unambig && !err) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+    // UnambiguousKmers: the source-order compaction reads its k-mers from the stream in reversed symbol order
+    uint32_t *rev = (st->unambig && out && lin_enabled()) ? static_cast<uint32_t *>(scratch.take(8 * (nb + 2))) : nullptr;
     st->err = err;
     unsigned long long *err_flat = static_cast<unsigned long long *>(scratch.take(8));
     uint64_t *err_out = static_cast<uint64_t *>(scratch.take(24));
-    if (!rec || !bad || !vstart || !err_flat || !err_out) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
+    if ((!rev_only && (!rec || !bad)) || !vstart || !err_flat || !err_out) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
     st->bad = bad;
     st->err_out = err_out;
 
     if (ascii) {
         const int lut = st->unambig ? 2 : ((flags & KMC_RNA) ? 1 : 0);
-        CU(ascii_recode(reinterpret_cast<const uint8_t *>(s->words), s->n_words, lut, k, rec, bad, err, vstart, nb, nb + 2, stream));
+        CU(ascii_recode(reinterpret_cast<const uint8_t *>(s->words), s->n_words, lut, k, rec, bad, err, vstart, nb, nb + 2, stream, rev));
     } else {
-        recode_vstart_kernel<<<static_cast<unsigned>((nb + 2 + 255) / 256), 256, 0, stream>>>(s->words, s->n_words, k, rec, bad,
-                                                                                             vstart, nb, nb + 2);
-        CU(cudaGetLastError());
+        CU(fourbit_recode(s->words, s->n_words, k, rec, bad, vstart, nb, nb + 2, stream, rev));
     }
 
     // the set is laid out for the extraction / compaction kernel's G; a count-only call (out == NULL)
@@ -279,8 +294,11 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     // survivors per chunk, so the total is known before the k-mers exist.  Any other layout goes through
     // compact_kernel, which places its tiles itself (the survivors are then counted up front only for callers that
     // need the number before the k-mers exist).
-    rc = lin_prepare(ctx, st->p, s, k, ge.g, nb + 2, known.linear, &host_small[8], stream, scratch, &st->lin);
+    rc = lin_prepare(ctx, st->p, s, k, nb + 2, rev ? known.linear : 0, &host_small[8], stream, scratch, &st->lin);
     if (rc) return rc;
+    st->lin.lp.rev32 = rev;
+    st->lin.lp.t_syms = 32 * nb;
+    if (rev_only && !st->lin.linear) return fail(ctx, KMC_E_BAD_ARG, "internal: the source-order compaction declined a set it had accepted");
     if (st->lin.linear) {
         st->total_dev = const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(st->lin.total_dev));
         if (count_first || !out) {

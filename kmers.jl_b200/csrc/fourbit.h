@@ -29,9 +29,10 @@ struct LinPlan {
     const uint64_t *total_dev = nullptr; // device: the number of k-mers the set emits (last entry of the chunk scan)
 };
 bool lin_enabled();
+bool lin_uniform_ok(const kmc_seqs *s, int k);
 uint64_t lin_chunks(uint64_t n_positions);
 uint64_t lin_scratch_bytes(uint64_t n_symbols, uint64_t n_seqs);
-int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int k, int g_windows, uint64_t n_vstart_words,
+int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int k, uint64_t n_vstart_words,
                     int known_linear, uint64_t *host_flag, cudaStream_t stream, Scratch &scratch, LinPlan *plan);
 
 // What one 4-bit extraction needs between its two phases.  Phase A enqueues the recoding (and, for
@@ -68,10 +69,20 @@ constexpr int kRecodeHalo = 5; // flag words beyond a group that its windows can
 // ascii.cu: byte sources (AsciiEncode).  lut: 0 = strict DNAAlphabet{2}, 1 = strict RNAAlphabet{2},
 // 2 = the UnambiguousKmers skipping table.  n_groups = groups of 32 bytes.
 // Writes rec / bad / err for the groups [0, n_groups) and the valid-start words [0, n_vstart).
+// rev (optional, both recoding passes): the codes once more as a stream in REVERSED symbol order (2 u32 per group)
 cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k, uint32_t *rec, uint32_t *bad, uint32_t *err,
-                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream);
+                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev = nullptr);
+// the first sequence (of at least min_len symbols) that holds a flagged byte -> atomicMin into *err_seq
 cudaError_t ascii_first_error_seq(const ExtractParams &p, const uint32_t *err, const uint64_t *seq_len, uint64_t uniform_len,
-                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream);
+                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream, uint64_t min_len = 0);
+// ASCII bytes -> nibbles of a 4-bit alphabet (2 u64 per group of 32 bytes) + error flags + the valid-start words
+cudaError_t ascii4_recode(const uint8_t *bytes, uint64_t n_bytes, bool rna, int k, uint64_t *nib, uint32_t *bad, uint32_t *vstart,
+                          uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream);
+// fourbit.cu: the FourToTwo recoding pass (2-bit codes, uncertainty flags, valid-start words); n_groups = groups of 32 symbols
+cudaError_t fourbit_recode(const uint64_t *words, uint64_t n_words, int k, uint32_t *rec, uint32_t *bad, uint32_t *vstart,
+                           uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev = nullptr);
+// kmer4.cu: TwoToFour, every 2-bit source word -> 128 bits of one-hot nibbles
+cudaError_t expand_two_to_four(const uint64_t *words, uint64_t n_words, void *wide, cudaStream_t stream);
 cudaError_t ascii_resolve_error(const ExtractParams &p, const uint8_t *bytes, const uint32_t *err, const uint64_t *seq_len,
                                 uint64_t uniform_len, uint64_t r, uint64_t *err_out, cudaStream_t stream);
 

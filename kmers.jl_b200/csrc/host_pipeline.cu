@@ -402,6 +402,12 @@ static int32_t run_pipeline(kmc_ctx *ctx, const kmc_seqs *hs, int32_t k, int32_t
             if (fused_digest) known.digest = reinterpret_cast<unsigned long long *>(ctx->dev_small);
             st = kmer4 ? extract_device_kmer4(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch)
                        : extract_device(ctx, &ds, k, mode, flags, &dout, &r, sm, known, bias, false, scratch);
+            if (st == KMC_E_AMBIGUOUS) { // 4-bit k-mers from ASCII bytes: a byte that is no symbol of the alphabet
+                result->n_written = 0;
+                result->err_seq = single ? 0 : c.seq0 + r.err_seq;
+                result->err_pos = r.err_pos + (single ? static_cast<uint64_t>(c.index_base) : 0);
+                result->err_sym = r.err_sym;
+            }
             if (st) return st;
             st = digest_chunk(c, sl, c.nout);
             if (st) return st;

@@ -8,24 +8,29 @@
 //
 //   lin_prepare   lays the candidate window starts out as POSITIONS p = 0, 1, 2, ... and leaves one bit per
 //                 position: "a window of a sequence starts here and its K symbols are certain".
-//                   uniform sets   position p = (sequence r, offset u) with u < W8 = windows per sequence
-//                                  rounded up to the item width G: the tails (last K-1 symbols) and the padding
-//                                  between sequences are not positions at all, and an item of G positions never
-//                                  straddles two sequences;
+//                   uniform sets   position p = (sequence, window) = divmod(p, windows per sequence): the tails
+//                                  (last K-1 symbols) and the padding between sequences are not positions at all;
 //                   sets with      position = symbol index in the recoded stream; the valid-start bits are
 //                   offsets        masked in place down to the window starts of the sequences.
 //                 The positions are cut into chunks of 2048; one popcount per chunk and ONE small exclusive scan
 //                 give every chunk its place in the output -- and the total, before a single k-mer exists;
-//   this kernel   one warp per chunk, no cooperation between warps or blocks at all: G positions per lane and
-//                 step, k-mers from the closed form of extract_kernel (one block load, static funnel shifts),
-//                 survivors compacted through a per-warp staging buffer so that the streams go out as ALIGNED
-//                 256-bit stores whatever the survivor pattern is.
+//   this kernel   one warp per chunk, no cooperation between warps or blocks and NO shared memory: a step takes
+//                 the 32 positions of one word of bits, lane l the l-th.  The survivors of a step are consecutive
+//                 elements of the output, so a lane's rank among them (a popcount of the bits below it) is its
+//                 place, and the warp's stores of a step are one contiguous run per stream.
+//                 The k-mer of a position comes out of the REVERSED stream the recoding pass writes beside the
+//                 forward one: symbol i at position T - 1 - i, so that the K symbols of a window, first symbol
+//                 highest -- the Kmer layout (kmer.jl:32-51) -- are a plain run of 2K bits: three overlapping
+//                 words (the lanes of a step read the same three or four words: one L1 wavefront each), two
+//                 funnel shifts and a mask per limb.  No bit reversal, no per-window block to amortise.
 //
-// It replaces compact_kernel's flat-window walk (two item locates per work item, a block scan between two
-// barriers and a decoupled look-back that spins on its predecessors), with no forward-progress assumption about
-// the block scheduler.  compact_kernel stays for sets whose sequences overlap or are out of order in the buffer.
+// History (profiles/r02_c3_*): the flat-window look-back kernel (compact_kernels.cuh) ran 2.5 G warp instructions per
+// 10 M reads with a block scan between two barriers; a first source-order kernel with G positions per lane and a
+// staging buffer in shared memory got that to 2.3 G but moved the bound to the L1 data pipe (87-90 % busy: every
+// survivor crosses shared memory once in each direction, 480 M wavefronts against 220 M ideal).  This form has no
+// staging to pay for.  compact_kernel stays for sets whose sequences overlap or are out of order in the buffer.
 #pragma once
-#include "compact_kernels.cuh"
+#include "extract_kernels.cuh"
 
 namespace kmc {
 
@@ -33,324 +38,227 @@ constexpr int kLinChunkPos = 2048;                 // positions per warp chunk
 constexpr int kLinChunkWords = kLinChunkPos / 32;  // u32 words of position bits per chunk
 constexpr int kLinWarps = kBlockThreads / 32;      // chunks per block
 
-#ifndef KMC_LIN_MIN_BLOCKS
-#define KMC_LIN_MIN_BLOCKS 4
-#endif
-
 struct LinParams {
-    const uint32_t *bits;        // one bit per position (uniform sets: packed by lin_prepare; offsets: the masked valid-start bits)
+    const uint32_t *bits;        // one bit per position (uniform sets: gathered by lin_prepare; offsets: the masked valid-start bits)
     const uint64_t *chunk_off;   // [n_chunks + 1] exclusive scan of the survivors per chunk
     const uint64_t *chunk_first; // offsets given: [n_chunks + 1] sequence that owns the chunk's first symbol (0 if none yet)
+    const uint32_t *rev32;       // the 2-bit codes in reversed symbol order: symbol i at symbol position t_syms - 1 - i
+    uint64_t t_syms;             // symbols in the reversed stream (a multiple of 32)
     uint64_t n_chunks;
     uint64_t capacity;           // elements the output buffers hold; nothing is written beyond
     uint64_t stride_syms;        // uniform sets: symbols from one sequence's start to the next
-    uint32_t w8;                 // uniform sets: positions per sequence (windows rounded up to G)
-    float inv_w8;                // a little below 1 / w8 (used when w8 < 4096)
+    uint32_t w8;                 // uniform sets: positions (= windows) per sequence
+    uint32_t jump;               // uniform sets: stride_syms - w8, the symbols between two sequences' windows
     uint32_t spu;                // symbols per offset unit (16: 4-bit source words, 1: ASCII bytes)
 };
 
-// staging index: two pad words per 16 keep pairs 16-byte aligned (128-bit shared-memory accesses) and spread
-// both the lanes' runs (G*E words apart) and the aligned quads of the read-out over all banks
-KMC_DEV uint32_t lin_slot(uint32_t w) { return w + 2u * (w >> 4); }
-
-constexpr int lin_stage_words(int n)
+// Predicated loads / stores without a memory clobber: the kernel below is straight-line code for two steps at a time, and
+// the compiler is free to move the loads of the second step above the stores of the first (they never alias: the loads
+// are read-only source data).
+KMC_DEV uint32_t ldg_if(const uint32_t *p, uint32_t on)
 {
-    const int w = 32 * group_of(n) * (n + 1) + 8; // + the misalignment of the first word and the read-out's last quad
-    return ((w + 2 * (w >> 4) + 4) + 1) & ~1;
+    uint32_t v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(on));
+    return v;
+}
+KMC_DEV void stg64_if(uint64_t *p, uint64_t v, uint32_t on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.L1::no_allocate.L2::cache_hint.u64 [%0], %1, %3;\n\t}" ::"l"(p), "l"(v),
+                 "r"(on), "l"(kEvictFirst));
+}
+KMC_DEV void stg128_if(uint64_t *p, uint64_t a, uint64_t b, uint32_t on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.L1::no_allocate.L2::cache_hint.v2.u64 [%0], {%1,%2}, %4;\n\t}" ::"l"(p),
+                 "l"(a), "l"(b), "r"(on), "l"(kEvictFirst));
 }
 
-KMC_DEV void sts128_if(uint32_t saddr, uint64_t a, uint64_t b, uint32_t on)
+// N limbs (head first) of a window: 2K bits of the reversed stream from bit offset d (may be negative) relative to
+// the byte address w0 on
+template <int N>
+KMC_DEV void lin_kmer(const char *__restrict__ w0, int32_t d, uint64_t head_mask, uint32_t on, uint64_t (&limb)[N])
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.v2.u64 [%0], {%1, %2};\n\t}" ::"r"(saddr), "l"(a), "l"(b), "r"(on)
-                 : "memory");
-}
-
-// Where this lane's survivors go in the staging buffer of a stream with E words per element whose first output
-// word is misaligned by `a` words against 32 bytes: slot j (if it survives) -> shared-memory byte address addr[j].
-// Computed once per step and used by every stream of the same E (the k-mer, index and hash streams of the SoA
-// layout share them: their base pointers are 32-byte aligned, so they share the misalignment too).
-template <int E, int G>
-KMC_DEV void lin_stage_addrs(uint32_t sbase, uint32_t a, uint32_t x, uint32_t m, uint32_t (&addr)[G])
-{
-    uint32_t w = a + x * E;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(w0 + static_cast<int64_t>(d >> 5) * 4); // arithmetic shift: floor
+    const uint32_t sh = static_cast<uint32_t>(d) & 31u;
+    uint32_t x[2 * N + 1];
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
-        addr[j] = sbase + 8u * lin_slot(w);
-        w += ((m >> j) & 1u) * E;
+    for (int i = 0; i <= 2 * N; ++i) x[i] = ldg_if(w + i, on); // (the word past the last needed one is readable: the stream is padded)
+#pragma unroll
+    for (int m = 0; m < N; ++m) { // m = 0 is the least significant limb
+        uint64_t v = pack64(__funnelshift_r(x[2 * m], x[2 * m + 1], sh), __funnelshift_r(x[2 * m + 1], x[2 * m + 2], sh));
+        if (m == N - 1) v &= head_mask;
+        limb[N - 1 - m] = v;
     }
 }
 
-// One stream of one warp step: the lane's G elements v (E words each) to the staging buffer at addr[], then the
-// warp's c * E words -- elements [o, o + c) of the stream -- to global memory: aligned quads as 256-bit stores, the
-// at most three words before the first and after the last aligned quad one by one.
-template <int E, int G>
-KMC_DEV void lin_emit(uint64_t *__restrict__ gbase, uint64_t o, uint32_t c, uint32_t a, uint32_t m, const uint32_t (&addr)[G],
-                      const uint64_t (&v)[G * E], const uint64_t *__restrict__ stage, uint32_t sbase, int lane)
+// CNT consecutive words to p (8-byte aligned; 16-byte stores where the address allows), if `on`
+template <int CNT> KMC_DEV void lin_store(uint64_t *p, const uint64_t (&v)[CNT], uint32_t on)
 {
-    const bool wide = (E % 2 == 0) && (a & 1u) == 0; // warp-uniform: elements are 16-byte aligned in the staging buffer
+    if (CNT % 2 == 0) {
+        const uint32_t al = (reinterpret_cast<uintptr_t>(p) & 15) == 0 ? on : 0u, un = on & ~al;
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
-        const uint32_t on = (m >> j) & 1u;
-        if (E == 1) {
-            sts64_if(addr[j], v[j], on);
-        } else if (E == 2 && wide) {
-            sts128_if(addr[j], v[2 * j], v[2 * j + 1], on); // an aligned pair never straddles a 16-word run
-        } else {
-            // word i of the element lies i words on, plus the two pad words if it has crossed into the next 16-word
-            // run: a padded index is 18 * (w >> 4) + (w & 15), so the element's place in its run is (index mod 18)
-            const uint32_t r15 = ((addr[j] - sbase) >> 3) % 18u;
-            if (wide) {
+        for (int i = 0; i + 1 < CNT; i += 2) stg128_if(p + i, v[i], v[i + 1], al);
+        if (un) { // an output buffer that is only 8-byte aligned: rare
 #pragma unroll
-                for (int i = 0; i + 1 < E; i += 2)
-                    sts128_if(addr[j] + 8u * (i + 2u * ((r15 + i) >> 4)), v[j * E + i], v[j * E + i + 1], on);
-            } else {
-#pragma unroll
-                for (int i = 0; i < E; ++i) sts64_if(addr[j] + 8u * (i + 2u * ((r15 + i) >> 4)), v[j * E + i], on);
-            }
+            for (int i = 0; i < CNT; ++i) stg64_if(p + i, v[i], 1u);
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) stg64_if(p + i, v[i], on);
     }
-    __syncwarp();
-    const uint32_t end = a + c * E;
-    uint64_t *g0 = gbase + (o * E - a); // 32-byte aligned
-    const uint32_t q_lo = (a + 3u) & ~3u, q_hi = end & ~3u;
-    for (uint32_t t = q_lo + 4u * lane; t < q_hi; t += 128u) {
-        const uint32_t s = lin_slot(t); // t is a multiple of 4: the quad lies inside one 16-word run, 16-byte aligned
-        const ulonglong2 lo = *reinterpret_cast<const ulonglong2 *>(stage + s);
-        const ulonglong2 hi = *reinterpret_cast<const ulonglong2 *>(stage + s + 2);
-        st_v4(g0 + t, lo.x, lo.y, hi.x, hi.y);
-    }
-    if (lane < 6) { // head [a, min(q_lo, end)) by lanes 0-2, tail [max(q_hi, q_lo), end) by lanes 3-5
-        const uint32_t t = lane < 3 ? a + lane : (q_hi > q_lo ? q_hi : q_lo) + (lane - 3);
-        const uint32_t lim = lane < 3 ? (q_lo < end ? q_lo : end) : end;
-        if (t < lim) st_u64(g0 + t, stage[lin_slot(t)]);
-    }
-    __syncwarp();
 }
 
 // OFFSETS = the set gives per-sequence offsets (seq_unit_off) and positions are symbols of the stream; otherwise
-// position p = (sequence p / w8, offset p % w8) and sequence r starts at symbol r * stride_syms + first
-template <int N, int NX, bool HASH, bool OFFSETS>
-__global__ void __launch_bounds__(kBlockThreads, KMC_LIN_MIN_BLOCKS) lin_compact_kernel(const ExtractParams p, const LinParams lp)
+// position p = (sequence p / w8, window p % w8) and sequence r starts at symbol r * stride_syms + first.
+// Everything inside a chunk is 32-bit arithmetic relative to the chunk's first position: the output element (against the
+// chunk's first element, whose pointers are formed once), the stream symbol (against the chunk's first symbol, whose
+// place in the reversed stream is formed once), the capacity left.  lin_prepare guarantees that a chunk's symbols span
+// less than 2^30 (lin_uniform_ok).  The loop body is branch-free for uniform sets (predicated loads and stores) and takes
+// two steps per trip, so that the loads of the second step are in flight while the first is finished.
+template <int N, bool HASH, bool OFFSETS>
+__global__ void __launch_bounds__(kBlockThreads) lin_compact_kernel(const ExtractParams p, const LinParams lp)
 {
-    constexpr int G = GroupOf<N>::G;
-    constexpr int LPW = 32 / G;                       // lanes that share one word of position bits
-    constexpr int ITERS = kLinChunkPos / (32 * G);    // warp steps per chunk
-    extern __shared__ __align__(16) uint64_t s_lin_stage[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t *stage = s_lin_stage + static_cast<size_t>(warp) * lin_stage_words(N);
-    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(stage));
-
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t c = static_cast<uint64_t>(blockIdx.x) * kLinWarps + warp;
     if (c >= lp.n_chunks) return;
-    uint64_t o = __ldg(lp.chunk_off + c);
-    if (__ldg(lp.chunk_off + c + 1) == o) return; // nothing survives in this chunk (warp-uniform)
-    const uint32_t *__restrict__ vs = lp.bits + c * kLinChunkWords;
+    const uint64_t o_c = __ldg(lp.chunk_off + c);
+    if (__ldg(lp.chunk_off + c + 1) == o_c) return; // nothing survives in this chunk (warp-uniform)
+    const uint32_t *bits = lp.bits + c * kLinChunkWords;
+    asm volatile("" : "+l"(bits));
     const uint64_t pos_c = c * kLinChunkPos;
     const bool tuple_ix = p.aos != 0;
-    // misalignment (in words, against 32 bytes) of the streams' base pointers
-    const uint32_t a_a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p.out_a) >> 3) & 3u;
-    const uint32_t a_i = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p.out_index) >> 3) & 3u;
-    const uint32_t a_h = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p.out_hash) >> 3) & 3u;
+    uint32_t lt_mask = (1u << lane) - 1u, lane_bit = 1u << lane;
+    uint32_t cap = o_c >= lp.capacity ? 0u : (lp.capacity - o_c > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(lp.capacity - o_c));
+    uint64_t *out_a = p.out_a + o_c * (tuple_ix ? N + 1 : N);
+    uint64_t *out_i = tuple_ix ? nullptr : reinterpret_cast<uint64_t *>(p.out_index) + o_c;
+    uint64_t *out_h = HASH ? p.out_hash + o_c : nullptr;
+    uint64_t head_mask = p.head_mask;
+    int64_t index_base = p.index_base + 1;
+    // (the chunk's constants are formed ONCE: without the barriers the compiler re-derives them from the parameter block
+    // inside the loop -- a dozen issue slots per step of a kernel that is bound by its issue slots)
+    asm volatile("" : "+r"(lt_mask), "+r"(lane_bit), "+r"(cap), "+l"(out_a), "+l"(out_i), "+l"(out_h), "+l"(head_mask), "+l"(index_base));
 
-    // where the chunk lies among the sequences
-    uint64_t r_lo = 0, r_hi = 0; // OFFSETS: the sequences that can own symbols of this chunk
-    uint32_t u_c = 0;            // uniform: offset of the chunk's first position in its sequence
-    uint64_t sym_rc = 0;         // uniform: first symbol (stream index) of that sequence
+    // this lane's position: its symbol relative to the chunk's first one and (uniform sets) its window inside its sequence
+    uint32_t rel = lane, u = 0;
+    uint32_t w8 = lp.w8, jump = lp.jump; // jump = stride_syms - w8: over a sequence's tail and the padding behind it
+    asm volatile("" : "+r"(w8), "+r"(jump));
+    uint64_t sym_c; // stream symbol of the chunk's first position
+    // offsets given: the sequence that owns the step's first symbol (warp-uniform), its first symbol and the next one's
+    uint64_t r_it = 0, s_cur = 0, s_next = ~0ull;
+    auto seq_start = [&](uint64_t r) -> uint64_t { return (__ldg(p.seq_unit_off + r) - p.unit_bias) * lp.spu + p.first; };
     if (OFFSETS) {
-        r_lo = __ldg(lp.chunk_first + c);
-        r_hi = __ldg(lp.chunk_first + c + 1);
+        sym_c = pos_c;
+        r_it = __ldg(lp.chunk_first + c);
+        s_cur = seq_start(r_it);
+        s_next = r_it + 1 < p.n_seqs ? seq_start(r_it + 1) : ~0ull;
     } else {
-        const uint64_t r_c = (pos_c >> 32) == 0 ? static_cast<uint32_t>(pos_c) / lp.w8 : pos_c / lp.w8;
-        u_c = static_cast<uint32_t>(pos_c - r_c * lp.w8);
-        sym_rc = r_c * lp.stride_syms + p.first;
+        const uint64_t r_c = (pos_c >> 32) == 0 ? static_cast<uint32_t>(pos_c) / w8 : pos_c / w8;
+        const uint32_t u_c = static_cast<uint32_t>(pos_c - r_c * w8);
+        sym_c = r_c * lp.stride_syms + p.first + u_c;
+        u = u_c + lane;
+        while (u >= w8) { // into the next sequence(s)
+            u -= w8;
+            rel += jump;
+        }
     }
-    auto seq_start = [&](uint64_t r) -> uint64_t { // first symbol of sequence r in the stream
-        return (__ldg(p.seq_unit_off + r) - p.unit_bias) * lp.spu + p.first;
-    };
-    // stream symbol of slot 0 of step `it` (uniform: and the slot's offset u in its sequence)
-    auto item_symbol = [&](int it, uint32_t &u) -> uint64_t {
-        const uint32_t off_it = static_cast<uint32_t>(it) * 32 * G + static_cast<uint32_t>(lane) * G;
+    // the window of relative symbol `rel` starts at bit b0 - 2 rel of the reversed stream, counted from byte address w0
+    const int64_t bit_c = 2 * (static_cast<int64_t>(lp.t_syms) - static_cast<int64_t>(sym_c) - p.k);
+    const char *w0 = reinterpret_cast<const char *>(lp.rev32 + (bit_c >> 5));
+    int32_t b0 = static_cast<int32_t>(bit_c & 31);
+    asm volatile("" : "+l"(w0), "+r"(b0));
+
+    // one step: the 32 positions of bit word v; `run` survivors of the chunk came before it
+    auto step = [&](uint32_t v, uint32_t run, int it) {
+        const uint32_t at = run + __popc(v & lt_mask); // this lane's element of the chunk's output, if it survives
+        const uint32_t on = ((v & lane_bit) && at < cap) ? 1u : 0u;
+        uint64_t limb[N];
+        lin_kmer<N>(w0, b0 - 2 * static_cast<int32_t>(rel), head_mask, on, limb);
+        int64_t index;
         if (OFFSETS) {
-            u = 0;
-            return pos_c + off_it;
-        }
-        const uint32_t off = u_c + off_it; // < w8 + 2048
-        uint32_t q;
-        if (lp.w8 >= 4096) {
-            q = off >= lp.w8 ? 1u : 0u;
-        } else {
-            q = static_cast<uint32_t>(static_cast<float>(off) * lp.inv_w8); // <= the quotient, at most 1 below it
-            if (off - q * lp.w8 >= lp.w8) ++q;
-        }
-        u = off - q * lp.w8;
-        return sym_rc + static_cast<uint64_t>(q) * lp.stride_syms + u;
-    };
-
-    // software pipeline: the position bits and the source words of the next step are requested before this step's
-    // k-mers are computed
-    uint32_t v_next = __ldg(vs + lane / LPW);
-    uint32_t raw_next[NX + 1], u_next;
-    uint64_t sym_next = item_symbol(0, u_next);
-    load_raw<NX>(p.w32, p.nw32, static_cast<int64_t>(2 * sym_next), raw_next);
-    const uint32_t sub = static_cast<uint32_t>(lane) % LPW;
-
-#pragma unroll 1
-    for (int it = 0; it < ITERS; ++it) {
-        const uint32_t v = v_next, u0 = u_next;
-        const uint64_t sym0 = sym_next;
-        uint32_t raw[NX + 1];
-#pragma unroll
-        for (int i = 0; i <= NX; ++i) raw[i] = raw_next[i];
-        if (it + 1 < ITERS) {
-            v_next = __ldg(vs + (it + 1) * G + lane / LPW);
-            sym_next = item_symbol(it + 1, u_next);
-            load_raw<NX>(p.w32, p.nw32, static_cast<int64_t>(2 * sym_next), raw_next);
-        }
-        // survivors of the step, and of the lanes before this one: the LPW lanes of a word hold the same popcount
-        const uint32_t pw = __popc(v);
-        uint32_t incl = pw;
-#pragma unroll
-        for (int d = LPW; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const uint32_t cnt = __shfl_sync(0xffffffffu, incl, 31);
-        if (cnt == 0) continue; // warp-uniform
-        const uint32_t m = (v >> (G * sub)) & ((1u << G) - 1u);
-        const uint32_t x = incl - pw + __popc(v & ((1u << (G * sub)) - 1u));
-        uint32_t cc = cnt;
-        if (o + cnt > lp.capacity) cc = o < lp.capacity ? static_cast<uint32_t>(lp.capacity - o) : 0u;
-        const uint64_t o_it = o;
-        o += cnt;
-
-        const uint32_t shift = (2u * static_cast<uint32_t>(sym0)) & 31u;
-        uint32_t xw[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) xw[i] = __funnelshift_r(raw[i], raw[i + 1], shift);
-        uint64_t fw[G][N], rv[G][N];
-        block_kmers<N, NX, G, true, false>(xw, p.s0, p.head_mask, fw, rv); // lanes without survivors: never staged
-
-        // 1-based start of every slot inside its sequence
-        int64_t ib[G];
-        if (OFFSETS) {
-            if (m) {
-                uint64_t lo = r_lo, hi = r_hi + 1; // largest r in [lo, hi) whose first symbol is <= sym0 (r_lo if none)
-                while (hi - lo > 1) {
-                    const uint64_t mid = (lo + hi) >> 1;
-                    if (seq_start(mid) <= sym0) lo = mid; else hi = mid;
+            index = 0;
+            if (v) { // warp-uniform: the sequence of the step's first symbol (symbols only ascend)
+                const uint64_t sym0 = pos_c + 32ull * it;
+                while (s_next <= sym0) {
+                    ++r_it;
+                    s_cur = s_next;
+                    s_next = r_it + 1 < p.n_seqs ? seq_start(r_it + 1) : ~0ull;
                 }
-                uint64_t r = lo, s_r = seq_start(r);
-                uint64_t next = r + 1 < p.n_seqs ? seq_start(r + 1) : ~0ull;
-                if (sym0 + G <= next) {
-                    const int64_t b = static_cast<int64_t>(sym0 - s_r) + 1 + p.index_base;
-#pragma unroll
-                    for (int j = 0; j < G; ++j) ib[j] = b + j;
-                } else { // the slots straddle sequences
-#pragma unroll
-                    for (int j = 0; j < G; ++j) {
-                        while (sym0 + j >= next) {
-                            ++r;
-                            s_r = next;
-                            next = r + 1 < p.n_seqs ? seq_start(r + 1) : ~0ull;
-                        }
-                        ib[j] = static_cast<int64_t>(sym0 + j - s_r) + 1 + p.index_base;
+            }
+            if (on) {
+                const uint64_t sym = sym_c + rel;
+                uint64_t s_r = s_cur;
+                if (sym >= s_next) { // a later sequence than the step's first
+                    uint64_t r = r_it + 1, nx;
+                    s_r = s_next;
+                    while (r + 1 < p.n_seqs && (nx = seq_start(r + 1)) <= sym) {
+                        ++r;
+                        s_r = nx;
                     }
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < G; ++j) ib[j] = 0;
+                index = static_cast<int64_t>(sym - s_r) + index_base;
             }
         } else {
-            const int64_t b = static_cast<int64_t>(u0) + 1 + p.index_base; // an item never straddles two sequences
-#pragma unroll
-            for (int j = 0; j < G; ++j) ib[j] = b + j;
+            index = static_cast<int64_t>(u) + index_base;
         }
+        if (tuple_ix) { // Vector{Tuple{Kmer,Int}}: {u64[N]; i64} elements
+            uint64_t e[N + 1];
+#pragma unroll
+            for (int i = 0; i < N; ++i) e[i] = limb[i];
+            e[N] = static_cast<uint64_t>(index);
+            lin_store<N + 1>(out_a + static_cast<uint64_t>(at) * (N + 1), e, on);
+        } else {
+            lin_store<N>(out_a + static_cast<uint64_t>(at) * N, limb, on);
+            stg64_if(out_i + at, static_cast<uint64_t>(index), on);
+        }
+        if (HASH) stg64_if(out_h + at, fx_hash<N>(limb, 0), on);
+        // the next step's 32 positions
+        rel += 32;
+        if (!OFFSETS) {
+            u += 32;
+            if (u >= w8) {
+                u -= w8;
+                rel += jump;
+                while (u >= w8) { // sequences of fewer than 32 windows
+                    u -= w8;
+                    rel += jump;
+                }
+            }
+        }
+    };
 
-        if (tuple_ix) {
-            // Vector{Tuple{Kmer,Int}}: {u64[N]; i64} elements
-            uint64_t buf[G * (N + 1)];
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) buf[j * (N + 1) + i] = fw[j][i];
-                buf[j * (N + 1) + N] = static_cast<uint64_t>(ib[j]);
-            }
-            const uint32_t a = (a_a + static_cast<uint32_t>(o_it) * (N + 1)) & 3u;
-            uint32_t addr[G];
-            lin_stage_addrs<N + 1, G>(sbase, a, x, m, addr);
-            lin_emit<N + 1, G>(p.out_a, o_it, cc, a, m, addr, buf, stage, sbase, lane);
-            if (HASH) {
-                uint64_t h[G];
-#pragma unroll
-                for (int j = 0; j < G; ++j) h[j] = fx_hash<N>(fw[j], 0);
-                const uint32_t ah = (a_h + static_cast<uint32_t>(o_it)) & 3u;
-                lin_stage_addrs<1, G>(sbase, ah, x, m, addr);
-                lin_emit<1, G>(p.out_hash, o_it, cc, ah, m, addr, h, stage, sbase, lane);
-            }
-        } else {
-            uint64_t buf[G * N];
-#pragma unroll
-            for (int j = 0; j < G; ++j)
-#pragma unroll
-                for (int i = 0; i < N; ++i) buf[j * N + i] = fw[j][i];
-            const uint32_t a = (a_a + static_cast<uint32_t>(o_it) * N) & 3u;
-            uint32_t addr[G];
-            lin_stage_addrs<N, G>(sbase, a, x, m, addr);
-            lin_emit<N, G>(p.out_a, o_it, cc, a, m, addr, buf, stage, sbase, lane);
-            // the one-word streams: the index, and the hash
-            uint64_t iw[G];
-#pragma unroll
-            for (int j = 0; j < G; ++j) iw[j] = static_cast<uint64_t>(ib[j]);
-            const uint32_t ai = (a_i + static_cast<uint32_t>(o_it)) & 3u;
-            if (N != 1 || ai != a) lin_stage_addrs<1, G>(sbase, ai, x, m, addr);
-            lin_emit<1, G>(reinterpret_cast<uint64_t *>(p.out_index), o_it, cc, ai, m, addr, iw, stage, sbase, lane);
-            if (HASH) {
-                uint64_t h[G];
-#pragma unroll
-                for (int j = 0; j < G; ++j) h[j] = fx_hash<N>(fw[j], 0);
-                const uint32_t ah = (a_h + static_cast<uint32_t>(o_it)) & 3u;
-                if (ah != ai) lin_stage_addrs<1, G>(sbase, ah, x, m, addr);
-                lin_emit<1, G>(p.out_hash, o_it, cc, ah, m, addr, h, stage, sbase, lane);
-            }
-        }
+    uint32_t run = 0; // survivors of the chunk's earlier steps
+    uint2 v_next = __ldg(reinterpret_cast<const uint2 *>(bits));
+#pragma unroll 1
+    for (int it = 0; it < kLinChunkWords; it += 2) {
+        const uint2 v = v_next;
+        v_next = __ldg(reinterpret_cast<const uint2 *>(bits + it + 2)); // (the bit array is padded)
+        step(v.x, run, it);
+        step(v.y, run + __popc(v.x), it + 1);
+        run += __popc(v.x) + __popc(v.y);
     }
 }
 
 using LinLaunchFn = cudaError_t (*)(ExtractParams, LinParams, cudaStream_t);
 
-template <int N, int NX, bool HASH, bool OFFSETS>
+template <int N, bool HASH, bool OFFSETS>
 cudaError_t launch_lin_compact(ExtractParams p, LinParams lp, cudaStream_t stream)
 {
     if (lp.n_chunks == 0) return cudaSuccess;
     const uint64_t blocks = (lp.n_chunks + kLinWarps - 1) / kLinWarps;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    constexpr size_t smem = static_cast<size_t>(kLinWarps) * lin_stage_words(N) * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute(lin_compact_kernel<N, NX, HASH, OFFSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    lin_compact_kernel<N, NX, HASH, OFFSETS><<<static_cast<unsigned>(blocks), kBlockThreads, smem, stream>>>(p, lp);
+    lin_compact_kernel<N, HASH, OFFSETS><<<static_cast<unsigned>(blocks), kBlockThreads, 0, stream>>>(p, lp);
     return cudaGetLastError();
 }
 
-LinLaunchFn get_lin_launcher_n1(int nx, bool hash, bool offsets);
-LinLaunchFn get_lin_launcher_n2(int nx, bool hash, bool offsets);
-LinLaunchFn get_lin_launcher_n3(int nx, bool hash, bool offsets);
-LinLaunchFn get_lin_launcher_n4(int nx, bool hash, bool offsets);
+LinLaunchFn get_lin_launcher_n1(bool hash, bool offsets);
+LinLaunchFn get_lin_launcher_n2(bool hash, bool offsets);
+LinLaunchFn get_lin_launcher_n3(bool hash, bool offsets);
+LinLaunchFn get_lin_launcher_n4(bool hash, bool offsets);
 
-#define KMC_DEFINE_LIN_TABLE(FN, N)                                                                 \
-    template <int NX>                                                                               \
-    static LinLaunchFn pickl_##N(bool hash, bool offsets)                                           \
-    {                                                                                               \
-        if (hash) return offsets ? &launch_lin_compact<N, NX, true, true> : &launch_lin_compact<N, NX, true, false>; \
-        return offsets ? &launch_lin_compact<N, NX, false, true> : &launch_lin_compact<N, NX, false, false>; \
-    }                                                                                               \
-    LinLaunchFn FN(int nx, bool hash, bool offsets)                                                 \
-    {                                                                                               \
-        constexpr int NXMAX = (64 * N + 2 * GroupOf<N>::G - 2 + 31) / 32;                           \
-        if (nx == NXMAX) return pickl_##N<NXMAX>(hash, offsets);                                    \
-        if (nx == NXMAX - 1) return pickl_##N<(NXMAX - 1 > 0 ? NXMAX - 1 : 1)>(hash, offsets);      \
-        if (nx == NXMAX - 2) return pickl_##N<(NXMAX - 2 > 0 ? NXMAX - 2 : 1)>(hash, offsets);      \
-        return nullptr;                                                                             \
+#define KMC_DEFINE_LIN_TABLE(FN, N)                                                                                  \
+    LinLaunchFn FN(bool hash, bool offsets)                                                                          \
+    {                                                                                                                \
+        if (hash) return offsets ? &launch_lin_compact<N, true, true> : &launch_lin_compact<N, true, false>;         \
+        return offsets ? &launch_lin_compact<N, false, true> : &launch_lin_compact<N, false, false>;                 \
     }
 
 } // namespace kmc

@@ -180,21 +180,36 @@ __global__ void __launch_bounds__(256) lin_chunk_kernel(const LinGeom g, uint64_
         if (OFFSETS) {
             v = g.vstart[w];
         } else {
+            // positions [32 w, 32 w + 32): runs of consecutive windows of one sequence each; the run of sequence r starts
+            // at its window u and ends with the sequence's windows.  With at least 32 windows per sequence a word holds at
+            // most two runs, and both gathers are issued before either is used (the kernel is a chain of dependent loads).
             v = 0;
             const uint64_t p0 = w * 32;
-            uint64_t r = p0 / g.w8;
-            uint32_t u = static_cast<uint32_t>(p0 - r * g.w8), filled = 0;
-            while (filled < 32 && r < g.n_seqs) {
-                const uint32_t take = min(32u - filled, g.w8 - u);
-                if (u < g.wpr) {
-                    const uint32_t nv = static_cast<uint32_t>(min(static_cast<uint64_t>(take), g.wpr - u));
-                    v |= vstart_bits(g.vstart, r * g.stride_syms + g.first + u, nv) << filled;
-                }
-                filled += take;
-                u += take;
-                if (u >= g.w8) {
-                    u = 0;
-                    ++r;
+            uint64_t r;
+            uint32_t u;
+            if (g.n_seqs == 1) {
+                r = p0 < g.w8 ? 0 : 1;
+                u = static_cast<uint32_t>(p0 < g.w8 ? p0 : 0);
+            } else {
+                r = (p0 >> 32) == 0 ? static_cast<uint32_t>(p0) / g.w8 : p0 / g.w8;
+                u = static_cast<uint32_t>(p0 - r * g.w8);
+            }
+            if (g.w8 >= 32) {
+                const uint32_t n0 = min(32u, g.w8 - u);
+                const uint32_t b0 = r < g.n_seqs ? vstart_bits(g.vstart, r * g.stride_syms + g.first + u, n0) : 0u;
+                const uint32_t b1 = (n0 < 32 && r + 1 < g.n_seqs) ? vstart_bits(g.vstart, (r + 1) * g.stride_syms + g.first, 32 - n0) : 0u;
+                v = b0 | (n0 < 32 ? b1 << n0 : 0u);
+            } else {
+                uint32_t filled = 0;
+                while (filled < 32 && r < g.n_seqs) {
+                    const uint32_t take = min(32u - filled, g.w8 - u);
+                    v |= vstart_bits(g.vstart, r * g.stride_syms + g.first + u, take) << filled;
+                    filled += take;
+                    u += take;
+                    if (u >= g.w8) {
+                        u = 0;
+                        ++r;
+                    }
                 }
             }
             g.packed[w] = v;
@@ -229,12 +244,25 @@ bool lin_enabled()
     return on;
 }
 
+// A set without offsets and with host-known lengths takes the source-order compaction iff this holds (lin_prepare
+// applies the same test; phase A of fourbit.cu asks before it decides which streams the recoding pass writes)
+bool lin_uniform_ok(const kmc_seqs *s, int k)
+{
+    if (s->n_seqs == 0 || s->seq_word_offset != nullptr || s->seq_len != nullptr) return false;
+    const uint64_t K = static_cast<uint64_t>(k), spu = s->src_bits == 8 ? 1 : 16;
+    const uint64_t wpr = s->uniform_len >= K ? s->uniform_len - K + 1 : 0, stride = s->uniform_stride_words * spu;
+    if (wpr == 0 || wpr > 0x7fffffffull) return false;
+    if (s->n_seqs > 1 && stride < wpr) return false; // overlapping sequences
+    const uint64_t jump = s->n_seqs > 1 ? stride - wpr : 0;
+    return jump < (1ull << 30) && (kLinChunkPos / wpr + 2) * jump + kLinChunkPos < (1ull << 30);
+}
+
 uint64_t lin_chunks(uint64_t n_positions) { return (n_positions + kLinChunkPos - 1) / kLinChunkPos; }
 
 // scratch lin_prepare can take for a set of n_seqs sequences over n_symbols symbols (any K, any layout)
 uint64_t lin_scratch_bytes(uint64_t n_symbols, uint64_t n_seqs)
 {
-    const uint64_t nc = lin_chunks(n_symbols + 8 * n_seqs + 64) + 1; // uniform sets: up to G - 1 extra positions per sequence
+    const uint64_t nc = lin_chunks(n_symbols + 64) + 1;
     return 3 * round_up(8 * (nc + 2), 256) + round_up(8 * (scan_tmp_elems(nc) + 1), 256) + round_up(4 * nc * kLinChunkWords, 256) + 1024;
 }
 
@@ -242,7 +270,7 @@ uint64_t lin_scratch_bytes(uint64_t n_symbols, uint64_t n_seqs)
 // chunks out.  plan->linear is the answer.  n_vstart_words: words of valid-start bits the recoding pass has written
 // (the array has room for whole chunks beyond).  `host_flag`: a pinned u64 the device check is copied to; the call
 // synchronises the stream only when the set gives offsets and the caller does not know the answer (known_linear < 0).
-int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int k, int g_windows, uint64_t n_vstart_words,
+int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int k, uint64_t n_vstart_words,
                     int known_linear, uint64_t *host_flag, cudaStream_t stream, Scratch &scratch, LinPlan *plan)
 {
     plan->linear = false;
@@ -267,10 +295,11 @@ int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int
     if (offsets) {
         n_pos = n_vstart_words * 32; // positions are the symbols of the stream
     } else {
-        g.wpr = s->uniform_len >= g.k ? s->uniform_len - g.k + 1 : 0;
-        if (s->n_seqs > 1 && g.stride_syms < g.wpr) return KMC_OK; // overlapping sequences
-        const uint64_t w8 = (g.wpr + g_windows - 1) / g_windows * g_windows;
-        if (w8 == 0 || w8 > 0x7fffffffull) return KMC_OK;
+        // (no overlapping sequences; and the kernel's 32-bit arithmetic: the symbols of one chunk of 2048 positions must
+        // span less than 2^30)
+        if (!lin_uniform_ok(s, k)) return KMC_OK;
+        g.wpr = s->uniform_len - g.k + 1;
+        const uint64_t w8 = g.wpr; // positions per sequence = its windows: the tails and the padding are no positions
         g.w8 = static_cast<uint32_t>(w8);
         n_pos = s->n_seqs * w8;
     }
@@ -281,7 +310,7 @@ int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int
     uint64_t *chunk_first = static_cast<uint64_t *>(scratch.take(8 * (nc + 2)));
     uint64_t *tmp = static_cast<uint64_t *>(scratch.take(8 * (scan_tmp_elems(nc) + 1)));
     unsigned long long *flag = static_cast<unsigned long long *>(scratch.take(8));
-    if (!offsets) g.packed = static_cast<uint32_t *>(scratch.take(4 * nc * kLinChunkWords));
+    if (!offsets) g.packed = static_cast<uint32_t *>(scratch.take(4 * (nc * kLinChunkWords + 8)));
     if (!cnt || !chunk_off || !chunk_first || !tmp || !flag || (!offsets && !g.packed))
         return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
     if (offsets) {
@@ -309,7 +338,7 @@ int32_t lin_prepare(kmc_ctx *ctx, const ExtractParams &p, const kmc_seqs *s, int
     plan->lp.capacity = 0;
     plan->lp.stride_syms = g.stride_syms;
     plan->lp.w8 = g.w8;
-    plan->lp.inv_w8 = g.w8 ? (1.0f / static_cast<float>(g.w8)) * (1.0f - 1.0f / 1048576.0f) : 0.f;
+    plan->lp.jump = (!offsets && s->n_seqs > 1) ? static_cast<uint32_t>(g.stride_syms - g.w8) : 0u;
     plan->lp.spu = g.spu;
     plan->offsets = offsets;
     plan->total_dev = chunk_off + nc;

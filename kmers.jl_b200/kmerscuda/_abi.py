@@ -93,6 +93,8 @@ SIGNATURES = {
                                 C.POINTER(kmc_out), C.POINTER(kmc_result)]),
     "kmc_extract_host": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint32,
                                      C.POINTER(kmc_out), C.POINTER(kmc_result)]),
+    "kmc_extract_spaced": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_uint32, C.POINTER(kmc_out),
+                                       C.POINTER(kmc_result)]),
     "kmc_fx_hash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]),
     "kmc_base_hash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]),
     "kmc_bucket_count": (C.c_int32, [C.c_void_p, C.POINTER(kmc_seqs), C.c_int32, C.c_int32, C.c_void_p,

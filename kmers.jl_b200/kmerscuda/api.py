@@ -560,29 +560,62 @@ class UnambiguousKmers(_KmerIterator):
 
 
 class SpacedKmers(_KmerIterator):
-    """Every J-th k-mer: SpacedKmers{A,K,J} (src/iterators/SpacedKmers.jl:23-44), positions 1, 1+J, ...
-    On the device this is kmc_minimizers with a window of ONE k-mer and step J (the closed form makes
-    the stride free).  2-bit LongSequence sources, K <= 32.  collect() -> u64[n, 1]."""
+    """Every J-th k-mer: SpacedKmers{A,K,J} (src/iterators/SpacedKmers.jl:22-139), starts 1, 1+J, 1+2J, ...
+    kmc_extract_spaced: 2- and 4-bit LongSequence sources and ASCII sources, k-mers over the 2- or the 4-bit
+    alphabets (every recoding scheme of construction.jl:75-100), K <= 128 (64 for 4-bit k-mers).
+    collect() -> u64[n, N]."""
     mode = KMC_FW
 
-    def __init__(self, A: Alphabet, K: int, J: int, seq: LongSequence):
+    def __init__(self, A: Alphabet, K: int, J: int, seq):
         super().__init__(A, K, seq)
         if not isinstance(J, (int, np.integer)) or isinstance(J, bool):
             raise TypeError("J must be an Int")
         if J < 1:
             raise ValueError("J must be at least 1")
-        if self.is_ascii or seq.alphabet.bits != 2:
-            raise NotImplementedError("SpacedKmers is accelerated for 2-bit LongSequence sources")
-        self.J = J
+        self.J = int(J)
 
     def __len__(self):
-        # SpacedKmers.jl:40-44
+        # SpacedKmers.jl:36-40
         L = len(self.seq)
         return 0 if L < self.K else (L - self.K) // self.J + 1
 
     def collect(self, **kw) -> np.ndarray:
-        km, _, _, _ = minimizers(ReadSet.single(self.seq), self.K, 1, self.J, **kw)
-        return km.reshape(-1, 1)
+        rs = ReadSet.ascii(self.seq) if self.is_ascii else ReadSet.single(self.seq)
+        return extract_spaced(rs, self.K, self.J, A=self.A, **kw).kmers
+
+
+def extract_spaced(rs, K: int, J: int, *, A: Alphabet = DNAAlphabet2, hash: bool = False, want_seq_offsets: bool = False,
+                   ctx: Optional[Context] = None) -> Extracted:
+    """Batched collect(SpacedKmers{A,K,J}(seq)) over a ReadSet / DeviceReadSet (kmc_extract_spaced)."""
+    _check_K(K)
+    if K > (KMC_MAX_K if A.bits == 2 else KMC_MAX_K4):
+        raise ValueError(f"K must be at most {KMC_MAX_K if A.bits == 2 else KMC_MAX_K4} for {A.name}")
+    ctx = ctx or default_context()
+    drs = rs if isinstance(rs, DeviceReadSet) else DeviceReadSet(ctx, rs)
+    hrs = drs.host
+    N = n_limbs(K, A.bits)
+    if hrs.seq_len is None:
+        cap = hrs.n_seqs * (0 if hrs.uniform_len < K else (hrs.uniform_len - K) // J + 1)
+    else:
+        ln = hrs.seq_len.astype(np.int64)
+        cap = int(np.where(ln >= K, (ln - K) // J + 1, 0).sum())
+    flags = (KMC_HASH_FX if hash else 0) | (KMC_RNA if A.name.startswith("RNA") else 0) | (KMC_KMER4 if A.bits == 4 else 0)
+    da = ctx.alloc(max(cap, 1) * N * 8)
+    dh = ctx.alloc(max(cap, 1) * 8) if hash else None
+    dso = ctx.alloc((hrs.n_seqs + 1) * 8) if want_seq_offsets else None
+    out = kmc_out(da.ptr, None, dh.ptr if dh else None, None, dso.ptr if dso else None, cap, 0)
+    res = kmc_result()
+    st = ctx.lib.kmc_extract_spaced(ctx.handle, C.byref(drs.desc), K, J, flags, C.byref(out), C.byref(res))
+    if st == KMC_E_AMBIGUOUS:
+        _raise_ambiguous(hrs.bits, A, res)
+    ctx._check(st)
+    n = int(res.n_written)
+    e = Extracted(kmers=da.download(np.uint64, n * N).reshape(n, N), hash=dh.download(np.uint64, n) if dh else None,
+                  seq_out_offset=dso.download(np.uint64, hrs.n_seqs + 1) if dso else None, n=n, kernel_ms=float(res.kernel_ms))
+    for d in (da, dh, dso):
+        if d:
+            d.free()
+    return e
 
 
 def SpacedDNAMers(K, J, seq):
@@ -593,9 +626,12 @@ def SpacedRNAMers(K, J, seq):
     return SpacedKmers(RNAAlphabet2, K, J, seq)
 
 
-def each_codon(seq: LongSequence):
-    """each_codon(s) = SpacedKmers{A,3,3}(s) (SpacedKmers.jl:57-81)."""
-    return SpacedKmers(seq.alphabet if seq.alphabet.bits == 2 else DNAAlphabet2, 3, 3, seq)
+def each_codon(seq, A: Optional[Alphabet] = None):
+    """each_codon(s) = SpacedKmers{A,3,3}(s) (SpacedKmers.jl:57-82): 2-bit DNA / RNA 3-mers with step 3.  A BioSequence
+    fixes DNA or RNA by its own alphabet; a byte-like source takes it from `A` (each_codon(DNA, s) / each_codon(RNA, s))."""
+    if isinstance(seq, LongSequence):
+        A = RNAAlphabet2 if seq.alphabet.name.startswith("RNA") else DNAAlphabet2
+    return SpacedKmers(A or DNAAlphabet2, 3, 3, seq)
 
 
 def FwDNAMers(K, seq):

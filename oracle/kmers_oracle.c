@@ -731,6 +731,116 @@ int ko_ascii_unambiguous(const uint8_t *src, uint64_t len, int K, uint64_t *out_
 
 
 /* ======================================================================
+ * SpacedKmers{A,K,J} (src/iterators/SpacedKmers.jl:22-139): k-mers at the 1-based starts 1, 1+J, 1+2J, ...
+ * (length: L < K ? 0 : div(L - K, J) + 1, :36-40).  The state machine is restated literally:
+ *   first element        unsafe_extract(R, T, src, 1); next_index = 1 + max(J, K)            (:92-105, :110-119)
+ *   later elements       stop when i > lastindex - min(K, J) + 1                              (:131)
+ *                        J >= K: unsafe_extract(R, T, src, i)            (i = the start of the k-mer)
+ *                        J <  K: unsafe_shift_from(R, kmer, src, i, Val(J)) (i = the first NEW symbol)   (:134-138)
+ * for every recoding scheme the nucleotide alphabets have (construction.jl:75-100): Copyable (2 -> 2, 4 -> 4),
+ * TwoToFour, FourToTwo (uncertain symbol -> EncodeError) and AsciiEncode (invalid byte -> EncodeError) into
+ * 2-bit or 4-bit k-mers.
+ *
+ * BioSequences.ascii_encode for the 4-bit alphabets is not in the reference tree; restated from BioSequences v3 /
+ * BioSymbols: every symbol of the alphabet -- A C M G R S V T W Y H K D B N and the gap '-', U instead of T for
+ * RNA -- in either case maps to its encoding (A=1 C=2 G=4 T/U=8, ambiguity codes = the OR of their bases, N=15,
+ * gap=0); everything else is > 0x7f.  The reference pins '-', 'N', 'K', 'W' being accepted through
+ * test/runtests.jl:855-863 (SpacedKmers{DNAAlphabet{4}} over codeunits("TA-NGAKATCGAWTAGA")).
+ * ====================================================================== */
+INL unsigned ascii_encode4(int rna, unsigned b)
+{
+    if (b >= 'a' && b <= 'z') b -= 32;
+    switch (b) {
+    case '-': return 0;
+    case 'A': return 1;
+    case 'C': return 2;
+    case 'M': return 3;
+    case 'G': return 4;
+    case 'R': return 5;
+    case 'S': return 6;
+    case 'V': return 7;
+    case 'T': return rna ? 0x80u : 8;
+    case 'U': return rna ? 8 : 0x80u;
+    case 'W': return 9;
+    case 'Y': return 10;
+    case 'H': return 11;
+    case 'K': return 12;
+    case 'D': return 13;
+    case 'B': return 14;
+    case 'N': return 15;
+    default: return 0x80u;
+    }
+}
+
+/* one symbol (1-based index i of the sequence) recoded into the k-mer alphabet; returns 0 on success, else the
+ * offending source encoding / byte through *bad */
+INL int spaced_symbol(const void *src, int src_bits, u64 first, u64 i, int rna, int kmer_bits, u64 *enc, u64 *bad)
+{
+    if (src_bits == 8) {
+        const unsigned byte = ((const uint8_t *)src)[first + i - 1];
+        const unsigned e = kmer_bits == 2 ? ascii_encode2(rna, byte) : ascii_encode4(rna, byte);
+        if (e > 0x7f) { *bad = byte; return 1; }
+        *enc = e;
+        return 0;
+    }
+    u64 e = extract_encoded_element((const u64 *)src, first + i, src_bits);
+    if (src_bits == 4 && kmer_bits == 2) { /* FourToTwo */
+        if (count_ones(e) != 1) { *bad = e; return 1; }
+        e = trailing_zeros(e);
+    } else if (src_bits == 2 && kmer_bits == 4) { /* TwoToFour */
+        e = left_shift(1, (unsigned)e);
+    }
+    *enc = e;
+    return 0;
+}
+
+/* src: LongSequence words (src_bits 2 / 4) or ASCII bytes (src_bits 8); first = 0-based symbol offset of the
+ * sequence in src; kmer_bits = 2 or 4.  out: N limbs per k-mer.  On KO_E_AMBIGUOUS *n_out = k-mers yielded before
+ * the error, *err_pos the 1-based position of the symbol that raised it, *err_enc its encoding / byte. */
+int ko_spaced(const void *src, int src_bits, uint64_t first, uint64_t len, int rna, int K, int J, int kmer_bits,
+              uint64_t *out, uint64_t *n_out, uint64_t *err_pos, uint64_t *err_enc)
+{
+    *n_out = 0;
+    if (K < 1 || J < 1 || (kmer_bits != 2 && kmer_bits != 4) || n_limbs(K, kmer_bits) > KO_MAX_LIMBS) return KO_E_BAD_K;
+    if (src_bits != 2 && src_bits != 4 && src_bits != 8) return KO_E_BAD_K;
+    const int N = n_limbs(K, kmer_bits);
+    u64 kmer[KO_MAX_LIMBS];
+    u64 n = 0, enc = 0, bad = 0;
+    if (len < (u64)K) return KO_OK;
+    /* unsafe_extract at 1 */
+    for (int j = 0; j < N; ++j) kmer[j] = 0;
+    for (u64 i = 1; i <= (u64)K; ++i) {
+        if (spaced_symbol(src, src_bits, first, i, rna, kmer_bits, &enc, &bad)) { *err_pos = i; *err_enc = bad; return KO_E_AMBIGUOUS; }
+        leftshift_carry(kmer, N, (unsigned)kmer_bits, enc);
+    }
+    u64 i = 1 + (u64)(J > K ? J : K);
+    const u64 mkj = (u64)(K < J ? K : J);
+    for (;;) {
+        for (int j = 0; j < N; ++j) out[n * (u64)N + j] = kmer[j];
+        ++n;
+        if (i + mkj > len + 1) break; /* i > lastindex - min(K, J) + 1 */
+        if (J >= K) {
+            for (int j = 0; j < N; ++j) kmer[j] = 0;
+            for (u64 q = i; q < i + (u64)K; ++q) {
+                if (spaced_symbol(src, src_bits, first, q, rna, kmer_bits, &enc, &bad)) { *n_out = n; *err_pos = q; *err_enc = bad; return KO_E_AMBIGUOUS; }
+                leftshift_carry(kmer, N, (unsigned)kmer_bits, enc);
+            }
+        } else {
+            for (u64 q = i; q < i + (u64)J; ++q) {
+                if (spaced_symbol(src, src_bits, first, q, rna, kmer_bits, &enc, &bad)) { *n_out = n; *err_pos = q; *err_enc = bad; return KO_E_AMBIGUOUS; }
+                if (kmer_bits == 2) shift_encoding(kmer, K, N, enc); else shift_encoding4(kmer, K, N, enc);
+            }
+        }
+        i += (u64)J;
+    }
+    *n_out = n;
+    return KO_OK;
+}
+
+/* FwKmers over an ASCII source into 4-bit k-mers (FwKmers.jl:69-78,117-129 with ascii_encode of a 4-bit alphabet):
+ * the spaced iterator with J = 1 is the same state machine (unsafe_shift_from of one symbol = shift_encoding). */
+
+/* ======================================================================
  * Base.hash(x::Kmer, h::UInt) = hash(x.data, h ⊻ (ksize(typeof(x)) % UInt))   -- src/kmer.jl:206.
  * hash(::NTuple{N,UInt64}, ::UInt) is Julia Base, not the reference; restated for Julia 1.10 / 1.11:
  *   tuple.jl     hash(::Tuple{}, h) = h + tuplehash_seed (0x77cfa1eef01bca90 on 64-bit)

@@ -347,6 +347,31 @@ def batch_unambiguous(words, n_seqs, k, *, word_off=None, seq_len=None, uniform_
     return km[:total], pos[:total], off
 
 
+def spaced(src, length, k, j, *, src_bits=2, kmer_bits=2, first=0, rna=False):
+    """SpacedKmers{A,K,J} over one sequence: LongSequence words (src_bits 2 / 4) or ASCII bytes (src_bits 8, `src`
+    bytes / str / uint8 array); kmer_bits = 2 or 4.  Raises AmbiguousError like the strict iterators."""
+    L = lib()
+    if src_bits == 8:
+        b, _ = _bytes(src)
+        buf = b
+    else:
+        buf = _words(src)
+    N = (k * kmer_bits + 63) // 64
+    n = 0 if length < k else (length - k) // j + 1
+    out = np.zeros((max(n, 1), N), dtype=np.uint64)
+    n_out, ep, ee = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    L.ko_spaced.restype = C.c_int
+    L.ko_spaced.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                            _u64p, _u64p, _u64p]
+    st = L.ko_spaced(_ptr(buf), src_bits, first, length, int(rna), k, j, kmer_bits, _ptr(out), C.byref(n_out), C.byref(ep), C.byref(ee))
+    if st == KO_E_AMBIGUOUS:
+        raise AmbiguousError(0, ep.value, ee.value, n_out.value)
+    if st != KO_OK:
+        raise ValueError(f"oracle status {st}")
+    assert n_out.value == n
+    return out[:n]
+
+
 def max_threads() -> int:
     return lib().ko_max_threads()
 

@@ -146,3 +146,13 @@ extern "C" void core_ascii_luts(uint8_t *out)
         out[512 + i] = l.skipping[i];
     }
 }
+
+// the two 4-bit tables (k-mers over DNAAlphabet{4} / RNAAlphabet{4} from ASCII sources)
+extern "C" void core_ascii_luts4(uint8_t *out)
+{
+    const kmc::AsciiLuts l = kmc::make_luts();
+    for (int i = 0; i < 256; ++i) {
+        out[i] = l.dna4[i];
+        out[256 + i] = l.rna4[i];
+    }
+}

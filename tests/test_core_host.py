@@ -198,3 +198,24 @@ def test_ascii_tables_follow_the_reference(core):
         c = chr(b)
         assert dna[b] == ("ACGT".index(c.upper()) if c.upper() in "ACGT" and c.isalpha() else ERR), b
         assert rna[b] == ("ACGU".index(c.upper()) if c.upper() in "ACGU" and c.isalpha() else ERR), b
+
+
+def test_ascii_tables_of_the_4bit_alphabets(core):
+    """The tables behind k-mers over DNAAlphabet{4} / RNAAlphabet{4} from ASCII bytes: every symbol of the alphabet -- the gap
+    and A C M G R S V T/U W Y H K D B N, encodings 0..15 (BioSymbols) -- in either case; any other byte is an error.  Checked
+    against the encodings the reference's own sequences use (kmertools.CODE4) and against the oracle's restatement, byte by
+    byte (SpacedKmers with K = J = 1 yields the encoding of each byte or raises)."""
+    core.core_ascii_luts4.restype = None
+    core.core_ascii_luts4.argtypes = [C.c_void_p]
+    out = np.zeros(512, dtype=np.uint8)
+    core.core_ascii_luts4(out.ctypes.data)
+    for rna, lut in ((False, out[:256]), (True, out[256:])):
+        for b in range(256):
+            c = chr(b).upper()
+            ok = c in kt.CODE4 and c != ("T" if rna else "U") and (chr(b).isalpha() or chr(b) == "-")
+            assert lut[b] == (kt.CODE4[c] if ok else 0x80), (rna, b)
+            try:
+                got = int(ko.spaced(bytes([b]), 1, 1, 1, src_bits=8, kmer_bits=4, rna=rna)[0, 0])
+            except ko.AmbiguousError:
+                got = 0x80
+            assert lut[b] == got, (rna, b)

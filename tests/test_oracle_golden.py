@@ -348,3 +348,36 @@ def test_base_hash_documented_value_and_invariants():
                     acc = (h64(x) - 3 * acc) & M
                 want.append(acc)
             assert ko.base_hash(km, K, h0).tolist() == want
+
+
+def test_julia_fixtures_if_present():
+    """tests/golden/julia_fixtures.json is what tests/golden/make_julia_fixtures.jl dumps from a REAL Julia + BioSequences +
+    Kmers installation (LongSequence.data words, iterator outputs, fx_hash / Base.hash values).  No Julia exists in this
+    build image, so the file is absent and this test skips; once generated it pins the oracle to the reference itself."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "julia_fixtures.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/julia_fixtures.json has not been generated (needs Julia + Kmers.jl)")
+    fx = json.load(open(path))
+    hx = lambda v: [int(x, 16) for x in v]  # noqa: E731
+    for e in fx["entries"]:
+        s2 = e["seq"]
+        if e["kind"] == "layout":
+            assert kt.pack2(s2).tolist()[: len(e["data2"])] == hx(e["data2"])
+            assert kt.pack4(e["seq4"]).tolist()[: len(e["data4"])] == hx(e["data4"])
+        elif e["kind"] == "iterators":
+            k = e["k"]
+            a, _, h = ko.iterate(kt.pack2(s2), len(s2), k, ko.CANON, want_hash=True)
+            assert [list(map(int, r)) for r in a] == [hx(v) for v in e["canonical"]]
+            assert [int(x) for x in h] == hx(e["fx_hash"])
+            f, _, _ = ko.iterate(kt.pack2(s2), len(s2), k, ko.FW)
+            assert [list(map(int, r)) for r in f] == [hx(v) for v in e["fw"]]
+            km, pos = ko.unambiguous(kt.pack4(e["seq4"]), len(s2), k, src_bits=4)
+            assert [[list(map(int, r)), int(p)] for r, p in zip(km, pos)] == [[hx(v[0]), v[1]] for v in e["unambiguous"]]
+            if fx["julia"].startswith(("1.10", "1.11")):
+                assert [int(x) for x in ko.base_hash(a, k)] == hx(e["base_hash"])
+                assert [int(x) for x in ko.base_hash(a, k, 7)] == hx(e["base_hash_h7"])
+        elif e["kind"] == "spaced":
+            sp = ko.spaced(kt.pack2(s2), len(s2), e["k"], e["j"])
+            assert [list(map(int, r)) for r in sp] == [hx(v) for v in e["spaced"]]
+            sp4 = ko.spaced(kt.pack4(e["seq4"]), len(s2), e["k"], e["j"], src_bits=4, kmer_bits=4)
+            assert [list(map(int, r)) for r in sp4] == [hx(v) for v in e["spaced4"]]
