@@ -130,7 +130,7 @@ def main():
     rt = cudart()
     n_dev = C.c_int(0)
     check(rt, rt.cudaGetDeviceCount(C.byref(n_dev)), "cudaGetDeviceCount")
-    reps = 20
+    reps = 10
     out = {"bytes_per_copy": BYTES, "reps": reps, "gpus": n_dev.value, "rows": []}
     for n in (1, 2, 4, 8):
         if n > n_dev.value:
