@@ -67,7 +67,8 @@ __device__ __forceinline__ void ascii_group(const uint8_t *__restrict__ bytes, u
 __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut, int k,
                                                            uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
                                                            uint32_t *__restrict__ err, uint32_t *__restrict__ vstart,
-                                                           uint64_t n_groups, uint64_t n_vstart, uint32_t *__restrict__ rev)
+                                                           uint64_t n_groups, uint64_t n_vstart, uint32_t *__restrict__ rev,
+                                                           unsigned long long *__restrict__ any_err)
 {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_bad[256 + 8];
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__rest
                     make_uint2(rev2_32(static_cast<uint32_t>(codes >> 32)), rev2_32(static_cast<uint32_t>(codes)));
             if (bad) bad[g] = fb;
             if (err) err[g] = fe;
+            if (fe && any_err) atomicOr(any_err, 1ull); // (rare: lets the per-sequence search for the first error return at once)
         }
         s_bad[threadIdx.x] = fb;
     }
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__rest
 // memory as above, the "K encodable symbols from here on" word.
 __global__ void __launch_bounds__(256) ascii4_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut, int k,
                                                             uint64_t *__restrict__ nib, uint32_t *__restrict__ bad,
-                                                            uint32_t *__restrict__ vstart, uint64_t n_groups, uint64_t n_vstart)
+                                                            uint32_t *__restrict__ vstart, uint64_t n_groups, uint64_t n_vstart,
+                                                            unsigned long long *__restrict__ any_err)
 {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_bad[256 + 8];
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(256) ascii4_recode_kernel(const uint8_t *__res
             nib[2 * g] = w0;
             nib[2 * g + 1] = w1;
             bad[g] = fe;
+            if (fe && any_err) atomicOr(any_err, 1ull);
         }
         s_bad[threadIdx.x] = fe;
     }
@@ -167,8 +171,12 @@ __global__ void __launch_bounds__(256) ascii4_recode_kernel(const uint8_t *__res
 // (min_len: the strict iterators never touch a sequence shorter than K, FwKmers.jl:62-66)
 __global__ void __launch_bounds__(256) seq_first_error_kernel(ExtractParams p, const uint32_t *__restrict__ err,
                                                               const uint64_t *__restrict__ seq_len, uint64_t uniform_len,
-                                                              uint64_t min_len, unsigned long long *__restrict__ err_seq)
+                                                              uint64_t min_len, unsigned long long *__restrict__ err_seq,
+                                                              const unsigned long long *__restrict__ any_err)
 {
+    // the recoding pass has seen no error byte anywhere in the buffer: nothing to look for (a warp per sequence and a
+    // handful of dependent loads each took 0.9 ms per 10 M reads -- a fifth of an UnambiguousKmers call over ASCII reads)
+    if (any_err && *any_err == 0) return;
     const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p.n_seqs == 1) { // one long sequence: the whole grid strides over its flag words
@@ -254,32 +262,42 @@ static cudaError_t upload_luts()
 
 // rna: U (not T) is the fourth base.  nib: 2 u64 per group of 32 bytes; bad / vstart as in ascii_recode.
 cudaError_t ascii4_recode(const uint8_t *bytes, uint64_t n_bytes, bool rna, int k, uint64_t *nib, uint32_t *bad, uint32_t *vstart,
-                          uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream)
+                          uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, unsigned long long *any_err)
 {
     cudaError_t e = upload_luts();
     if (e != cudaSuccess) return e;
+    if (any_err) {
+        e = cudaMemsetAsync(any_err, 0, 8, stream);
+        if (e != cudaSuccess) return e;
+    }
     ascii4_recode_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, rna ? 4 : 3, k, nib, bad,
-                                                                                           vstart, n_groups, n_vstart);
+                                                                                           vstart, n_groups, n_vstart, any_err);
     return cudaGetLastError();
 }
 
 cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k, uint32_t *rec, uint32_t *bad, uint32_t *err,
-                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev)
+                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev,
+                         unsigned long long *any_err)
 {
     cudaError_t e = upload_luts();
     if (e != cudaSuccess) return e;
+    if (any_err) {
+        e = cudaMemsetAsync(any_err, 0, 8, stream);
+        if (e != cudaSuccess) return e;
+    }
     ascii_recode_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, lut, k, rec, bad, err,
-                                                                                          vstart, n_groups, n_vstart, rev);
+                                                                                          vstart, n_groups, n_vstart, rev, any_err);
     return cudaGetLastError();
 }
 
 cudaError_t ascii_first_error_seq(const ExtractParams &p, const uint32_t *err, const uint64_t *seq_len, uint64_t uniform_len,
-                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream, uint64_t min_len)
+                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream, uint64_t min_len,
+                                  const unsigned long long *any_err)
 {
     if (p.n_seqs == 0) return cudaSuccess;
     const uint64_t want = p.n_seqs == 1 ? static_cast<uint64_t>(sm_count) * 32 : (p.n_seqs * 32 + 255) / 256;
     const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 32 ? want : static_cast<uint64_t>(sm_count) * 32);
-    seq_first_error_kernel<<<grid, 256, 0, stream>>>(p, err, seq_len, uniform_len, min_len, err_seq);
+    seq_first_error_kernel<<<grid, 256, 0, stream>>>(p, err, seq_len, uniform_len, min_len, err_seq, any_err);
     return cudaGetLastError();
 }
 

@@ -19,62 +19,92 @@ constexpr int kCountLayoutG = 32; // windows per work item when the survivors ar
 // flags are never re-read from global memory and no second pass is launched.
 // rev (optional): the same codes as one stream in REVERSED symbol order -- group g goes, its 32 symbols reversed, to
 // 64-bit word n_groups - 1 - g -- in which the forward k-mer of every window is a plain run of 2K bits (lincompact.cuh).
+// FULL: every group of the block and of its halo exists, both source words of each lie inside the array, and the
+// array is 16-byte aligned -- all blocks but the last one or two.  The bounds tests and 64-bit index arithmetic of the
+// general form were 40 % of the pass's instructions, and the pass is bound by its integer instructions.
+template <bool FULL>
+__device__ __forceinline__ void recode_vstart_block(const uint64_t *__restrict__ words, uint64_t n_words, int k,
+                                                    uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
+                                                    uint32_t *__restrict__ vstart, uint64_t n_groups, uint64_t n_vstart,
+                                                    uint32_t *__restrict__ rev, uint32_t *s_bad)
+{
+    // kRecodeGroups groups per thread, all their source words requested before the first is used: with one 16-byte
+    // load per short-lived thread the pass was latency-bound, and the halo below was recomputed once per 256 groups
+    const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * (256 * kRecodeGroups);
+    const uint32_t t = threadIdx.x;
+    const uint4 *src = reinterpret_cast<const uint4 *>(words) + g0; // (FULL: 16-byte aligned)
+    const bool aligned = (reinterpret_cast<uintptr_t>(words) & 15) == 0;
+    // words past the end read as 'A' (one-hot): never part of a window, never flagged
+    auto load_pair = [&](uint32_t i) -> uint4 { // group g0 + i
+        if (FULL) return __ldg(src + i);
+        const uint64_t g = g0 + i;
+        if (2 * g + 1 < n_words && aligned) return __ldg(src + i);
+        const uint64_t a = 2 * g < n_words ? __ldg(words + 2 * g) : 0x1111111111111111ull;
+        const uint64_t b = 2 * g + 1 < n_words ? __ldg(words + 2 * g + 1) : 0x1111111111111111ull;
+        return make_uint4(static_cast<uint32_t>(a), static_cast<uint32_t>(a >> 32), static_cast<uint32_t>(b), static_cast<uint32_t>(b >> 32));
+    };
+    uint4 w[kRecodeGroups];
+#pragma unroll
+    for (int j = 0; j < kRecodeGroups; ++j) w[j] = load_pair(256 * j + t);
+    uint4 h = make_uint4(0x11111111u, 0x11111111u, 0x11111111u, 0x11111111u);
+    if (t < kRecodeHalo) h = load_pair(256 * kRecodeGroups + t);
+    auto recode = [](const uint4 &v, uint32_t &c0, uint32_t &c1) -> uint32_t { // 32 symbols: codes of the two words, 32 flags
+        uint32_t a, b, fa, fb;
+        recode_half(v.x, a, fa);
+        recode_half(v.y, b, fb);
+        c0 = a | (b << 16);
+        uint32_t f = fa | (fb << 8);
+        recode_half(v.z, a, fa);
+        recode_half(v.w, b, fb);
+        c1 = a | (b << 16);
+        return f | (fa << 16) | (fb << 24);
+    };
+    uint2 *rec2 = reinterpret_cast<uint2 *>(rec) + g0;
+    uint2 *rev2 = reinterpret_cast<uint2 *>(rev) + (n_groups - 1 - g0); // group g0 + i goes to rev2[-i]
+    uint32_t *bad0 = bad + g0;
+#pragma unroll
+    for (int j = 0; j < kRecodeGroups; ++j) {
+        const uint32_t i = 256 * j + t;
+        uint32_t c0, c1;
+        const uint32_t f = recode(w[j], c0, c1); // (a group past the end: all 'A', no flag)
+        if (FULL || g0 + i < n_groups) {
+            if (rec) rec2[i] = make_uint2(c0, c1);
+            if (rev) *(rev2 - i) = make_uint2(rev2_32(c1), rev2_32(c0));
+            if (bad) bad0[i] = f;
+        }
+        s_bad[i] = f;
+    }
+    if (t < kRecodeHalo) {
+        uint32_t c0, c1;
+        s_bad[256 * kRecodeGroups + t] = recode(h, c0, c1);
+    }
+    __syncthreads();
+    uint32_t *vs0 = vstart + g0;
+#pragma unroll
+    for (int j = 0; j < kRecodeGroups; ++j) {
+        const uint32_t i = 256 * j + t;
+        if (FULL || g0 + i < n_vstart) {
+            uint32_t a[6];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) a[d] = s_bad[i + d];
+            a[5] = 0;
+            vs0[i] = valid_start_word(a, k);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) recode_vstart_kernel(const uint64_t *__restrict__ words, uint64_t n_words, int k,
                                                             uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
                                                             uint32_t *__restrict__ vstart, uint64_t n_groups,
                                                             uint64_t n_vstart, uint32_t *__restrict__ rev)
 {
-    __shared__ uint32_t s_bad[256 + 8];
-    const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * 256;
-    // words past the end read as 'A' (one-hot): never part of a window, never flagged
-    auto load_pair = [&](uint64_t g, uint64_t &w0, uint64_t &w1) {
-        if (2 * g + 1 < n_words && (reinterpret_cast<uintptr_t>(words) & 15) == 0) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(words) + g);
-            w0 = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
-            w1 = static_cast<uint64_t>(v.z) | (static_cast<uint64_t>(v.w) << 32);
-        } else {
-            w0 = 2 * g < n_words ? __ldg(words + 2 * g) : 0x1111111111111111ull;
-            w1 = 2 * g + 1 < n_words ? __ldg(words + 2 * g + 1) : 0x1111111111111111ull;
-        }
-    };
-    {
-        const uint64_t g = g0 + threadIdx.x;
-        uint32_t f = 0;
-        if (g < n_groups) {
-            uint64_t w0, w1;
-            load_pair(g, w0, w1);
-            uint32_t c0, c1, f0, f1;
-            recode_word(w0, c0, f0);
-            recode_word(w1, c1, f1);
-            if (rec) reinterpret_cast<uint2 *>(rec)[g] = make_uint2(c0, c1);
-            if (rev) reinterpret_cast<uint2 *>(rev)[n_groups - 1 - g] = make_uint2(rev2_32(c1), rev2_32(c0));
-            f = f0 | (f1 << 16);
-            if (bad) bad[g] = f;
-        }
-        s_bad[threadIdx.x] = f;
-    }
-    if (threadIdx.x < kRecodeHalo) {
-        const uint64_t g = g0 + 256 + threadIdx.x;
-        uint32_t f = 0;
-        if (g < n_groups) {
-            uint64_t w0, w1;
-            load_pair(g, w0, w1);
-            uint32_t c0, c1, f0, f1;
-            recode_word(w0, c0, f0);
-            recode_word(w1, c1, f1);
-            f = f0 | (f1 << 16);
-        }
-        s_bad[256 + threadIdx.x] = f;
-    }
-    __syncthreads();
-    const uint64_t g = g0 + threadIdx.x;
-    if (g < n_vstart) {
-        uint32_t a[6];
-#pragma unroll
-        for (int d = 0; d < 5; ++d) a[d] = s_bad[threadIdx.x + d];
-        a[5] = 0;
-        vstart[g] = valid_start_word(a, k);
-    }
+    __shared__ uint32_t s_bad[256 * kRecodeGroups + 8];
+    const uint64_t g_end = (static_cast<uint64_t>(blockIdx.x) + 1) * (256 * kRecodeGroups) + kRecodeHalo; // one past the halo
+    const bool full = g_end <= n_groups && 2 * g_end <= n_words && (reinterpret_cast<uintptr_t>(words) & 15) == 0; // block-uniform
+    if (full)
+        recode_vstart_block<true>(words, n_words, k, rec, bad, vstart, n_groups, n_vstart, rev, s_bad);
+    else
+        recode_vstart_block<false>(words, n_words, k, rec, bad, vstart, n_groups, n_vstart, rev, s_bad);
 }
 
 // Turns the first offending flat window of a strict mode into what the reference throws on:
@@ -179,7 +209,7 @@ CompactLaunchFn compact_launcher(const Geometry &ge, bool hash, bool ragged)
 cudaError_t fourbit_recode(const uint64_t *words, uint64_t n_words, int k, uint32_t *rec, uint32_t *bad, uint32_t *vstart,
                            uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev)
 {
-    recode_vstart_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(words, n_words, k, rec, bad, vstart, n_groups,
+    recode_vstart_kernel<<<static_cast<unsigned>((n_vstart + 256 * kRecodeGroups - 1) / (256 * kRecodeGroups)), 256, 0, stream>>>(words, n_words, k, rec, bad, vstart, n_groups,
                                                                                            n_vstart, rev);
     return cudaGetLastError();
 }
@@ -193,7 +223,7 @@ uint64_t fourbit_scratch_bytes(const kmc_seqs *s, int k, int mode)
     need += round_up(8 * (nb + 2), 256);     // rec32
     need += 3 * round_up(4 * (nb + 8), 256); // bad, vstart, err
     need += 4 * kLinChunkWords + 256;        // vstart rounded up to whole chunks of the source-order compaction
-    if (mode == KMC_UNAMBIG) need += lin_scratch_bytes(32 * (nb + 2), s->n_seqs) + round_up(8 * (nb + 2), 256); // + the reversed stream
+    if (mode == KMC_UNAMBIG) need += lin_scratch_bytes(32 * (nb + 2), s->n_seqs) + round_up(8 * (nb + 2), 256) + 256; // + the reversed stream
     need += 3 * 256;                         // err_flat, err_out, total
     need += layout_scratch_bytes(s);
     if (mode == KMC_UNAMBIG) {
@@ -235,9 +265,10 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     uint32_t *err = (ascii && st->unambig) ? static_cast<uint32_t *>(scratch.take(4 * (nb + 8))) : nullptr;
     if (ascii && st->unambig && !err) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
     // UnambiguousKmers: the source-order compaction reads its k-mers from the stream in reversed symbol order
-    uint32_t *rev = (st->unambig && out && lin_enabled()) ? static_cast<uint32_t *>(scratch.take(8 * (nb + 2))) : nullptr;
+    uint32_t *rev = (st->unambig && out && lin_enabled()) ? static_cast<uint32_t *>(scratch.take(8 * (nb + 2) + 256)) : nullptr;
+    if (rev) rev += 64; // (lin_compact2_kernel may read the word before the stream)
     st->err = err;
-    unsigned long long *err_flat = static_cast<unsigned long long *>(scratch.take(8));
+    unsigned long long *err_flat = static_cast<unsigned long long *>(scratch.take(16)); // [1]: "the recoding pass flagged an error byte"
     uint64_t *err_out = static_cast<uint64_t *>(scratch.take(24));
     if ((!rev_only && (!rec || !bad)) || !vstart || !err_flat || !err_out) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
     st->bad = bad;
@@ -245,7 +276,8 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
 
     if (ascii) {
         const int lut = st->unambig ? 2 : ((flags & KMC_RNA) ? 1 : 0);
-        CU(ascii_recode(reinterpret_cast<const uint8_t *>(s->words), s->n_words, lut, k, rec, bad, err, vstart, nb, nb + 2, stream, rev));
+        CU(ascii_recode(reinterpret_cast<const uint8_t *>(s->words), s->n_words, lut, k, rec, bad, err, vstart, nb, nb + 2, stream, rev,
+                        err ? err_flat + 1 : nullptr));
     } else {
         CU(fourbit_recode(s->words, s->n_words, k, rec, bad, vstart, nb, nb + 2, stream, rev));
     }
@@ -268,7 +300,7 @@ int32_t fourbit_phase_a(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode
     if (ascii && st->unambig) {
         // every byte of every sequence is read (UnambiguousKmers.jl:109-132), whatever its length
         CU(cudaMemsetAsync(err_flat, 0xff, 8, stream));
-        CU(ascii_first_error_seq(st->p, err, s->seq_len, s->uniform_len, err_flat, ctx->sm_count, stream));
+        CU(ascii_first_error_seq(st->p, err, s->seq_len, s->uniform_len, err_flat, ctx->sm_count, stream, 0, err_flat + 1));
         CU(cudaMemcpyAsync(&host_small[1], err_flat, 8, cudaMemcpyDeviceToHost, stream));
     }
     if (L.total == 0) {

@@ -64,6 +64,7 @@ struct FourBitState {
 cudaError_t count_valid(const ExtractParams &p, bool ragged, int g, unsigned long long *total, cudaStream_t stream);
 
 // (valid_start_word: fourbit_core.cuh)
+constexpr int kRecodeGroups = 4; // groups of 32 symbols per thread of the 4-bit recoding pass
 constexpr int kRecodeHalo = 5; // flag words beyond a group that its windows can reach (31 + K - 1 <= 158 bits)
 
 // ascii.cu: byte sources (AsciiEncode).  lut: 0 = strict DNAAlphabet{2}, 1 = strict RNAAlphabet{2},
@@ -71,13 +72,16 @@ constexpr int kRecodeHalo = 5; // flag words beyond a group that its windows can
 // Writes rec / bad / err for the groups [0, n_groups) and the valid-start words [0, n_vstart).
 // rev (optional, both recoding passes): the codes once more as a stream in REVERSED symbol order (2 u32 per group)
 cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k, uint32_t *rec, uint32_t *bad, uint32_t *err,
-                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev = nullptr);
+                         uint32_t *vstart, uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev = nullptr,
+                         unsigned long long *any_err = nullptr);
+// (any_err, optional: a device word the pass clears and then sets if it flags any byte as an error)
 // the first sequence (of at least min_len symbols) that holds a flagged byte -> atomicMin into *err_seq
 cudaError_t ascii_first_error_seq(const ExtractParams &p, const uint32_t *err, const uint64_t *seq_len, uint64_t uniform_len,
-                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream, uint64_t min_len = 0);
+                                  unsigned long long *err_seq, int sm_count, cudaStream_t stream, uint64_t min_len = 0,
+                                  const unsigned long long *any_err = nullptr);
 // ASCII bytes -> nibbles of a 4-bit alphabet (2 u64 per group of 32 bytes) + error flags + the valid-start words
 cudaError_t ascii4_recode(const uint8_t *bytes, uint64_t n_bytes, bool rna, int k, uint64_t *nib, uint32_t *bad, uint32_t *vstart,
-                          uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream);
+                          uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, unsigned long long *any_err = nullptr);
 // fourbit.cu: the FourToTwo recoding pass (2-bit codes, uncertainty flags, valid-start words); n_groups = groups of 32 symbols
 cudaError_t fourbit_recode(const uint64_t *words, uint64_t n_words, int k, uint32_t *rec, uint32_t *bad, uint32_t *vstart,
                            uint64_t n_groups, uint64_t n_vstart, cudaStream_t stream, uint32_t *rev = nullptr);

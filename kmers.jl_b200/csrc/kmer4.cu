@@ -110,12 +110,12 @@ int32_t extract_device_kmer4(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t
         uint64_t *nib = static_cast<uint64_t *>(scratch.take(16 * (nb + 2)));
         uint32_t *bad = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
         uint32_t *vstart = static_cast<uint32_t *>(scratch.take(4 * (nb + 8)));
-        unsigned long long *err_seq = static_cast<unsigned long long *>(scratch.take(8));
+        unsigned long long *err_seq = static_cast<unsigned long long *>(scratch.take(16)); // [1]: "the recoding pass flagged a byte"
         uint64_t *err_out = static_cast<uint64_t *>(scratch.take(24));
         if (!nib || !bad || !vstart || !err_seq || !err_out) return fail(ctx, KMC_E_BAD_ARG, "internal: scratch window too small");
         st = ensure_host_small(ctx);
         if (st) return st;
-        CU(ascii4_recode(bytes, s->n_words, (flags & KMC_RNA) != 0, k, nib, bad, vstart, nb, nb + 2, stream));
+        CU(ascii4_recode(bytes, s->n_words, (flags & KMC_RNA) != 0, k, nib, bad, vstart, nb, nb + 2, stream, err_seq + 1));
         p.w32 = reinterpret_cast<const uint32_t *>(nib);
         p.nw32 = static_cast<int64_t>(nb) * 4;
         p.unit_bits = 4; // offsets count bytes = symbols = nibbles of the recoded stream
@@ -126,7 +126,7 @@ int32_t extract_device_kmer4(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t
         pe.unit_bits = 2;
         uint64_t *flag = ctx->host_small + 60;
         CU(cudaMemsetAsync(err_seq, 0xff, 8, stream));
-        CU(ascii_first_error_seq(pe, bad, s->seq_len, s->uniform_len, err_seq, ctx->sm_count, stream, static_cast<uint64_t>(k)));
+        CU(ascii_first_error_seq(pe, bad, s->seq_len, s->uniform_len, err_seq, ctx->sm_count, stream, static_cast<uint64_t>(k), err_seq + 1));
         CU(cudaMemcpyAsync(flag, err_seq, 8, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         if (*flag != ~0ull) {

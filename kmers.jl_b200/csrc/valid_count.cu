@@ -194,23 +194,11 @@ __global__ void __launch_bounds__(256) lin_chunk_kernel(const LinGeom g, uint64_
                 r = (p0 >> 32) == 0 ? static_cast<uint32_t>(p0) / g.w8 : p0 / g.w8;
                 u = static_cast<uint32_t>(p0 - r * g.w8);
             }
-            if (g.w8 >= 32) {
+            {
                 const uint32_t n0 = min(32u, g.w8 - u);
                 const uint32_t b0 = r < g.n_seqs ? vstart_bits(g.vstart, r * g.stride_syms + g.first + u, n0) : 0u;
                 const uint32_t b1 = (n0 < 32 && r + 1 < g.n_seqs) ? vstart_bits(g.vstart, (r + 1) * g.stride_syms + g.first, 32 - n0) : 0u;
                 v = b0 | (n0 < 32 ? b1 << n0 : 0u);
-            } else {
-                uint32_t filled = 0;
-                while (filled < 32 && r < g.n_seqs) {
-                    const uint32_t take = min(32u - filled, g.w8 - u);
-                    v |= vstart_bits(g.vstart, r * g.stride_syms + g.first + u, take) << filled;
-                    filled += take;
-                    u += take;
-                    if (u >= g.w8) {
-                        u = 0;
-                        ++r;
-                    }
-                }
             }
             g.packed[w] = v;
         }
@@ -251,7 +239,7 @@ bool lin_uniform_ok(const kmc_seqs *s, int k)
     if (s->n_seqs == 0 || s->seq_word_offset != nullptr || s->seq_len != nullptr) return false;
     const uint64_t K = static_cast<uint64_t>(k), spu = s->src_bits == 8 ? 1 : 16;
     const uint64_t wpr = s->uniform_len >= K ? s->uniform_len - K + 1 : 0, stride = s->uniform_stride_words * spu;
-    if (wpr == 0 || wpr > 0x7fffffffull) return false;
+    if (wpr < 32 || wpr > 0x7fffffffull) return false; // (fewer than 32 windows per sequence: compact_kernel; the kernel's steps cross at most one boundary)
     if (s->n_seqs > 1 && stride < wpr) return false; // overlapping sequences
     const uint64_t jump = s->n_seqs > 1 ? stride - wpr : 0;
     return jump < (1ull << 30) && (kLinChunkPos / wpr + 2) * jump + kLinChunkPos < (1ull << 30);

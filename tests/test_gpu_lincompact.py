@@ -69,7 +69,10 @@ def check(kc, rs, per_read, k, **kw):
 
 
 @pytest.mark.parametrize("k,length,stride", [(31, 150, 150), (31, 150, 157), (5, 37, 37), (2, 9, 9), (1, 8, 8), (31, 31, 33),
-                                             (63, 150, 151), (97, 300, 301), (3, 10, 4097), (31, 150, 5000)])
+                                             (63, 150, 151), (97, 300, 301), (3, 10, 4097), (31, 150, 5000),
+                                             # K = 32 N (every bit of the run's last word is used); odd and tiny numbers of windows per read
+                                             (32, 150, 150), (64, 200, 203), (96, 250, 250), (128, 300, 307), (32, 33, 40), (32, 34, 34),
+                                             (30, 150, 150), (33, 151, 160)])
 def test_uniform_ascii_reads_straddle_items(kc, k, length, stride):
     """Uniform ASCII reads: one symbol per offset unit, so a stride that is not a multiple of the item width makes
     items straddle two reads, and the per-slot position has to wrap (strides below and above 4096 take different
@@ -154,6 +157,15 @@ def test_tiny_uniform_strides(kc):
             buf[i * stride:i * stride + length] = np.frombuffer(r, dtype=np.uint8)
         rs = kc.ReadSet(8, buf, 900, uniform_len=length, uniform_stride_words=stride)
         check(kc, rs, [ko.ascii_unambiguous(r, k) for r in reads], k)
+
+
+def test_one_long_sequence_and_a_tail_chunk(kc):
+    """One sequence whose windows do not fill the last chunk of 2048 positions; K = 31 and K = 32."""
+    rng = np.random.default_rng(77)
+    for k, n in ((31, 70_001), (32, 5000), (64, 2048 + 63)):
+        words = kt.pack_codes(codes4(rng, n, 0.01), 4)
+        rs = kc.ReadSet(4, words, 1, uniform_len=n, uniform_stride_words=len(words))
+        check(kc, rs, [ko.unambiguous(words, n, k, src_bits=4)], k)
 
 
 def test_general_path_still_passes_its_suites():
