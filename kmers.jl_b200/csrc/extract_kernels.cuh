@@ -64,6 +64,7 @@ struct ExtractParams {
     uint64_t it_dq, it_dr; // divmod(kBlockThreads, gprm): per-iteration advance of (r, gi)
     uint64_t read_bits;    // stride_units * unit_bits: stream bits from one read to the next (uniform offsets)
     uint32_t aligned;      // uniform set whose windows per read are a multiple of G: item i IS flat group i (set_iteration_strides)
+    uint32_t al_magic;     // floor(2^32 / gprm) (2^32 - 1 for gprm = 1): extract_aligned_kernel divides by gprm with it
     // ragged locator
     const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
     const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
@@ -366,6 +367,36 @@ inline void set_iteration_strides(ExtractParams &p, int g = 0)
 
 
 
+// DIGEST instantiations: the threads' shares of the fingerprint -> one set of atomics per block (same-address atomics
+// serialise in L2).  Every thread of the block calls it.
+KMC_DEV void digest_epilogue(unsigned long long *digest, uint64_t dg_xa, uint64_t dg_sa, uint64_t dg_xh, uint64_t dg_sh)
+{
+    __shared__ uint64_t s_dg[4][kBlockThreads / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        dg_xa ^= __shfl_xor_sync(0xffffffffu, dg_xa, d);
+        dg_sa += __shfl_xor_sync(0xffffffffu, dg_sa, d);
+        dg_xh ^= __shfl_xor_sync(0xffffffffu, dg_xh, d);
+        dg_sh += __shfl_xor_sync(0xffffffffu, dg_sh, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_dg[0][threadIdx.x >> 5] = dg_xa;
+        s_dg[1][threadIdx.x >> 5] = dg_sa;
+        s_dg[2][threadIdx.x >> 5] = dg_xh;
+        s_dg[3][threadIdx.x >> 5] = dg_sh;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int w = 0; w < kBlockThreads / 32; ++w) v = (threadIdx.x & 1) ? v + s_dg[threadIdx.x][w] : v ^ s_dg[threadIdx.x][w];
+        if (threadIdx.x & 1)
+            atomicAdd(digest + threadIdx.x, static_cast<unsigned long long>(v));
+        else
+            atomicXor(digest + threadIdx.x, static_cast<unsigned long long>(v));
+    }
+}
+
 template <int N, int NX, int MODE, bool HASH, bool RAGGED, int SINK = SINK_STREAMS, bool STRICT4 = false, int BPS = 2,
           bool DIGEST = false>
 __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractParams p)
@@ -546,33 +577,121 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
 #if KMC_TMA_STORE
     if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory stays valid until read
 #endif
-    if (DIGEST) {
-        // one set of atomics per block (same-address atomics serialise in L2)
-        __shared__ uint64_t s_dg[4][kBlockThreads / 32];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            dg_xa ^= __shfl_xor_sync(0xffffffffu, dg_xa, d);
-            dg_sa += __shfl_xor_sync(0xffffffffu, dg_sa, d);
-            dg_xh ^= __shfl_xor_sync(0xffffffffu, dg_xh, d);
-            dg_sh += __shfl_xor_sync(0xffffffffu, dg_sh, d);
+    if (DIGEST) digest_epilogue(p.digest, dg_xa, dg_sa, dg_xh, dg_sh);
+}
+
+// ---------------------------------------------------------------------------------------------
+// extract_aligned_kernel: the same work items for the case every headline configuration is in -- a uniform read set
+// (or one sequence) whose windows per read are a multiple of G (C2: 120 = 15 x 8), SoA streams with 32-byte aligned
+// bases, fewer than 2^32 items.  Then item i IS flat group i, all G slots are windows, and nothing of the general
+// kernel's bookkeeping is left: no (read, slot) cursor carried through the loop (one multiply-high by a precomputed
+// reciprocal per item instead), no partial groups, no run-time choice of an output layout, no bounds test on the
+// block load (one test per tile: only a tile that can reach the last words of the buffer takes the clamped loads).
+// The k-mer arithmetic is the shared block_kmers / limbs_less / fx_hash.  SINK_IDS writes the 32-bit bucket id of
+// every window (first pass of the binned count, buckets.cu).
+// ---------------------------------------------------------------------------------------------
+template <int N, int NX, int MODE, bool HASH, int SINK = SINK_STREAMS, int BPS = 2, bool DIGEST = false>
+__global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const ExtractParams p)
+{
+    static_assert(SINK == SINK_STREAMS || (SINK == SINK_IDS && MODE == MODE_CANON && HASH), "bucket ids are hashes of canonical k-mers");
+    constexpr int G = GroupOf<N>::G;
+    constexpr bool WANT_RV = (MODE != MODE_FW);
+    uint64_t dg_xa = 0, dg_sa = 0, dg_xh = 0, dg_sh = 0;
+    const uint32_t n_items = static_cast<uint32_t>(p.items);
+    const uint32_t tile_base = blockIdx.x * static_cast<uint32_t>(kTileItems); // the launcher keeps items below 2^32 - kTileItems
+    if (p.pf_tiles) burst_prefetch<false, G, BPS>(p, n_items);
+    const uint32_t gprm = static_cast<uint32_t>(p.gprm), magic = p.al_magic, read_bits = static_cast<uint32_t>(p.read_bits);
+    const uint64_t first_bits = static_cast<uint64_t>(BPS) * p.first;
+    // bit offset of an item's first symbol; offsets grow with the item, so the tile's last item bounds its loads
+    auto bit_of = [&](uint32_t item) -> uint64_t {
+        uint32_t r = __umulhi(item, magic), gi = item - r * gprm; // r is the quotient or one below it
+        if (gi >= gprm) {
+            gi -= gprm;
+            ++r;
         }
-        if ((threadIdx.x & 31) == 0) {
-            s_dg[0][threadIdx.x >> 5] = dg_xa;
-            s_dg[1][threadIdx.x >> 5] = dg_sa;
-            s_dg[2][threadIdx.x >> 5] = dg_xh;
-            s_dg[3][threadIdx.x >> 5] = dg_sh;
-        }
-        __syncthreads();
-        if (threadIdx.x < 4) {
-            uint64_t v = 0;
+        return static_cast<uint64_t>(r) * read_bits + (first_bits + gi * static_cast<uint32_t>(G * BPS));
+    };
+    const uint32_t tile_last = (n_items - tile_base > static_cast<uint32_t>(kTileItems) ? tile_base + kTileItems : n_items) - 1u;
+    const bool safe = static_cast<int64_t>(bit_of(tile_last) >> 5) + NX < p.nw32; // block-uniform
+
+#pragma unroll 1
+    for (int it = 0; it < kTileIters; ++it) {
+        const uint32_t item = tile_base + static_cast<uint32_t>(it) * kBlockThreads + threadIdx.x;
+        if (item >= n_items) break;
+        const uint64_t bit = bit_of(item);
+        uint32_t x[NX];
+        if (safe) {
+            const uint32_t *w = p.w32 + (bit >> 5);
+            uint32_t a[NX + 1];
 #pragma unroll
-            for (int w = 0; w < kBlockThreads / 32; ++w) v = (threadIdx.x & 1) ? v + s_dg[threadIdx.x][w] : v ^ s_dg[threadIdx.x][w];
-            if (threadIdx.x & 1)
-                atomicAdd(p.digest + threadIdx.x, static_cast<unsigned long long>(v));
-            else
-                atomicXor(p.digest + threadIdx.x, static_cast<unsigned long long>(v));
+            for (int i = 0; i <= NX; ++i) a[i] = __ldg(w + i);
+            const uint32_t sh = static_cast<uint32_t>(bit) & 31u;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = __funnelshift_r(a[i], a[i + 1], sh);
+        } else {
+            load_block<NX>(p.w32, p.nw32, static_cast<int64_t>(bit), x);
+        }
+        uint64_t fw[G][N], rv[G][N];
+        block_kmers<N, NX, G, true, WANT_RV, BPS>(x, p.s0, p.head_mask, fw, rv);
+
+        uint64_t a[G][N], h[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            bool take_fw = true;
+            if (MODE == MODE_CANON) take_fw = limbs_less<N>(fw[j], rv[j]);
+#pragma unroll
+            for (int i = 0; i < N; ++i) a[j][i] = take_fw ? fw[j][i] : rv[j][i];
+            if (HASH) h[j] = fx_hash<N>(a[j], 0);
+            if (DIGEST) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    dg_xa ^= a[j][i];
+                    dg_sa += a[j][i];
+                }
+                if (HASH) {
+                    dg_xh ^= h[j];
+                    dg_sh += h[j];
+                }
+            }
+        }
+
+        if constexpr (SINK == SINK_IDS) {
+            // G ids = G / 2 words; the group is 4 G bytes and the base is 32-byte aligned
+            uint64_t w[G / 2];
+#pragma unroll
+            for (int t = 0; t < G / 2; ++t) w[t] = (h[2 * t] >> p.bucket_shift) | ((h[2 * t + 1] >> p.bucket_shift) << 32);
+            uint64_t *dst = p.out_a + static_cast<uint64_t>(item) * (G / 2);
+            if (G == 8) st_v4(dst, w[0], w[1 % (G / 2)], w[2 % (G / 2)], w[3 % (G / 2)]);
+            else if (G == 4) st_v2(dst, w[0], w[1 % (G / 2)]);
+            else st_u64(dst, w[0]);
+        } else {
+            uint64_t buf[G * N];
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+#pragma unroll
+                for (int i = 0; i < N; ++i) buf[j * N + i] = a[j][i];
+            store_run<G * N>(p.out_a + static_cast<uint64_t>(item) * (G * N), buf, true);
+            if (MODE == MODE_FWRV) {
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) buf[j * N + i] = rv[j][i];
+                store_run<G * N>(p.out_b + static_cast<uint64_t>(item) * (G * N), buf, true);
+            }
+            if (HASH) store_run<G>(p.out_hash + static_cast<uint64_t>(item) * G, h, true);
         }
     }
+    if (DIGEST) digest_epilogue(p.digest, dg_xa, dg_sa, dg_xh, dg_sh);
+}
+
+// KMC_ALIGNED_KERNEL=0 sends aligned uniform sets through the general kernel (A/B measurements, and the tests of both)
+inline bool aligned_kernel_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("KMC_ALIGNED_KERNEL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 // Host-side launcher: one block per tile of kTileItems work items.  Defined per N in
@@ -604,6 +723,15 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
         if (e != cudaSuccess) return e;
     }
 #endif
+    if constexpr (!RAGGED && !STRICT4 && SINK != SINK_BUCKETS && !KMC_TMA_STORE) {
+        const bool plain_soa = SINK == SINK_IDS || (!p.aos && !p.out_index);
+        if (p.aligned && p.vec_ok && plain_soa && !p.items_dev && p.gprm < 0x80000000ull &&
+            p.items < 0xffffffffull - kTileItems && aligned_kernel_enabled()) {
+            p.al_magic = p.gprm == 1 ? 0xffffffffu : static_cast<uint32_t>(0x100000000ull / p.gprm);
+            extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
     extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS, DIGEST>
         <<<static_cast<unsigned>(tiles), kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();

@@ -115,12 +115,35 @@ KMC_DEV bool limbs_less(const uint64_t (&a)[N], const uint64_t (&b)[N])
     return lt;
 }
 
+// x * FX_CONSTANT mod 2^64.  On the device: one 32 x 32 -> 64-bit product and two multiply-adds into its high half
+// (the compiler's own expansion takes a fourth instruction; this multiplication runs once per k-mer and limb).
+KMC_DEV uint64_t mul_fx(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 xl, xh, pl, ph;\n\t"
+        "mov.b64 {xl, xh}, %1;\n\t"
+        "mul.lo.u32 pl, xl, 0x27220a95;\n\t"
+        "mul.hi.u32 ph, xl, 0x27220a95;\n\t"
+        "mad.lo.u32 ph, xh, 0x27220a95, ph;\n\t"
+        "mad.lo.u32 ph, xl, 0x517cc1b7, ph;\n\t"
+        "mov.b64 %0, {pl, ph};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(x));
+    return r;
+#else
+    return x * FX_CONSTANT;
+#endif
+}
+
 // fx_hash (src/kmer.jl:255-261)
 template <int N>
 KMC_DEV uint64_t fx_hash(const uint64_t (&d)[N], uint64_t h)
 {
 #pragma unroll
-    for (int i = 0; i < N; ++i) h = (((h << 5) | (h >> 59)) ^ d[i]) * FX_CONSTANT;
+    for (int i = 0; i < N; ++i) h = mul_fx(((h << 5) | (h >> 59)) ^ d[i]);
     return h;
 }
 
@@ -262,6 +285,15 @@ KMC_DEV void load_block(const uint32_t *__restrict__ w32, int64_t nw32, int64_t 
 // alphabet (and of the stream): 2 or 4.
 //   s0        = 32*NX - BPS*K - BPS*(G-1), in [0, 32)
 //   head_mask = get_mask (src/kmer.jl:603-605)
+// The head limb holds BPS*K - 64(N-1) bits, and a block of NX words only serves K with BPS*K + BPS*(G-1) > 32(NX-1): where
+// that leaves at least 32 bits in the head limb, the low half of head_mask is all ones and only the high half is applied.
+template <int N, int NX, int G, int BPS> KMC_DEV uint64_t mask_head(uint64_t v, uint64_t head_mask)
+{
+    constexpr bool kLoFull = 32 * (NX - 1) - BPS * (G - 1) + 1 - 64 * (N - 1) >= 32;
+    if (kLoFull) return pack64(static_cast<uint32_t>(v), static_cast<uint32_t>(v >> 32) & static_cast<uint32_t>(head_mask >> 32));
+    return v & head_mask;
+}
+
 template <int N, int NX, int G, bool WANT_FW, bool WANT_RV, int BPS = 2>
 KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mask, uint64_t (&fw)[G][N],
                          uint64_t (&rv)[G][N])
@@ -277,7 +309,7 @@ KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mas
 #pragma unroll
             for (int m = 0; m < N; ++m) { // m = 0 is the least significant limb
                 uint64_t v = stream64<NX>(nx, BPS * j + 64 * m);
-                if (m == N - 1) v &= head_mask;
+                if (m == N - 1) v = mask_head<N, NX, G, BPS>(v, head_mask);
                 rv[j][N - 1 - m] = v;
             }
         }
@@ -296,7 +328,7 @@ KMC_DEV void block_kmers(const uint32_t (&x)[NX], uint32_t s0, uint64_t head_mas
 #pragma unroll
             for (int m = 0; m < N; ++m) {
                 uint64_t v = stream64<NX>(t, BPS * (G - 1 - j) + 64 * m);
-                if (m == N - 1) v &= head_mask;
+                if (m == N - 1) v = mask_head<N, NX, G, BPS>(v, head_mask);
                 fw[j][N - 1 - m] = v;
             }
         }

@@ -183,6 +183,45 @@ def test_uniform_read_set(kc, k, length):
             assert np.array_equal(e.rv, b)
 
 
+# windows per read a multiple of the group size G (8 / 4 / 4 / 2 for 1..4 limbs): extract_aligned_kernel, every
+# (limbs, block width) class of its launcher tables; the read count leaves a partial last tile
+@pytest.mark.parametrize("k,length", [(3, 10), (9, 24), (10, 25), (16, 31), (25, 64), (26, 65), (31, 150), (32, 63),
+                                      (33, 36), (40, 47), (47, 54), (48, 59), (57, 64), (64, 151),
+                                      (65, 72), (72, 75), (81, 88), (96, 211),
+                                      (97, 98), (104, 113), (113, 126), (128, 255)])
+def test_aligned_uniform_sets(kc, k, length):
+    rng = np.random.default_rng(k * 977 + length)
+    g = {1: 8, 2: 4, 3: 4, 4: 2}[(2 * k + 63) // 64]
+    assert (length - k + 1) % g == 0
+    stride = (length + 31) // 32 + (k % 2)
+    n_reads = 2048 * 3 * g // (length - k + 1) + 37
+    words = rng.integers(0, 2**64, size=n_reads * stride, dtype=np.uint64)
+    rs = kc.ReadSet(2, words, n_reads, uniform_len=length, uniform_stride_words=stride)
+    for mode, omode, hash_ in (("canon", ko.CANON, True), ("fwrv", ko.FWRV, False), ("fw", ko.FW, True), ("canon", ko.CANON, False)):
+        a, b, h, _ = ko.batch_iterate(words, n_reads, k, omode, uniform_len=length, uniform_stride=stride, want_hash=True)
+        e = kc.extract(MODES[mode], rs, k, hash=hash_)
+        assert e.n == a.shape[0] and np.array_equal(e.kmers, a)
+        if hash_:
+            assert np.array_equal(e.hash, h)
+        if b is not None:
+            assert np.array_equal(e.rv, b)
+
+
+def test_aligned_single_sequence_and_views(kc):
+    """One long sequence whose window count is a multiple of G (one read of the uniform locator: the quotient of every
+    item is 0), and views that start inside a word; the last tile reaches the end of the buffer (clamped loads)."""
+    rng = np.random.default_rng(4242)
+    for k in (31, 63, 21):
+        g = 8 if k <= 32 else 4
+        for first in (0, 5, 17):
+            n = 40_000 * g + k - 1
+            w = rng.integers(0, 2**64, size=(n + first + 31) // 32, dtype=np.uint64)
+            rs = kc.ReadSet(2, w, 1, uniform_len=n, uniform_stride_words=w.size, first_symbol_offset=first)
+            a, _, h = ko.iterate(w, n, k, ko.CANON, first=first, want_hash=True)
+            e = kc.extract(MODES["canon"], rs, k, hash=True)
+            assert e.n == a.shape[0] and np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+
+
 def test_subsequence_views(kc):
     """first_symbol_offset: a LongSubSeq-style view starting inside a word."""
     rng = np.random.default_rng(77)
@@ -347,7 +386,8 @@ def test_host_sequences_device_outputs_and_digest(kc, ctx):
 
 
 @pytest.mark.parametrize("mode,k,hash_,ragged", [("fw", 31, False, False), ("canon", 63, True, True), ("fw", 5, True, True),
-                                                 ("canon", 32, False, False)])
+                                                 ("canon", 32, False, False), ("canon", 31, True, False),
+                                                 ("canon", 63, True, False)])
 def test_digest_fused_into_the_extraction_kernel(kc, ctx, mode, k, hash_, ragged):
     """KMC_DIGEST for the SoA forms of FwKmers / CanonicalKmers over 2-bit sources comes out of the extraction kernel
     itself (no second pass over the streams): one- and two-limb k-mers, with and without the hash stream, uniform and
