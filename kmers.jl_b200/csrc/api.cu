@@ -617,6 +617,38 @@ int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t
     bool binned = table_bytes > (96ull << 20) && bucket_bits <= 32;
     AsyncBuf ids_buf, tmp_buf, matrix_buf, offs_buf, scan_buf; // freed (stream-ordered) on every way out
     const uint64_t n_ids = (L.items + 1) * static_cast<uint64_t>(ge.g); // flat windows, rounded up to whole groups
+    if (binned && ge.n_limbs == 1 && L.uniform_len && binned_count_bin_bits(bucket_bits) == 6 && fused_bin_enabled()) {
+        // One-limb k-mers over an aligned uniform set (C5): ids and bins from one kernel, bins of a fixed capacity.  A bin
+        // that overflows (a set whose k-mers crowd into one range of buckets) sends the call to the exact path below.
+        ExtractParams q = p;
+        set_iteration_strides(q, ge.g);
+        if (q.aligned && q.items < 0xffffffffull - kTileItems) {
+            AsyncBuf bins_buf, cursor_buf;
+            const uint64_t cap = fused_bin_capacity(L.total);
+            cudaError_t e = bins_buf.alloc(ctx, (cap * 64 + 4096) * 4, stream); // 64 bins + the dump area of one iteration
+            if (e == cudaSuccess) e = cursor_buf.alloc(ctx, 65 * 8, stream);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+            } else {
+                st = ensure_host_small(ctx);
+                if (st) return st;
+                unsigned long long *cursor = cursor_buf.as<unsigned long long>();
+                CU(fused_bin_ids(q, ge.nx, bucket_bits, bins_buf.as<uint32_t>(), cap, cursor, stream));
+                uint64_t *flag = ctx->host_small + 64;
+                CU(cudaMemcpyAsync(flag, cursor + 64, 8, cudaMemcpyDeviceToHost, stream));
+                CU(cudaStreamSynchronize(stream)); // ~10 us: the table must not be touched before the bins are known to be whole
+                if (*flag == 0) {
+                    CU(fused_bin_apply(bins_buf.as<uint32_t>(), cap, cursor, bucket_bits, table, warm_sink(ctx), ctx->sm_count, stream,
+                                       n_parts, events));
+                    if (n_parts) return KMC_OK;
+                    CU(cudaEventRecord(ctx->ev_k1, stream));
+                    CU(cudaStreamSynchronize(stream));
+                    CU(cudaEventElapsedTime(&result->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+                    return KMC_OK;
+                }
+            }
+        }
+    }
     if (binned) {
         const uint64_t cells = (static_cast<uint64_t>(1) << binned_count_bin_bits(bucket_bits)) * binned_count_blocks(n_ids);
         cudaError_t e = ids_buf.alloc(ctx, round_up(n_ids * 4, 256), stream);

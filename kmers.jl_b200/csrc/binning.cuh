@@ -172,114 +172,143 @@ template <typename Key> struct Scatter64Smem {
     uint32_t tot[kTpBins];
 };
 
+// One iteration of the 64-bin scatter: the block's kPerIter keys (PT per thread, in registers) are counted per bin,
+// ranked, staged in shared memory in bin order and written out as one run per bin.  reserve(bin, count), called by the
+// lanes of warp 0 for the bins 2 * lane and 2 * lane + 1, returns the index in `out` of the run of `count` keys of `bin`.
+// FULL (block-uniform, a template parameter so that the common case carries no per-key tests or branches): all
+// kPerIter keys exist; otherwise bit j of ok_mask says whether key[j] does.  Ends without a barrier: the next
+// iteration's writes to cnt / off / start / dst are ordered behind this one's reads by its own barriers.
+template <typename Key, bool FULL, typename BinOf, typename Reserve>
+__device__ __forceinline__ void scatter64_iter(Scatter64Smem<Key> &sm, const Key (&key)[Shape<Key>::kPerThread], uint32_t ok_mask,
+                                               BinOf bin_of, Reserve reserve, Key *__restrict__ out)
+{
+    using S = Shape<Key>;
+    constexpr int PT = S::kPerThread;
+    static_assert(PT * kBlock == S::kPerIter, "the write-out of a full iteration takes PT keys per thread");
+    constexpr bool kStageBins = sizeof(Key) == 8; // recomputing a hash bin at write-out costs more than a byte of staging
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int g = 0; g < kTpGroups; ++g) sm.cnt[g][threadIdx.x] = 0;
+    uint32_t rank[PT / 4], bins[kStageBins ? PT / 4 : 1]; // four byte fields per word (a rank is < PT, a bin < 64)
+    uint8_t *cnt = reinterpret_cast<uint8_t *>(&sm.cnt[0][0]);
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+        const uint32_t b = bin_of(key[j]);
+        uint32_t r = 0;
+        if (FULL || ((ok_mask >> j) & 1u)) r = tp_count(cnt, b);
+        rank[j / 4] = (j % 4 == 0) ? r : (rank[j / 4] | (r << (8 * (j % 4))));
+        if (kStageBins) bins[j / 4] = (j % 4 == 0) ? b : (bins[j / 4] | (b << (8 * (j % 4))));
+    }
+    __syncthreads();
+    // exclusive prefix of every bin's counters over the threads in (lane, warp) order
+#pragma unroll
+    for (int q = 0; q < kTpGroups / kWarps; ++q) {
+        const int g = warp * (kTpGroups / kWarps) + q;
+        uint32_t lo[kBlock / 32], hi[kBlock / 32], slo = 0, shi = 0;
+#pragma unroll
+        for (int i = 0; i < kBlock / 32; ++i) {
+            const uint32_t x = sm.cnt[g][lane + 32 * i];
+            lo[i] = slo;
+            hi[i] = shi;
+            slo += x & 0x00ff00ffu;
+            shi += (x >> 8) & 0x00ff00ffu;
+        }
+        uint32_t ilo = slo, ihi = shi;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, ilo, d), b = __shfl_up_sync(0xffffffffu, ihi, d);
+            if (lane >= d) {
+                ilo += a;
+                ihi += b;
+            }
+        }
+        const uint32_t blo = ilo - slo, bhi = ihi - shi;
+#pragma unroll
+        for (int i = 0; i < kBlock / 32; ++i) {
+            sm.off[2 * g + 0][lane + 32 * i] = blo + lo[i]; // bins 4g (low field) and 4g + 2 (high field)
+            sm.off[2 * g + 1][lane + 32 * i] = bhi + hi[i]; // bins 4g + 1 and 4g + 3
+        }
+        if (lane == 31) {
+            sm.tot[4 * g + 0] = ilo & 0xffffu;
+            sm.tot[4 * g + 1] = ihi & 0xffffu;
+            sm.tot[4 * g + 2] = ilo >> 16;
+            sm.tot[4 * g + 3] = ihi >> 16;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) { // exclusive scan of the 64 totals
+        const uint32_t t0 = sm.tot[2 * lane], t1 = sm.tot[2 * lane + 1];
+        uint32_t incl = t0 + t1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += a;
+        }
+        const uint32_t s0 = incl - t0 - t1, s1 = incl - t1;
+        sm.start[2 * lane] = s0;
+        sm.start[2 * lane + 1] = s1;
+        sm.dst[2 * lane] = reserve(2 * lane, t0) - s0;
+        sm.dst[2 * lane + 1] = reserve(2 * lane + 1, t1) - s1;
+        if (lane == 31) sm.start[kTpBins] = incl;
+    }
+    __syncthreads();
+    const uint32_t *off_col = &sm.off[0][threadIdx.x];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+        if (FULL || ((ok_mask >> j) & 1u)) {
+            const uint32_t b = kStageBins ? ((bins[j / 4] >> (8 * (j % 4))) & 0xffu) : bin_of(key[j]);
+            const uint32_t w = off_col[(((b >> 1) & ~1u) | (b & 1u)) * kBlock];
+            const uint32_t slot = sm.start[b] + ((w >> ((b & 2u) << 3)) & 0xffffu) + ((rank[j / 4] >> (8 * (j % 4))) & 0xffu);
+            sm.keys[slot] = key[j];
+            if (kStageBins) sm.bins[slot] = static_cast<uint8_t>(b);
+        }
+    }
+    __syncthreads();
+    if (FULL) {
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            const uint32_t t = threadIdx.x + i * kBlock;
+            const Key v = sm.keys[t];
+            const uint32_t b = kStageBins ? static_cast<uint32_t>(sm.bins[t]) : bin_of(v);
+            out[sm.dst[b] + t] = v; // (dst wraps; only the sum is used)
+        }
+    } else {
+        const uint32_t total = sm.start[kTpBins];
+        for (uint32_t t = threadIdx.x; t < total; t += kBlock) {
+            const Key v = sm.keys[t];
+            const uint32_t b = kStageBins ? static_cast<uint32_t>(sm.bins[t]) : bin_of(v);
+            out[sm.dst[b] + t] = v;
+        }
+    }
+}
+
 // out[offs[bin * n_blocks + block] ...) receives the block's keys of bin `bin` (any order within the bin)
 template <typename Key, typename BinOf>
 __global__ void __launch_bounds__(kBlock, 3) scatter64_kernel(const Key *__restrict__ in, uint64_t n, BinOf bin_of, uint64_t n_blocks,
                                                              const uint64_t *__restrict__ offs, Key *__restrict__ out)
 {
     using S = Shape<Key>;
-    constexpr int PT = S::kPerThread;
-    constexpr bool kStageBins = sizeof(Key) == 8; // recomputing a hash bin at write-out costs more than a byte of staging
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Scatter64Smem<Key> &sm = *reinterpret_cast<Scatter64Smem<Key> *>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < kTpBins) sm.glob[threadIdx.x] = offs[static_cast<uint64_t>(threadIdx.x) * n_blocks + blockIdx.x];
     const uint64_t base = static_cast<uint64_t>(blockIdx.x) * S::kChunk;
     for (int it = 0; it < kIters; ++it) {
         const uint64_t it_base = base + static_cast<uint64_t>(it) * S::kPerIter;
         if (it_base >= n) break; // block-uniform
         const bool full = it_base + S::kPerIter <= n; // block-uniform: all but the last iteration of the last block
-#pragma unroll
-        for (int g = 0; g < kTpGroups; ++g) sm.cnt[g][threadIdx.x] = 0;
-        Key key[PT];
+        Key key[S::kPerThread];
         uint32_t ok_mask;
-        uint32_t rank[PT / 4], bins[kStageBins ? PT / 4 : 1]; // four byte fields per word (a rank is < PT, a bin < 64)
         load_iter(in, n, it_base, key, ok_mask);
-        uint8_t *cnt = reinterpret_cast<uint8_t *>(&sm.cnt[0][0]);
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-            const uint32_t b = bin_of(key[j]);
-            uint32_t r = 0;
-            if (full || ((ok_mask >> j) & 1u)) r = tp_count(cnt, b);
-            rank[j / 4] = (j % 4 == 0) ? r : (rank[j / 4] | (r << (8 * (j % 4))));
-            if (kStageBins) bins[j / 4] = (j % 4 == 0) ? b : (bins[j / 4] | (b << (8 * (j % 4))));
-        }
-        __syncthreads();
-        // exclusive prefix of every bin's counters over the threads in (lane, warp) order
-#pragma unroll
-        for (int q = 0; q < kTpGroups / kWarps; ++q) {
-            const int g = warp * (kTpGroups / kWarps) + q;
-            uint32_t lo[kBlock / 32], hi[kBlock / 32], slo = 0, shi = 0;
-#pragma unroll
-            for (int i = 0; i < kBlock / 32; ++i) {
-                const uint32_t x = sm.cnt[g][lane + 32 * i];
-                lo[i] = slo;
-                hi[i] = shi;
-                slo += x & 0x00ff00ffu;
-                shi += (x >> 8) & 0x00ff00ffu;
-            }
-            uint32_t ilo = slo, ihi = shi;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t a = __shfl_up_sync(0xffffffffu, ilo, d), b = __shfl_up_sync(0xffffffffu, ihi, d);
-                if (lane >= d) {
-                    ilo += a;
-                    ihi += b;
-                }
-            }
-            const uint32_t blo = ilo - slo, bhi = ihi - shi;
-#pragma unroll
-            for (int i = 0; i < kBlock / 32; ++i) {
-                sm.off[2 * g + 0][lane + 32 * i] = blo + lo[i]; // bins 4g (low field) and 4g + 2 (high field)
-                sm.off[2 * g + 1][lane + 32 * i] = bhi + hi[i]; // bins 4g + 1 and 4g + 3
-            }
-            if (lane == 31) {
-                sm.tot[4 * g + 0] = ilo & 0xffffu;
-                sm.tot[4 * g + 1] = ihi & 0xffffu;
-                sm.tot[4 * g + 2] = ilo >> 16;
-                sm.tot[4 * g + 3] = ihi >> 16;
-            }
-        }
-        __syncthreads();
-        if (warp == 0) { // exclusive scan of the 64 totals
-            const uint32_t t0 = sm.tot[2 * lane], t1 = sm.tot[2 * lane + 1];
-            uint32_t incl = t0 + t1;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t a = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += a;
-            }
-            const uint32_t s0 = incl - t0 - t1, s1 = incl - t1;
-            sm.start[2 * lane] = s0;
-            sm.start[2 * lane + 1] = s1;
-            sm.dst[2 * lane] = sm.glob[2 * lane] - s0;
-            sm.dst[2 * lane + 1] = sm.glob[2 * lane + 1] - s1;
-            sm.glob[2 * lane] += t0;
-            sm.glob[2 * lane + 1] += t1;
-            if (lane == 31) sm.start[kTpBins] = incl;
-        }
-        __syncthreads();
-        const uint32_t *off_col = &sm.off[0][threadIdx.x];
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-            if (full || ((ok_mask >> j) & 1u)) {
-                const uint32_t b = kStageBins ? ((bins[j / 4] >> (8 * (j % 4))) & 0xffu) : bin_of(key[j]);
-                const uint32_t w = off_col[(((b >> 1) & ~1u) | (b & 1u)) * kBlock];
-                const uint32_t slot = sm.start[b] + ((w >> ((b & 2u) << 3)) & 0xffffu) + ((rank[j / 4] >> (8 * (j % 4))) & 0xffu);
-                sm.keys[slot] = key[j];
-                if (kStageBins) sm.bins[slot] = static_cast<uint8_t>(b);
-            }
-        }
-        __syncthreads();
-        const uint32_t total = full ? static_cast<uint32_t>(S::kPerIter) : sm.start[kTpBins];
-#pragma unroll 4
-        for (uint32_t t = threadIdx.x; t < total; t += kBlock) {
-            const Key v = sm.keys[t];
-            const uint32_t b = kStageBins ? static_cast<uint32_t>(sm.bins[t]) : bin_of(v);
-            out[sm.dst[b] + t] = v;
-        }
-        // the next iteration's writes to cnt / off / start / dst are ordered behind these reads by its barriers;
-        // its writes to keys / bins come after its third barrier
+        // (sm.glob was filled before the first iteration's barriers; only warp 0 touches it afterwards)
+        auto reserve = [&](int b, uint32_t count) {
+            const uint64_t g = sm.glob[b];
+            sm.glob[b] = g + count;
+            return g;
+        };
+        if (full)
+            scatter64_iter<Key, true>(sm, key, ok_mask, bin_of, reserve, out);
+        else
+            scatter64_iter<Key, false>(sm, key, ok_mask, bin_of, reserve, out);
     }
 }
 

@@ -11,6 +11,7 @@
 //     table is final range by range, which kmc_bucket_count_async reports through events so that the merge of
 //     several GPUs' tables can overlap the count.
 #include <cstdlib>
+#include <type_traits>
 
 #include "binning.cuh"
 #include "plan.h"
@@ -62,6 +63,112 @@ __global__ void __launch_bounds__(256) bin_apply_kernel(const uint32_t *__restri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The fused first half of the binned count for the common case -- one-limb k-mers (K <= 32) over an aligned uniform
+// read set (extract_kernels.cuh: AlignedItems; C5 is 150 bp reads, K = 31).  The three passes of the exact path
+// (bucket ids written out, per-chunk bin histogram, scatter) read and write 12 bytes per k-mer three times over and
+// need the histogram only to know where every chunk's run of every bin goes.  Counting does not care about the order
+// inside a bin, so here ONE kernel produces the ids and bins them: a block computes the canonical k-mers and hashes
+// of 4096 windows per iteration (16 per thread, in registers), runs the same shared-memory binning step
+// (binning.cuh: scatter64_iter) and reserves the place of each of its 64 runs with one atomicAdd on the bin's
+// cursor.  The bins have a fixed capacity, mean + 12.5 % + 8192: fx_hash spreads distinct k-mers evenly, and a set in
+// which one bucket range attracts that much more than its share (reads of one repeated k-mer, say) overflows a bin --
+// its runs go to a dump area, the flag is set, and the caller repeats the count on the exact path (tests/test_gpu_parity.py
+// forces that).  4.2 + 1.9 + 7.9 ms of the 30.6 ms per 3 G k-mers become one kernel.
+// ---------------------------------------------------------------------------------------------
+struct FusedBins {
+    uint32_t *binned;             // 64 bins of `cap` ids each, then a dump area of one iteration's ids (runs that found their bin full)
+    uint64_t cap;                 // a multiple of 4 (the apply kernel loads 16 bytes at a time)
+    unsigned long long *cursor;   // [64] ids reserved per bin, [64] = overflow flag
+    int bin_shift;                // bin = id >> bin_shift
+};
+
+template <int NX>
+__global__ void __launch_bounds__(binning::kBlock, 3) bucket_bin_kernel(const ExtractParams p, const FusedBins f)
+{
+    using S = binning::Shape<uint32_t>;
+    constexpr int G = 8, PT = S::kPerThread;
+    static_assert(PT == 2 * G && S::kChunk == kTileItems * G, "a thread bins the ids of two work items per iteration");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    binning::Scatter64Smem<uint32_t> &sm = *reinterpret_cast<binning::Scatter64Smem<uint32_t> *>(smem_raw);
+    const uint32_t n_items = static_cast<uint32_t>(p.items);
+    const uint32_t tile_base = blockIdx.x * static_cast<uint32_t>(kTileItems);
+    if (p.pf_tiles) burst_prefetch<false, G, 2>(p, n_items);
+    const AlignedItems<G, 2> items(p);
+    const uint32_t tile_end = n_items - tile_base > static_cast<uint32_t>(kTileItems) ? tile_base + kTileItems : n_items;
+    const bool inside = items.template loads_inside<NX>(p, tile_end - 1u);
+    const binning::IdBin bin_of{f.bin_shift};
+    constexpr int kItemsPerIter = 2 * binning::kBlock;
+    // where the run of `count` ids of bin b goes; a run that does not fit is sent to the dump area behind the last bin
+    auto reserve = [&](int b, uint32_t count) -> uint64_t {
+        if (count == 0) return 0;
+        const uint64_t at = atomicAdd(f.cursor + b, static_cast<unsigned long long>(count));
+        if (at + count > f.cap) {
+            f.cursor[binning::kTpBins] = 1; // the bin is full: the caller repeats the count on the exact path
+            return binning::kTpBins * f.cap;
+        }
+        return static_cast<uint64_t>(b) * f.cap + at;
+    };
+    // the bucket ids of one work item (its G windows)
+    auto ids_of = [&](uint32_t item, uint32_t *key) {
+        uint32_t x[NX];
+        load_block_at<NX>(p, items.bit_of(item), inside, x);
+        uint64_t fw[G][1], rv[G][1];
+        block_kmers<1, NX, G, true, true, 2>(x, p.s0, p.head_mask, fw, rv);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint64_t c[1] = {fw[j][0] < rv[j][0] ? fw[j][0] : rv[j][0]};
+            key[j] = static_cast<uint32_t>(fx_hash<1>(c, 0) >> p.bucket_shift);
+        }
+    };
+#pragma unroll 1
+    for (uint32_t it_base = tile_base; it_base < tile_end; it_base += kItemsPerIter) {
+        uint32_t key[PT];
+        if (tile_end - it_base >= static_cast<uint32_t>(kItemsPerIter)) { // block-uniform: every iteration but the set's last
+            ids_of(it_base + threadIdx.x, key);
+            ids_of(it_base + binning::kBlock + threadIdx.x, key + G);
+            binning::scatter64_iter<uint32_t, true>(sm, key, 0xffffu, bin_of, reserve, f.binned);
+        } else {
+            uint32_t ok_mask = 0;
+#pragma unroll
+            for (int j = 0; j < PT; ++j) key[j] = 0;
+            if (it_base + threadIdx.x < tile_end) {
+                ids_of(it_base + threadIdx.x, key);
+                ok_mask = 0xffu;
+            }
+            if (it_base + binning::kBlock + threadIdx.x < tile_end) {
+                ids_of(it_base + binning::kBlock + threadIdx.x, key + G);
+                ok_mask |= 0xff00u;
+            }
+            binning::scatter64_iter<uint32_t, false>(sm, key, ok_mask, bin_of, reserve, f.binned);
+        }
+    }
+}
+
+// the ids of bin b are binned[b * cap .. b * cap + min(cursor[b], cap))
+__global__ void __launch_bounds__(256) bin_apply_fused_kernel(const uint32_t *__restrict__ binned, uint64_t cap,
+                                                              const unsigned long long *__restrict__ cursor, int bin, int bin_end,
+                                                              uint32_t *__restrict__ table)
+{
+    const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t threads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (int b = bin; b < bin_end; ++b) {
+        const uint32_t *ids = binned + static_cast<uint64_t>(b) * cap; // 16-byte aligned: cap is a multiple of 4
+        uint64_t n = cursor[b];
+        if (n > cap) n = cap;
+        const uint64_t n4 = n & ~3ull;
+        for (uint64_t i = tid * 4; i < n4; i += threads * 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ids + i));
+            atomicAdd(table + v.x, 1u);
+            atomicAdd(table + v.y, 1u);
+            atomicAdd(table + v.z, 1u);
+            atomicAdd(table + v.w, 1u);
+        }
+        if (tid < n - n4) atomicAdd(table + ids[n4 + tid], 1u);
+    }
+}
+
 } // namespace
 
 // ids[0..n) are bucket ids of `bucket_bits` bits; adds their histogram to table.  tmp: n u32 (binned ids),
@@ -99,6 +206,81 @@ cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint3
         }
     }
     return cudaGetLastError();
+}
+
+uint64_t fused_bin_capacity(uint64_t n_ids)
+{
+    const uint64_t cap = n_ids / binning::kTpBins + n_ids / (8 * binning::kTpBins) + 8192;
+    return (cap + 3) & ~3ull;
+}
+
+// First half: cursor (65 u64) is zeroed, then one kernel bins the bucket ids of every window.  p: the parameter block of an
+// aligned uniform set of one-limb k-mers (the caller has checked that), bucket_shift set.
+cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *binned, uint64_t cap, unsigned long long *cursor,
+                          cudaStream_t stream)
+{
+    const int pbits = binned_count_bin_bits(bucket_bits);
+    if (pbits != 6 || bucket_bits < pbits) return cudaErrorInvalidValue;
+    const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
+    if (tiles == 0 || tiles > 0x7fffffffull || p.items >= 0xffffffffull - kTileItems) return cudaErrorInvalidConfiguration;
+    set_iteration_strides(p, 8);
+    if (!p.aligned) return cudaErrorInvalidValue;
+    p.al_magic = aligned_magic(p.gprm);
+    p.pf_tiles = 0;
+    if (prefetch_enabled()) {
+        const uint64_t per_tile = static_cast<uint64_t>(p.nw32) * 4 / tiles + 1, t = kPfChunkBytes / per_tile;
+        p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
+    }
+    cudaError_t e = cudaMemsetAsync(cursor, 0, (binning::kTpBins + 1) * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    const FusedBins f{binned, cap, cursor, bucket_bits - pbits};
+    constexpr int smem = static_cast<int>(sizeof(binning::Scatter64Smem<uint32_t>));
+    auto launch = [&](auto tag) -> cudaError_t {
+        constexpr int NX = decltype(tag)::value;
+        cudaError_t e2 = cudaFuncSetAttribute(bucket_bin_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e2 != cudaSuccess) return e2;
+        bucket_bin_kernel<NX><<<static_cast<unsigned>(tiles), binning::kBlock, smem, stream>>>(p, f);
+        return cudaGetLastError();
+    };
+    switch (nx) {
+    case 1: return launch(std::integral_constant<int, 1>());
+    case 2: return launch(std::integral_constant<int, 2>());
+    case 3: return launch(std::integral_constant<int, 3>());
+    }
+    return cudaErrorInvalidValue;
+}
+
+// Second half (once the caller has seen that no bin overflowed): the bins are applied in table order, as in binned_count.
+cudaError_t fused_bin_apply(const uint32_t *binned, uint64_t cap, const unsigned long long *cursor, int bucket_bits, uint32_t *table,
+                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events)
+{
+    if (!events) n_parts = 0;
+    const int pbits = binned_count_bin_bits(bucket_bits);
+    const int n_bins = 1 << pbits, shift = bucket_bits - pbits;
+    const uint64_t slice = 1ull << shift;
+    const int group = apply_group(2);
+    uint32_t parts_done = 0;
+    for (int b = 0; b < n_bins; b += group) {
+        const int b_end = b + group < n_bins ? b + group : n_bins;
+        warm_slice_kernel<<<static_cast<unsigned>(sm_count * 8), 256, 0, stream>>>(table + static_cast<uint64_t>(b) * slice,
+                                                                                  slice * (b_end - b), sink);
+        bin_apply_fused_kernel<<<static_cast<unsigned>(sm_count * 16), 256, 0, stream>>>(binned, cap, cursor, b, b_end, table);
+        while (parts_done < n_parts && static_cast<uint64_t>(parts_done + 1) * n_bins <= static_cast<uint64_t>(b_end) * n_parts) {
+            cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(events[parts_done++]), stream);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaGetLastError();
+}
+
+// KMC_FUSED_BIN=0 keeps every binned count on the exact three-pass path (A/B measurements, tests of both)
+bool fused_bin_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("KMC_FUSED_BIN");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 // Bins applied per launch.  Measured on a B200 (KMC_APPLY_GROUP overrides, for experiments): the bucket table

@@ -580,6 +580,51 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
     if (DIGEST) digest_epilogue(p.digest, dg_xa, dg_sa, dg_xh, dg_sh);
 }
 
+// The work items of an aligned uniform set (ExtractParams::aligned): item i is flat group i of G windows, wholly inside
+// read i / gprm.  The quotient comes from a multiply-high by floor(2^32 / gprm) (al_magic) and one correction step.
+template <int G, int BPS> struct AlignedItems {
+    uint32_t gprm, magic, read_bits;
+    uint64_t first_bits;
+    KMC_DEV explicit AlignedItems(const ExtractParams &p)
+        : gprm(static_cast<uint32_t>(p.gprm)), magic(p.al_magic), read_bits(static_cast<uint32_t>(p.read_bits)),
+          first_bits(static_cast<uint64_t>(BPS) * p.first)
+    {
+    }
+    // bit offset in the stream of the item's first symbol
+    KMC_DEV uint64_t bit_of(uint32_t item) const
+    {
+        uint32_t r = __umulhi(item, magic), gi = item - r * gprm; // r is the quotient or one below it
+        if (gi >= gprm) {
+            gi -= gprm;
+            ++r;
+        }
+        return static_cast<uint64_t>(r) * read_bits + (first_bits + gi * static_cast<uint32_t>(G * BPS));
+    }
+    // Offsets grow with the item, so the last item of a tile bounds the block loads of all of them: true when NX + 1
+    // words from there lie inside the buffer (all tiles but the one or two that reach the end of it).
+    template <int NX> KMC_DEV bool loads_inside(const ExtractParams &p, uint32_t last_item) const
+    {
+        return static_cast<int64_t>(bit_of(last_item) >> 5) + NX < p.nw32;
+    }
+};
+inline uint32_t aligned_magic(uint64_t gprm) { return gprm == 1 ? 0xffffffffu : static_cast<uint32_t>(0x100000000ull / gprm); }
+
+// the aligned x-stream of the block at `bit`; inside = loads_inside() of the tile (no clamping needed)
+template <int NX> KMC_DEV void load_block_at(const ExtractParams &p, uint64_t bit, bool inside, uint32_t (&x)[NX])
+{
+    if (inside) {
+        const uint32_t *w = p.w32 + (bit >> 5);
+        uint32_t a[NX + 1];
+#pragma unroll
+        for (int i = 0; i <= NX; ++i) a[i] = __ldg(w + i);
+        const uint32_t sh = static_cast<uint32_t>(bit) & 31u;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = __funnelshift_r(a[i], a[i + 1], sh);
+    } else {
+        load_block<NX>(p.w32, p.nw32, static_cast<int64_t>(bit), x);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // extract_aligned_kernel: the same work items for the case every headline configuration is in -- a uniform read set
 // (or one sequence) whose windows per read are a multiple of G (C2: 120 = 15 x 8), SoA streams with 32-byte aligned
@@ -600,37 +645,16 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
     const uint32_t n_items = static_cast<uint32_t>(p.items);
     const uint32_t tile_base = blockIdx.x * static_cast<uint32_t>(kTileItems); // the launcher keeps items below 2^32 - kTileItems
     if (p.pf_tiles) burst_prefetch<false, G, BPS>(p, n_items);
-    const uint32_t gprm = static_cast<uint32_t>(p.gprm), magic = p.al_magic, read_bits = static_cast<uint32_t>(p.read_bits);
-    const uint64_t first_bits = static_cast<uint64_t>(BPS) * p.first;
-    // bit offset of an item's first symbol; offsets grow with the item, so the tile's last item bounds its loads
-    auto bit_of = [&](uint32_t item) -> uint64_t {
-        uint32_t r = __umulhi(item, magic), gi = item - r * gprm; // r is the quotient or one below it
-        if (gi >= gprm) {
-            gi -= gprm;
-            ++r;
-        }
-        return static_cast<uint64_t>(r) * read_bits + (first_bits + gi * static_cast<uint32_t>(G * BPS));
-    };
+    const AlignedItems<G, BPS> items(p);
     const uint32_t tile_last = (n_items - tile_base > static_cast<uint32_t>(kTileItems) ? tile_base + kTileItems : n_items) - 1u;
-    const bool safe = static_cast<int64_t>(bit_of(tile_last) >> 5) + NX < p.nw32; // block-uniform
+    const bool safe = items.template loads_inside<NX>(p, tile_last); // block-uniform
 
 #pragma unroll 1
     for (int it = 0; it < kTileIters; ++it) {
         const uint32_t item = tile_base + static_cast<uint32_t>(it) * kBlockThreads + threadIdx.x;
         if (item >= n_items) break;
-        const uint64_t bit = bit_of(item);
         uint32_t x[NX];
-        if (safe) {
-            const uint32_t *w = p.w32 + (bit >> 5);
-            uint32_t a[NX + 1];
-#pragma unroll
-            for (int i = 0; i <= NX; ++i) a[i] = __ldg(w + i);
-            const uint32_t sh = static_cast<uint32_t>(bit) & 31u;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) x[i] = __funnelshift_r(a[i], a[i + 1], sh);
-        } else {
-            load_block<NX>(p.w32, p.nw32, static_cast<int64_t>(bit), x);
-        }
+        load_block_at<NX>(p, items.bit_of(item), safe, x);
         uint64_t fw[G][N], rv[G][N];
         block_kmers<N, NX, G, true, WANT_RV, BPS>(x, p.s0, p.head_mask, fw, rv);
 
@@ -727,8 +751,23 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
         const bool plain_soa = SINK == SINK_IDS || (!p.aos && !p.out_index);
         if (p.aligned && p.vec_ok && plain_soa && !p.items_dev && p.gprm < 0x80000000ull &&
             p.items < 0xffffffffull - kTileItems && aligned_kernel_enabled()) {
-            p.al_magic = p.gprm == 1 ? 0xffffffffu : static_cast<uint32_t>(0x100000000ull / p.gprm);
-            extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
+            p.al_magic = aligned_magic(p.gprm);
+            // Three resident blocks per SM, not the six its 38 registers allow: the kernel is bound by the HBM write stream, and
+            // more blocks only mean more write streams in flight at once (measured, profiles/r02_ab_aligned_occupancy.txt:
+            // FwRvIterator SoA 2.73 ms with 6 blocks per SM, 2.68 with 5, 2.66 with 4, 2.64 with 3; the ALU-bound canonical
+            // stream without hash 1.41 ms with 3 to 6 and 1.6 ms with 2).  The cap is an unused dynamic shared-memory
+            // request; KMC_ALIGNED_SMEM overrides its size in bytes (0 = no cap).
+            static const int pad = [] {
+                const char *e = getenv("KMC_ALIGNED_SMEM");
+                const int v = e ? atoi(e) : (SINK == SINK_STREAMS ? 72 * 1024 : 0);
+                return v < 0 ? 0 : (v > 200 * 1024 ? 200 * 1024 : v);
+            }();
+            if (pad > 0) {
+                cudaError_t e = cudaFuncSetAttribute(extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+                if (e != cudaSuccess) return e;
+            }
+            extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST><<<static_cast<unsigned>(tiles), kBlockThreads, pad, stream>>>(p);
             return cudaGetLastError();
         }
     }

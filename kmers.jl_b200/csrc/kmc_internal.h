@@ -90,6 +90,16 @@ cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint3
                          uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream, uint32_t n_parts = 0,
                          void *const *events = nullptr);
 
+// The same count for one-limb k-mers over an aligned uniform set, ids produced and binned by ONE kernel into bins of a fixed
+// capacity (buckets.cu): fused_bin_ids, then -- if cursor[64], the overflow flag, is still 0 -- fused_bin_apply.
+struct ExtractParams;
+bool fused_bin_enabled();
+uint64_t fused_bin_capacity(uint64_t n_ids); // ids per bin; the binned buffer holds 64 of them
+cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *binned, uint64_t cap, unsigned long long *cursor,
+                          cudaStream_t stream);
+cudaError_t fused_bin_apply(const uint32_t *binned, uint64_t cap, const unsigned long long *cursor, int bucket_bits, uint32_t *table,
+                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events);
+
 // misc_kernels.cu -----------------------------------------------------------------------------
 cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,
                            cudaStream_t stream);

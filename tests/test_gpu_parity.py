@@ -438,6 +438,36 @@ def test_bucket_count_binned_ragged(kc):
         assert np.array_equal(np.nonzero(table)[0], idx) and np.array_equal(table[idx], cnt.astype(np.uint32))
 
 
+def test_bucket_count_fused_bins_and_overflow_fallback(kc):
+    """Tables beyond L2, one-limb k-mers, aligned uniform set: ids and bins come from one kernel with bins of a fixed
+    capacity.  Random reads fit; a set dominated by one repeated k-mer overflows its bin and the call repeats the count
+    on the exact path -- the table is the same exact histogram either way."""
+    rng = np.random.default_rng(99)
+    n_reads, length, stride, k = 40_000, 150, 5, 31
+    words = rng.integers(0, 2**64, size=n_reads * stride, dtype=np.uint64)
+    cases = {"random": words.copy()}
+    w = words.copy()
+    w.reshape(n_reads, stride)[n_reads // 3:] = 0  # two thirds of the reads are poly-A: one bucket gets 67 % of the k-mers
+    cases["crowded"] = w
+    cases["single k-mer"] = np.zeros_like(words)
+    for name, ww in cases.items():
+        rs = kc.ReadSet(2, ww, n_reads, uniform_len=length, uniform_stride_words=stride)
+        _, _, h, _ = ko.batch_iterate(ww, n_reads, k, ko.CANON, uniform_len=length, uniform_stride=stride, want_hash=True)
+        for bits in (26, 28):
+            table, n, _ = kc.bucket_count(rs, k, bits)
+            idx, cnt = np.unique((h >> np.uint64(64 - bits)).astype(np.int64), return_counts=True)
+            assert n == h.size and int(table.sum(dtype=np.int64)) == h.size, name
+            assert np.array_equal(np.nonzero(table)[0], idx) and np.array_equal(table[idx], cnt.astype(np.uint32)), name
+    # a partial last tile and a partial last iteration of the binning step
+    for n_small in (1, 7, 300, 2048 // 15 + 1, 4500):
+        ww = words[: n_small * stride]
+        rs = kc.ReadSet(2, ww, n_small, uniform_len=length, uniform_stride_words=stride)
+        _, _, h, _ = ko.batch_iterate(ww, n_small, k, ko.CANON, uniform_len=length, uniform_stride=stride, want_hash=True)
+        table, n, _ = kc.bucket_count(rs, k, 27)
+        idx, cnt = np.unique((h >> np.uint64(64 - 27)).astype(np.int64), return_counts=True)
+        assert n == h.size and np.array_equal(np.nonzero(table)[0], idx) and np.array_equal(table[idx], cnt.astype(np.uint32))
+
+
 @pytest.mark.parametrize("k,bits", [(31, 20), (63, 12), (15, 28)])
 def test_bucket_count(kc, k, bits):
     rng = np.random.default_rng(k)
