@@ -342,6 +342,9 @@ int32_t kmc_ctx_destroy(kmc_ctx *ctx)
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    for (auto e : ctx->aux_events)
+        if (e) cudaEventDestroy(e);
     if (ctx->comm) comm_detach(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -614,72 +617,145 @@ int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t
     // bin after bin (buckets.cu).  Needs 8 bytes per k-mer of temporary memory; without it (or for
     // L2-sized tables) the kernel increments the table directly.
     const uint64_t table_bytes = 4ull << bucket_bits;
-    bool binned = table_bytes > (96ull << 20) && bucket_bits <= 32;
-    AsyncBuf ids_buf, tmp_buf, matrix_buf, offs_buf, scan_buf; // freed (stream-ordered) on every way out
-    const uint64_t n_ids = (L.items + 1) * static_cast<uint64_t>(ge.g); // flat windows, rounded up to whole groups
-    if (binned && ge.n_limbs == 1 && L.uniform_len && binned_count_bin_bits(bucket_bits) == 6 && fused_bin_enabled()) {
-        // One-limb k-mers over an aligned uniform set (C5): ids and bins from one kernel, bins of a fixed capacity.  A bin
-        // that overflows (a set whose k-mers crowd into one range of buckets) sends the call to the exact path below.
-        ExtractParams q = p;
-        set_iteration_strides(q, ge.g);
-        if (q.aligned && q.items < 0xffffffffull - kTileItems) {
-            AsyncBuf bins_buf, cursor_buf;
-            const uint64_t cap = fused_bin_capacity(L.total);
-            cudaError_t e = bins_buf.alloc(ctx, (cap * 64 + 4096) * 4, stream); // 64 bins + the dump area of one iteration
-            if (e == cudaSuccess) e = cursor_buf.alloc(ctx, 65 * 8, stream);
-            if (e != cudaSuccess) {
-                (void)cudaGetLastError();
-            } else {
-                st = ensure_host_small(ctx);
-                if (st) return st;
-                unsigned long long *cursor = cursor_buf.as<unsigned long long>();
-                CU(fused_bin_ids(q, ge.nx, bucket_bits, bins_buf.as<uint32_t>(), cap, cursor, stream));
-                uint64_t *flag = ctx->host_small + 64;
-                CU(cudaMemcpyAsync(flag, cursor + 64, 8, cudaMemcpyDeviceToHost, stream));
-                CU(cudaStreamSynchronize(stream)); // ~10 us: the table must not be touched before the bins are known to be whole
-                if (*flag == 0) {
-                    CU(fused_bin_apply(bins_buf.as<uint32_t>(), cap, cursor, bucket_bits, table, warm_sink(ctx), ctx->sm_count, stream,
-                                       n_parts, events));
-                    if (n_parts) return KMC_OK;
-                    CU(cudaEventRecord(ctx->ev_k1, stream));
-                    CU(cudaStreamSynchronize(stream));
-                    CU(cudaEventElapsedTime(&result->kernel_ms, ctx->ev_k0, ctx->ev_k1));
-                    return KMC_OK;
-                }
-            }
-        }
-    }
-    if (binned) {
-        const uint64_t cells = (static_cast<uint64_t>(1) << binned_count_bin_bits(bucket_bits)) * binned_count_blocks(n_ids);
-        cudaError_t e = ids_buf.alloc(ctx, round_up(n_ids * 4, 256), stream);
-        if (e == cudaSuccess) e = tmp_buf.alloc(ctx, round_up(n_ids * 4, 256), stream);
-        if (e == cudaSuccess) e = matrix_buf.alloc(ctx, (cells + 1) * 8, stream);
-        if (e == cudaSuccess) e = offs_buf.alloc(ctx, (cells + 2) * 8, stream);
-        if (e == cudaSuccess) e = scan_buf.alloc(ctx, (scan_tmp_elems(cells) + 1) * 8, stream);
-        if (e != cudaSuccess) { // not enough memory for the binned path: fall back to direct increments
-            (void)cudaGetLastError();
-            binned = false;
-        }
-    }
-    if (binned) {
-        // the flat id array is exactly the flat window array: every flat index < L.total is written
-        // once (slots of partial groups that are not windows are not written and not binned)
-        p.out_a = ids_buf.as<uint64_t>();
-        p.vec_ok = 1;
-        ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKET_IDS, true, !L.uniform_len);
-        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
-        CU(fn(p, ctx->sm_count, stream));
-        CU(binned_count(ids_buf.as<uint32_t>(), L.total, bucket_bits, table, tmp_buf.as<uint32_t>(), matrix_buf.as<uint64_t>(),
-                        offs_buf.as<uint64_t>(), scan_buf.as<uint64_t>(), ctx->sm_count, stream, n_parts, events));
-    } else {
+    const bool want_binned = table_bytes > (96ull << 20) && bucket_bits <= 32;
+
+    // the table is incremented directly by the extraction kernel
+    auto count_direct = [&](ExtractParams q, cudaStream_t s) -> int32_t {
+        int32_t rc = ensure_host_small(ctx); // allocates dev_small, where warm_table's sink lives
+        if (rc) return rc;
         // a table that fits L2 is pulled into it first: increments that miss L2 serialise at DRAM latency
-        st = ensure_host_small(ctx); // allocates dev_small, where warm_table's sink lives
-        if (st) return st;
-        if (table_bytes <= (96ull << 20)) CU(warm_table(table, 1ull << bucket_bits, ctx->sm_count, warm_sink(ctx), stream));
-        p.bucket_table = table;
+        if (table_bytes <= (96ull << 20)) CU(warm_table(table, 1ull << bucket_bits, ctx->sm_count, warm_sink(ctx), s));
+        q.bucket_table = table;
         ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKETS, true, !L.uniform_len);
         if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
-        CU(fn(p, ctx->sm_count, stream));
+        CU(fn(q, ctx->sm_count, s));
+        return KMC_OK;
+    };
+    // the exact binned path for the set (or piece of a uniform set) q describes: ids, histogram, scatter, apply
+    auto count_exact = [&](ExtractParams q, uint64_t windows, cudaStream_t s, uint32_t np, void *const *ev) -> int32_t {
+        AsyncBuf ids_buf, tmp_buf, matrix_buf, offs_buf, scan_buf; // freed (stream-ordered) on every way out
+        const uint64_t n_ids = (q.items + 1) * static_cast<uint64_t>(ge.g); // flat windows, rounded up to whole groups
+        const uint64_t cells = (static_cast<uint64_t>(1) << binned_count_bin_bits(bucket_bits)) * binned_count_blocks(n_ids);
+        cudaError_t e = ids_buf.alloc(ctx, round_up(n_ids * 4, 256), s);
+        if (e == cudaSuccess) e = tmp_buf.alloc(ctx, round_up(n_ids * 4, 256), s);
+        if (e == cudaSuccess) e = matrix_buf.alloc(ctx, (cells + 1) * 8, s);
+        if (e == cudaSuccess) e = offs_buf.alloc(ctx, (cells + 2) * 8, s);
+        if (e == cudaSuccess) e = scan_buf.alloc(ctx, (scan_tmp_elems(cells) + 1) * 8, s);
+        if (e != cudaSuccess) { // not enough memory for the binned path: direct increments
+            (void)cudaGetLastError();
+            int32_t rc = count_direct(q, s);
+            if (rc) return rc;
+            for (uint32_t i = 0; i < np; ++i) CU(cudaEventRecord(static_cast<cudaEvent_t>(ev[i]), s));
+            return KMC_OK;
+        }
+        // the flat id array is exactly the flat window array: every flat index < windows is written
+        // once (slots of partial groups that are not windows are not written and not binned)
+        q.out_a = ids_buf.as<uint64_t>();
+        q.vec_ok = 1;
+        ExtractLaunchFn fn = get_launcher(ge, MODE_BUCKET_IDS, true, !L.uniform_len);
+        if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no kernel for this K");
+        CU(fn(q, ctx->sm_count, s));
+        CU(binned_count(ids_buf.as<uint32_t>(), windows, bucket_bits, table, tmp_buf.as<uint32_t>(), matrix_buf.as<uint64_t>(),
+                        offs_buf.as<uint64_t>(), scan_buf.as<uint64_t>(), ctx->sm_count, s, np, ev));
+        return KMC_OK;
+    };
+
+    bool done = false;
+    ExtractParams pa = p;
+    if (want_binned) set_iteration_strides(pa, ge.g);
+    if (want_binned && ge.n_limbs == 1 && L.uniform_len && binned_count_bin_bits(bucket_bits) == 6 && fused_bin_enabled() && pa.aligned &&
+        pa.items < 0xffffffffull - kTileItems) {
+        // One-limb k-mers over an aligned uniform set (C5): ids and bins from one kernel, bins of a fixed capacity
+        // (buckets.cu).  The set is cut into pieces by read ranges: the bins of piece i are applied on a second stream
+        // while piece i + 1 is being binned on the first -- the increments are bound by the L2 atomic path, the binning
+        // by instruction issue and shared memory, and an SM has room for both.  A piece one of whose bins overflows (a
+        // set whose k-mers crowd into one range of buckets) is skipped by its apply kernels and counted on the exact path.
+        constexpr int kMaxPieces = 16;
+        int pieces = fused_bin_pieces(L.total);
+        if (static_cast<uint64_t>(pieces) > seqs->n_seqs) pieces = static_cast<int>(seqs->n_seqs);
+        st = ensure_host_small(ctx);
+        if (st) return st;
+        cudaStream_t s_apply = stream;
+        if (pieces > 1) {
+            if (!ctx->aux_stream) {
+                int lo = 0, hi = 0;
+                CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CU(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+                for (auto &e : ctx->aux_events) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+            s_apply = ctx->aux_stream;
+            CU(cudaEventRecord(ctx->aux_events[16], stream)); // what the caller enqueued before (the table's memset) comes first
+            CU(cudaStreamWaitEvent(s_apply, ctx->aux_events[16], 0));
+        }
+        struct Piece {
+            ExtractParams q;
+            uint64_t windows = 0, cap = 0;
+            AsyncBuf bins, cursor;
+        } piece[kMaxPieces];
+        const uint64_t stride32 = pa.read_bits / 32; // 32-bit words from one read to the next (read_bits is a multiple of 32)
+        bool have_mem = true;
+        for (int i = 0; i < pieces && have_mem; ++i) {
+            const uint64_t r0 = seqs->n_seqs * i / pieces, r1 = seqs->n_seqs * (i + 1) / pieces;
+            Piece &pc = piece[i];
+            pc.q = p;
+            pc.q.w32 = p.w32 + r0 * stride32;
+            pc.q.nw32 = p.nw32 - static_cast<int64_t>(r0 * stride32);
+            pc.q.n_seqs = r1 - r0;
+            pc.q.items = (r1 - r0) * L.gprm;
+            pc.windows = (r1 - r0) * L.wpr;
+            pc.cap = fused_bin_capacity(pc.windows);
+            cudaError_t e = pc.bins.alloc(ctx, (pc.cap * 64 + 4096) * 4, stream); // 64 bins + the dump area of one iteration
+            if (e == cudaSuccess) e = pc.cursor.alloc(ctx, 65 * 8, stream);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                have_mem = false;
+            }
+        }
+        if (have_mem) {
+            for (int i = 0; i < pieces; ++i) {
+                Piece &pc = piece[i];
+                CU(fused_bin_ids(pc.q, ge.nx, bucket_bits, pc.bins.as<uint32_t>(), pc.cap, pc.cursor.as<unsigned long long>(), stream));
+                CU(cudaMemcpyAsync(ctx->host_small + 64 + i, pc.cursor.as<unsigned long long>() + 64, 8, cudaMemcpyDeviceToHost, stream));
+                if (pieces > 1) CU(cudaEventRecord(ctx->aux_events[i], stream));
+                if (i > 0) { // the bins of the piece before: beside this piece's binning
+                    Piece &pv = piece[i - 1];
+                    CU(cudaStreamWaitEvent(s_apply, ctx->aux_events[i - 1], 0));
+                    CU(fused_bin_apply(pv.bins.as<uint32_t>(), pv.cap, pv.cursor.as<unsigned long long>(), bucket_bits, table, warm_sink(ctx),
+                                       ctx->sm_count, s_apply, 0, nullptr, true));
+                }
+            }
+            // every piece is binned once this returns (~10 us after the last binning kernel; the applies go on beside it):
+            // the range events below must not be recorded before every flagged piece has been counted
+            CU(cudaStreamSynchronize(stream));
+            if (pieces > 1) CU(cudaStreamWaitEvent(s_apply, ctx->aux_events[pieces - 1], 0));
+            for (int i = 0; i + 1 < pieces; ++i)
+                if (ctx->host_small[64 + i]) {
+                    st = count_exact(piece[i].q, piece[i].windows, s_apply, 0, nullptr);
+                    if (st) return st;
+                }
+            Piece &pl = piece[pieces - 1];
+            if (ctx->host_small[64 + pieces - 1]) {
+                st = count_exact(pl.q, pl.windows, s_apply, n_parts, events);
+                if (st) return st;
+            } else {
+                CU(fused_bin_apply(pl.bins.as<uint32_t>(), pl.cap, pl.cursor.as<unsigned long long>(), bucket_bits, table, warm_sink(ctx),
+                                   ctx->sm_count, s_apply, n_parts, events, false));
+            }
+            if (pieces > 1) { // later work on the context's stream (and the release of the pieces' buffers) comes after the applies
+                CU(cudaEventRecord(ctx->aux_events[17], s_apply));
+                CU(cudaStreamWaitEvent(stream, ctx->aux_events[17], 0));
+            }
+            done = true;
+        }
+    }
+    if (!done && want_binned) {
+        st = count_exact(p, L.total, stream, n_parts, events);
+        if (st) return st;
+        done = true;
+    }
+    if (!done) {
+        st = count_direct(p, stream);
+        if (st) return st;
         st = record_all();
         if (st) return st;
     }

@@ -172,6 +172,17 @@ template <typename Key> struct Scatter64Smem {
     uint32_t tot[kTpBins];
 };
 
+// The binned keys are written once and read back much later (or by another kernel): no L1 allocation, first in line for
+// eviction from L2 -- so that they do not push out what a kernel running beside this one keeps there (buckets.cu: the table
+// slice the increments of the previous piece are working on).
+template <typename Key> __device__ __forceinline__ void st_binned(Key *p, Key v)
+{
+    if constexpr (sizeof(Key) == 4)
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(0x12F0000000000000ull) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(0x12F0000000000000ull) : "memory");
+}
+
 // One iteration of the 64-bin scatter: the block's kPerIter keys (PT per thread, in registers) are counted per bin,
 // ranked, staged in shared memory in bin order and written out as one run per bin.  reserve(bin, count), called by the
 // lanes of warp 0 for the bins 2 * lane and 2 * lane + 1, returns the index in `out` of the run of `count` keys of `bin`.
@@ -270,14 +281,14 @@ __device__ __forceinline__ void scatter64_iter(Scatter64Smem<Key> &sm, const Key
             const uint32_t t = threadIdx.x + i * kBlock;
             const Key v = sm.keys[t];
             const uint32_t b = kStageBins ? static_cast<uint32_t>(sm.bins[t]) : bin_of(v);
-            out[sm.dst[b] + t] = v; // (dst wraps; only the sum is used)
+            st_binned(out + (sm.dst[b] + t), v); // (dst wraps; only the sum is used)
         }
     } else {
         const uint32_t total = sm.start[kTpBins];
         for (uint32_t t = threadIdx.x; t < total; t += kBlock) {
             const Key v = sm.keys[t];
             const uint32_t b = kStageBins ? static_cast<uint32_t>(sm.bins[t]) : bin_of(v);
-            out[sm.dst[b] + t] = v;
+            st_binned(out + (sm.dst[b] + t), v);
         }
     }
 }

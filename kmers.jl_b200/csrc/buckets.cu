@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(256) warm_slice_kernel(const uint32_t *__restr
     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
          i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         uint4 v;
-        asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + i));
+        // evict_last: the slice is to stay in L2 while its bins are applied, whatever streams through beside it
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(p + i), "l"(0x14F0000000000000ull));
         acc |= v.x & v.y & v.z & v.w;
     }
     if (acc == 0xffffffffu) *sink = acc; // keeps the loads alive; a count of 2^32-1 in four neighbours does not happen
@@ -146,26 +149,47 @@ __global__ void __launch_bounds__(binning::kBlock, 3) bucket_bin_kernel(const Ex
     }
 }
 
-// the ids of bin b are binned[b * cap .. b * cap + min(cursor[b], cap))
-__global__ void __launch_bounds__(256) bin_apply_fused_kernel(const uint32_t *__restrict__ binned, uint64_t cap,
-                                                              const unsigned long long *__restrict__ cursor, int bin, int bin_end,
-                                                              uint32_t *__restrict__ table)
+// The ids of bin b are binned[b * cap .. b * cap + cursor[b]).  Does nothing when the piece's overflow flag (cursor[64]) is set:
+// the caller repeats that piece on the exact path.  The next 16 bytes of ids are loaded before the current four are
+// applied, so that a few warps per SM keep the increment path busy (the kernel also runs beside the binning kernel of
+// the next piece, in whatever that leaves free of an SM).
+__device__ __forceinline__ uint4 ld_ids(const uint32_t *p)
 {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(0x12F0000000000000ull));
+    return v;
+}
+__device__ __forceinline__ void inc_counter(uint32_t *p)
+{
+    asm volatile("red.global.add.L2::cache_hint.u32 [%0], 1, %1;" ::"l"(p), "l"(0x14F0000000000000ull) : "memory");
+}
+
+__global__ void bin_apply_fused_kernel(const uint32_t *__restrict__ binned, uint64_t cap, const unsigned long long *__restrict__ cursor,
+                                       int bin, int bin_end, uint32_t *__restrict__ table)
+{
+    if (cursor[binning::kTpBins] != 0) return;
     const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const uint64_t threads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t step = static_cast<uint64_t>(gridDim.x) * blockDim.x * 4;
     for (int b = bin; b < bin_end; ++b) {
         const uint32_t *ids = binned + static_cast<uint64_t>(b) * cap; // 16-byte aligned: cap is a multiple of 4
-        uint64_t n = cursor[b];
-        if (n > cap) n = cap;
-        const uint64_t n4 = n & ~3ull;
-        for (uint64_t i = tid * 4; i < n4; i += threads * 4) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ids + i));
-            atomicAdd(table + v.x, 1u);
-            atomicAdd(table + v.y, 1u);
-            atomicAdd(table + v.z, 1u);
-            atomicAdd(table + v.w, 1u);
+        const uint64_t n = cursor[b], n4 = n & ~3ull;
+        uint64_t i = tid * 4;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < n4) v = ld_ids(ids + i);
+        while (i < n4) {
+            const uint64_t nxt = i + step;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (nxt < n4) w = ld_ids(ids + nxt);
+            inc_counter(table + v.x);
+            inc_counter(table + v.y);
+            inc_counter(table + v.z);
+            inc_counter(table + v.w);
+            v = w;
+            i = nxt;
         }
-        if (tid < n - n4) atomicAdd(table + ids[n4 + tid], 1u);
+        if (tid < n - n4) inc_counter(table + ids[n4 + tid]);
     }
 }
 
@@ -250,27 +274,51 @@ cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *bi
     return cudaErrorInvalidValue;
 }
 
-// Second half (once the caller has seen that no bin overflowed): the bins are applied in table order, as in binned_count.
+// Second half: the bins are applied in table order, as in binned_count (a piece whose overflow flag is set is skipped on the
+// device).  beside = the binning kernel of the next piece is running on another stream: smaller blocks, which fit into
+// what its three blocks per SM leave of the register file.
 cudaError_t fused_bin_apply(const uint32_t *binned, uint64_t cap, const unsigned long long *cursor, int bucket_bits, uint32_t *table,
-                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events)
+                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events, bool beside)
 {
     if (!events) n_parts = 0;
     const int pbits = binned_count_bin_bits(bucket_bits);
     const int n_bins = 1 << pbits, shift = bucket_bits - pbits;
     const uint64_t slice = 1ull << shift;
     const int group = apply_group(2);
+    static const int env_block = [] { const char *e = getenv("KMC_APPLY_BLOCK"); return e ? atoi(e) : 0; }();
+    static const int env_grid = [] { const char *e = getenv("KMC_APPLY_GRID"); return e ? atoi(e) : 0; }();
+    int block = beside ? 128 : 256, per_sm = beside ? 4 : 16;
+    if (beside && env_block >= 32 && env_block <= 1024 && env_block % 32 == 0) block = env_block;
+    if (beside && env_grid >= 1 && env_grid <= 64) per_sm = env_grid;
+    if (beside) {
+        // An SM holds blocks of two kernels at once only under one shared-memory carve-out: ask for the binning kernel's
+        // (it uses nearly all of it), or these kernels wait until an SM has drained.
+        cudaError_t e = cudaFuncSetAttribute(bin_apply_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(warm_slice_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
     uint32_t parts_done = 0;
     for (int b = 0; b < n_bins; b += group) {
         const int b_end = b + group < n_bins ? b + group : n_bins;
         warm_slice_kernel<<<static_cast<unsigned>(sm_count * 8), 256, 0, stream>>>(table + static_cast<uint64_t>(b) * slice,
                                                                                   slice * (b_end - b), sink);
-        bin_apply_fused_kernel<<<static_cast<unsigned>(sm_count * 16), 256, 0, stream>>>(binned, cap, cursor, b, b_end, table);
+        bin_apply_fused_kernel<<<static_cast<unsigned>(sm_count * per_sm), block, 0, stream>>>(binned, cap, cursor, b, b_end, table);
         while (parts_done < n_parts && static_cast<uint64_t>(parts_done + 1) * n_bins <= static_cast<uint64_t>(b_end) * n_parts) {
             cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(events[parts_done++]), stream);
             if (e != cudaSuccess) return e;
         }
     }
     return cudaGetLastError();
+}
+
+// Pieces a fused count is cut into (KMC_BIN_PIECES overrides): the increments of piece i run beside the binning of piece i + 1.
+int fused_bin_pieces(uint64_t n_ids)
+{
+    static const int env = [] { const char *e = getenv("KMC_BIN_PIECES"); return e ? atoi(e) : 0; }();
+    int pieces = env > 0 ? (env > 16 ? 16 : env) : 1;
+    while (pieces > 1 && n_ids / pieces < (1ull << 26)) --pieces; // a piece of less than 64 M ids is not worth its launches
+    return pieces;
 }
 
 // KMC_FUSED_BIN=0 keeps every binned count on the exact three-pass path (A/B measurements, tests of both)
