@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, second 2-GPU call (after the fused bucket count and the aligned kernel): the multi-GPU tests (NCCL communicators, group, exchange, C example) and bench.py at N = 2 (both arms)
+mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/r2u_topo2.txt 2>&1
+(python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r2u_pytest_multi.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2u_pytest_multi.log); tail -8 gpurun_out/r2u_pytest_multi.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --impl reference --steps 5 --warmup 1 > gpurun_out/r2u_ref_n2.json 2> gpurun_out/r2u_ref_n2.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2u_bench_n2.json 2> gpurun_out/r2u_bench_n2.err
+echo "bench exit $?"; tail -5 gpurun_out/r2u_bench_n2.err
+python - <<'PY'
+import json
+for f in ("gpurun_out/r2u_ref_n2.json", "gpurun_out/r2u_bench_n2.json"):
+    try:
+        d=[json.loads(l) for l in open(f) if l.startswith("{")][0]
+        print(f, d.get("impl","ours"), "value", d["value"], "cores", d.get("cpu_baseline",{}).get("cores"), "e2e", d.get("e2e",{}).get("value"))
+        for k in ("c4","c5"):
+            if k in d: print(k, {x: d[k][x] for x in d[k] if x not in ("workload","parity","collective")})
+    except Exception as e: print(f, "ERR", e)
+PY

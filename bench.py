@@ -763,7 +763,7 @@ def run_ours(args, rank, local_rank, world):
                          if sus_ms else None,
                          "frac_burst": (BYTES_PER_KMER * n_kmers / (float(np.median(gap_ms)) / 1e3) / 1e9 / peak) if gap_ms else None,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "extract_kernel<N=1,NX=3,CANON,HASH,uniform,G=8>",
+                         "kernel": "extract_aligned_kernel<N=1,NX=3,CANON,HASH,SINK_STREAMS,BPS=2> (G=8; aligned uniform set: extract_kernels.cuh)",
                          "kernel_ms": k_ms, "bytes_per_kmer": BYTES_PER_KMER, "peak_source": peak_src,
                          "idle_gaps": {"kernel_ms": float(np.median(gap_ms)),
                                        "achieved": BYTES_PER_KMER * n_kmers / (float(np.median(gap_ms)) / 1e3) / 1e9,

@@ -664,7 +664,7 @@ int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t
     ExtractParams pa = p;
     if (want_binned) set_iteration_strides(pa, ge.g);
     if (want_binned && ge.n_limbs == 1 && L.uniform_len && binned_count_bin_bits(bucket_bits) == 6 && fused_bin_enabled() && pa.aligned &&
-        pa.items < 0xffffffffull - kTileItems) {
+        pa.al_tail == 0 && pa.items < 0xffffffffull - kTileItems) {
         // One-limb k-mers over an aligned uniform set (C5): ids and bins from one kernel, bins of a fixed capacity
         // (buckets.cu).  The set is cut into pieces by read ranges: the bins of piece i are applied on a second stream
         // while piece i + 1 is being binned on the first -- the increments are bound by the L2 atomic path, the binning

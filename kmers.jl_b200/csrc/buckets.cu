@@ -248,7 +248,7 @@ cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *bi
     const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
     if (tiles == 0 || tiles > 0x7fffffffull || p.items >= 0xffffffffull - kTileItems) return cudaErrorInvalidConfiguration;
     set_iteration_strides(p, 8);
-    if (!p.aligned) return cudaErrorInvalidValue;
+    if (!p.aligned || p.al_tail) return cudaErrorInvalidValue; // whole groups only
     p.al_magic = aligned_magic(p.gprm);
     p.pf_tiles = 0;
     if (prefetch_enabled()) {

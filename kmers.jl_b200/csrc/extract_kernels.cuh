@@ -65,6 +65,7 @@ struct ExtractParams {
     uint64_t read_bits;    // stride_units * unit_bits: stream bits from one read to the next (uniform offsets)
     uint32_t aligned;      // uniform set whose windows per read are a multiple of G: item i IS flat group i (set_iteration_strides)
     uint32_t al_magic;     // floor(2^32 / gprm) (2^32 - 1 for gprm = 1): extract_aligned_kernel divides by gprm with it
+    uint32_t al_tail;      // aligned single sequence: windows of its last, partial group (0: the last group is whole too)
     // ragged locator
     const uint64_t *seq_unit_off; // [n_seqs] or NULL (then r * stride_units); used by both locators
     const uint64_t *win_off;      // [n_seqs+1] exclusive scan of window counts
@@ -359,10 +360,14 @@ inline void set_iteration_strides(ExtractParams &p, int g = 0)
     p.it_dq = kBlockThreads / p.gprm;
     p.it_dr = kBlockThreads % p.gprm;
     p.read_bits = p.stride_units * p.unit_bits;
-    p.aligned = (g > 0 && !p.seq_unit_off && p.wpr > 0 && p.wpr % static_cast<uint64_t>(g) == 0 && p.gprm == p.wpr / g &&
-                 p.n_seqs < 0xffffffffull && p.read_bits < 0xffffffffull && p.gprm < 0xffffffffull)
+    // groups never straddle two reads when the windows per read are a multiple of g -- or when there is one read only (a
+    // long sequence, a shard of one: C4), whose last group may then be partial (al_tail windows)
+    const bool whole = g > 0 && p.wpr > 0 && p.wpr % static_cast<uint64_t>(g) == 0 && p.gprm == p.wpr / g;
+    const bool single = g > 0 && p.wpr > 0 && p.n_seqs == 1 && p.gprm == (p.wpr + g - 1) / g;
+    p.aligned = ((whole || single) && !p.seq_unit_off && p.n_seqs < 0xffffffffull && p.read_bits < 0xffffffffull && p.gprm < 0xffffffffull)
                     ? 1u
                     : 0u;
+    p.al_tail = (p.aligned && !whole) ? static_cast<uint32_t>(p.wpr % static_cast<uint64_t>(g)) : 0u;
 }
 
 
@@ -658,6 +663,9 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
         uint64_t fw[G][N], rv[G][N];
         block_kmers<N, NX, G, true, WANT_RV, BPS>(x, p.s0, p.head_mask, fw, rv);
 
+        // all G slots are windows, except in the last group of a single sequence whose window count is not a multiple of G
+        const bool partial = p.al_tail != 0 && item == n_items - 1u;
+        const int jhi = partial ? static_cast<int>(p.al_tail) : G;
         uint64_t a[G][N], h[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
@@ -666,7 +674,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
 #pragma unroll
             for (int i = 0; i < N; ++i) a[j][i] = take_fw ? fw[j][i] : rv[j][i];
             if (HASH) h[j] = fx_hash<N>(a[j], 0);
-            if (DIGEST) {
+            if (DIGEST && j < jhi) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     dg_xa ^= a[j][i];
@@ -685,7 +693,12 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
 #pragma unroll
             for (int t = 0; t < G / 2; ++t) w[t] = (h[2 * t] >> p.bucket_shift) | ((h[2 * t + 1] >> p.bucket_shift) << 32);
             uint64_t *dst = p.out_a + static_cast<uint64_t>(item) * (G / 2);
-            if (G == 8) st_v4(dst, w[0], w[1 % (G / 2)], w[2 % (G / 2)], w[3 % (G / 2)]);
+            if (partial) {
+                uint32_t *ids = reinterpret_cast<uint32_t *>(dst);
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (j < jhi) ids[j] = static_cast<uint32_t>(h[j] >> p.bucket_shift);
+            } else if (G == 8) st_v4(dst, w[0], w[1 % (G / 2)], w[2 % (G / 2)], w[3 % (G / 2)]);
             else if (G == 4) st_v2(dst, w[0], w[1 % (G / 2)]);
             else st_u64(dst, w[0]);
         } else {
@@ -694,6 +707,18 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
             for (int j = 0; j < G; ++j)
 #pragma unroll
                 for (int i = 0; i < N; ++i) buf[j * N + i] = a[j][i];
+            if (partial) { // (one thread of the launch)
+                store_words<G * N>(p.out_a + static_cast<uint64_t>(item) * (G * N), buf, 0, jhi * N, false, true);
+                if (MODE == MODE_FWRV) {
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) buf[j * N + i] = rv[j][i];
+                    store_words<G * N>(p.out_b + static_cast<uint64_t>(item) * (G * N), buf, 0, jhi * N, false, true);
+                }
+                if (HASH) store_words<G>(p.out_hash + static_cast<uint64_t>(item) * G, h, 0, jhi, false, true);
+                continue;
+            }
             store_run<G * N>(p.out_a + static_cast<uint64_t>(item) * (G * N), buf, true);
             if (MODE == MODE_FWRV) {
 #pragma unroll

@@ -208,18 +208,22 @@ def test_aligned_uniform_sets(kc, k, length):
 
 
 def test_aligned_single_sequence_and_views(kc):
-    """One long sequence whose window count is a multiple of G (one read of the uniform locator: the quotient of every
-    item is 0), and views that start inside a word; the last tile reaches the end of the buffer (clamped loads)."""
+    """One long sequence (one read of the uniform locator: the quotient of every item is 0): its window count need not be a
+    multiple of G -- the last group is then partial (al_tail) -- and views may start inside a word; the last tile
+    reaches the end of the buffer (clamped loads)."""
     rng = np.random.default_rng(4242)
-    for k in (31, 63, 21):
-        g = 8 if k <= 32 else 4
-        for first in (0, 5, 17):
-            n = 40_000 * g + k - 1
+    for k in (31, 63, 21, 97):
+        g = {1: 8, 2: 4, 3: 4, 4: 2}[(2 * k + 63) // 64]
+        for first, tail in ((0, 0), (5, 1), (17, g - 1), (0, g // 2)):
+            n = 40_000 * g + k - 1 + tail
             w = rng.integers(0, 2**64, size=(n + first + 31) // 32, dtype=np.uint64)
             rs = kc.ReadSet(2, w, 1, uniform_len=n, uniform_stride_words=w.size, first_symbol_offset=first)
             a, _, h = ko.iterate(w, n, k, ko.CANON, first=first, want_hash=True)
             e = kc.extract(MODES["canon"], rs, k, hash=True)
             assert e.n == a.shape[0] and np.array_equal(e.kmers, a) and np.array_equal(e.hash, h)
+            f, r, _ = ko.iterate(w, n, k, ko.FWRV, first=first, want_hash=False)
+            e = kc.extract(MODES["fwrv"], rs, k)
+            assert e.n == f.shape[0] and np.array_equal(e.kmers, f) and np.array_equal(e.rv, r)
 
 
 def test_subsequence_views(kc):
