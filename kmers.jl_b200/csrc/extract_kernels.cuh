@@ -242,7 +242,7 @@ struct TileCursor {
             }
             ubit = unit_off * p.unit_bits;
         } else {
-            if (p.aligned) {
+            if (p.aligned && !p.al_tail) {
                 // windows per read are a multiple of G (C2: 120 = 15 x 8): every group lies wholly inside one read, item i
                 // is flat group i and all G slots are windows.  One 32 x 32 -> 64-bit product instead of the two 64-bit
                 // products and the divisions-by-G bookkeeping below (60 of the 314 instructions per item, ncu r01).
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
 #if KMC_TMA_STORE
             // (a warp whose last lane is past the end takes the ordinary stores: its lanes have left the loop)
             const bool warp_full = tile_base + static_cast<uint64_t>(it) * kBlockThreads + (threadIdx.x | 31u) < n_items;
-            if (N == 1 && SINK == SINK_STREAMS && MODE != MODE_FWRV && p.aligned && p.vec_ok && !p.out_index && warp_full) {
+            if (N == 1 && SINK == SINK_STREAMS && MODE != MODE_FWRV && p.aligned && !p.al_tail && p.vec_ok && !p.out_index && warp_full) {
                 // the warp's 32 items are 256 consecutive elements of every stream: lane l's 8 go to bytes [64 l, 64 l + 64)
                 extern __shared__ __align__(128) unsigned char s_tma[];
                 const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -640,7 +640,7 @@ template <int NX> KMC_DEV void load_block_at(const ExtractParams &p, uint64_t bi
 // The k-mer arithmetic is the shared block_kmers / limbs_less / fx_hash.  SINK_IDS writes the 32-bit bucket id of
 // every window (first pass of the binned count, buckets.cu).
 // ---------------------------------------------------------------------------------------------
-template <int N, int NX, int MODE, bool HASH, int SINK = SINK_STREAMS, int BPS = 2, bool DIGEST = false>
+template <int N, int NX, int MODE, bool HASH, int SINK = SINK_STREAMS, int BPS = 2, bool DIGEST = false, bool STRICT4 = false>
 __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const ExtractParams p)
 {
     static_assert(SINK == SINK_STREAMS || (SINK == SINK_IDS && MODE == MODE_CANON && HASH), "bucket ids are hashes of canonical k-mers");
@@ -658,14 +658,23 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
     for (int it = 0; it < kTileIters; ++it) {
         const uint32_t item = tile_base + static_cast<uint32_t>(it) * kBlockThreads + threadIdx.x;
         if (item >= n_items) break;
-        uint32_t x[NX];
-        load_block_at<NX>(p, items.bit_of(item), safe, x);
-        uint64_t fw[G][N], rv[G][N];
-        block_kmers<N, NX, G, true, WANT_RV, BPS>(x, p.s0, p.head_mask, fw, rv);
-
+        const uint64_t bit = items.bit_of(item);
         // all G slots are windows, except in the last group of a single sequence whose window count is not a multiple of G
         const bool partial = p.al_tail != 0 && item == n_items - 1u;
         const int jhi = partial ? static_cast<int>(p.al_tail) : G;
+        if (STRICT4) {
+            // recoded 4-bit / ASCII source, strict iteration: the first window with a symbol that cannot be encoded is the
+            // error (extract_kernel has the same test; the host resolves it to the symbol the reference throws on)
+            const uint32_t ok = valid_slots(p.vstart, static_cast<int64_t>(bit >> 1), 0, jhi);
+            const uint32_t want = (1u << jhi) - 1u;
+            if (ok != want)
+                atomicMin(p.err_flat, static_cast<unsigned long long>(static_cast<uint64_t>(item) * G + (__ffs(ok ^ want) - 1)));
+        }
+        uint32_t x[NX];
+        load_block_at<NX>(p, bit, safe, x);
+        uint64_t fw[G][N], rv[G][N];
+        block_kmers<N, NX, G, true, WANT_RV, BPS>(x, p.s0, p.head_mask, fw, rv);
+
         uint64_t a[G][N], h[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
@@ -772,7 +781,7 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
         if (e != cudaSuccess) return e;
     }
 #endif
-    if constexpr (!RAGGED && !STRICT4 && SINK != SINK_BUCKETS && !KMC_TMA_STORE) {
+    if constexpr (!RAGGED && SINK != SINK_BUCKETS && !KMC_TMA_STORE) {
         const bool plain_soa = SINK == SINK_IDS || (!p.aos && !p.out_index);
         if (p.aligned && p.vec_ok && plain_soa && !p.items_dev && p.gprm < 0x80000000ull &&
             p.items < 0xffffffffull - kTileItems && aligned_kernel_enabled()) {
@@ -788,11 +797,12 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
                 return v < 0 ? 0 : (v > 200 * 1024 ? 200 * 1024 : v);
             }();
             if (pad > 0) {
-                cudaError_t e = cudaFuncSetAttribute(extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST>,
+                cudaError_t e = cudaFuncSetAttribute(extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST, STRICT4>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
                 if (e != cudaSuccess) return e;
             }
-            extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST><<<static_cast<unsigned>(tiles), kBlockThreads, pad, stream>>>(p);
+            extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST, STRICT4>
+                <<<static_cast<unsigned>(tiles), kBlockThreads, pad, stream>>>(p);
             return cudaGetLastError();
         }
     }
