@@ -115,28 +115,29 @@ KMC_DEV bool limbs_less(const uint64_t (&a)[N], const uint64_t (&b)[N])
     return lt;
 }
 
-// x * FX_CONSTANT mod 2^64.  On the device: one 32 x 32 -> 64-bit product and two multiply-adds into its high half
-// (the compiler's own expansion takes a fourth instruction; this multiplication runs once per k-mer and limb).
-KMC_DEV uint64_t mul_fx(uint64_t x)
+// x * C mod 2^64 for a compile-time C.  On the device: one 32 x 32 -> 64-bit product and two multiply-adds into its high
+// half (the compiler's own expansion takes a fourth instruction; fx_hash runs this once per k-mer and limb).
+template <uint64_t C> KMC_DEV uint64_t mul_c64(uint64_t x)
 {
 #ifdef __CUDA_ARCH__
     uint64_t r;
     asm("{\n\t"
         ".reg .u32 xl, xh, pl, ph;\n\t"
         "mov.b64 {xl, xh}, %1;\n\t"
-        "mul.lo.u32 pl, xl, 0x27220a95;\n\t"
-        "mul.hi.u32 ph, xl, 0x27220a95;\n\t"
-        "mad.lo.u32 ph, xh, 0x27220a95, ph;\n\t"
-        "mad.lo.u32 ph, xl, 0x517cc1b7, ph;\n\t"
+        "mul.lo.u32 pl, xl, %2;\n\t"
+        "mul.hi.u32 ph, xl, %2;\n\t"
+        "mad.lo.u32 ph, xh, %2, ph;\n\t"
+        "mad.lo.u32 ph, xl, %3, ph;\n\t"
         "mov.b64 %0, {pl, ph};\n\t"
         "}"
         : "=l"(r)
-        : "l"(x));
+        : "l"(x), "n"(static_cast<uint32_t>(C)), "n"(static_cast<uint32_t>(C >> 32)));
     return r;
 #else
-    return x * FX_CONSTANT;
+    return x * C;
 #endif
 }
+KMC_DEV uint64_t mul_fx(uint64_t x) { return mul_c64<FX_CONSTANT>(x); }
 
 // fx_hash (src/kmer.jl:255-261)
 template <int N>

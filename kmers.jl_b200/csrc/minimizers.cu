@@ -151,12 +151,17 @@ KMC_DEV void store_dense(uint64_t *p, const uint64_t (&v)[CNT], int n)
     }
 }
 
-template <int L, bool CANON, bool INDEX>
+constexpr int log2_floor(int w) { return w < 2 ? 0 : 1 + log2_floor(w / 2); }
+
+// W is a template parameter (31 instantiations per form): a thread builds and hashes exactly the G + W - 1 k-mers its G
+// windows can see, and the last merge has a compile-time distance.  (Templated on the class 2^L <= W < 2^(L+1) only, the
+// kernel hashed G + 2^(L+1) - 2 k-mers -- 30 instead of 25 for W = 10 -- and carried them through every doubling step.)
+template <int W, bool CANON, bool INDEX>
 __global__ void __launch_bounds__(128) minimizer_dense_kernel(const DenseParams p)
 {
+    constexpr int L = log2_floor(W);
     constexpr int G = dense_group(L);
-    constexpr int WCLASS = (2 << L) - 1;            // largest W of the class
-    constexpr int MM = G + WCLASS - 1;              // k-mers a thread hashes (those beyond G+W-1 never reach a result)
+    constexpr int MM = G + W - 1;                     // k-mers a thread hashes
     constexpr int NX = (64 + 2 * (MM - 1) + 31) / 32; // block words for K = 32
     const uint64_t item = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (item >= p.items) return;
@@ -203,14 +208,12 @@ __global__ void __launch_bounds__(128) minimizer_dense_kernel(const DenseParams 
             const uint64_t rv = stream64<NX>(nx, 2 * j) & p.mask; // ~W: the reverse complement (kmer_core.cuh)
             km = km < rv ? km : rv;
         }
-        h[j] = km * FX_CONSTANT; // fx_hash of a one-limb k-mer, h0 = 0 (src/kmer.jl:255-261)
+        h[j] = mul_fx(km); // fx_hash of a one-limb k-mer, h0 = 0 (src/kmer.jl:255-261)
         if (INDEX) pos[j] = j;
     }
     // sliding minima by doubling; ties keep the left (earlier) k-mer
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int s = 1 << l;
 #pragma unroll
         for (int i = 0; i + s < MM; ++i) {
@@ -221,16 +224,13 @@ __global__ void __launch_bounds__(128) minimizer_dense_kernel(const DenseParams 
     }
     // the window of W = 2^L + d k-mers: two blocks of 2^L, d apart (in place: h[i + d] is still a block minimum
     // when h[i] is overwritten, for every d >= 0)
-    const int d = p.w - (1 << L); // 0 <= d < 2^L, uniform
+    constexpr int d = W - (1 << L); // 0 <= d < 2^L
+    if (d > 0) {
 #pragma unroll
-    for (int dd = 1; dd < (1 << L); ++dd) {
-        if (d == dd) {
-#pragma unroll
-            for (int i = 0; i < G; ++i) {
-                const bool take = h[i + dd] < h[i];
-                h[i] = take ? h[i + dd] : h[i];
-                if (INDEX) pos[i] = take ? pos[i + dd] : pos[i];
-            }
+        for (int i = 0; i < G; ++i) {
+            const bool take = h[i + d] < h[i];
+            h[i] = take ? h[i + d] : h[i];
+            if (INDEX) pos[i] = take ? pos[i + d] : pos[i];
         }
     }
     const uint64_t e0 = r * p.cnt + t0;
@@ -247,34 +247,30 @@ __global__ void __launch_bounds__(128) minimizer_dense_kernel(const DenseParams 
         store_dense<G>(reinterpret_cast<uint64_t *>(p.out_index) + e0, o, nwin);
     }
 #pragma unroll
-    for (int i = 0; i < G; ++i) o[i] = h[i] * FX_INVERSE; // the k-mer itself
+    for (int i = 0; i < G; ++i) o[i] = mul_c64<FX_INVERSE>(h[i]); // the k-mer itself
     store_dense<G>(p.out_kmer + e0, o, nwin);
 }
 
 using DenseLaunchFn = void (*)(const DenseParams &, unsigned, cudaStream_t);
 
-template <int L, bool CANON, bool INDEX>
+template <int W, bool CANON, bool INDEX>
 void launch_dense(const DenseParams &p, unsigned blocks, cudaStream_t stream)
 {
-    minimizer_dense_kernel<L, CANON, INDEX><<<blocks, 128, 0, stream>>>(p);
+    minimizer_dense_kernel<W, CANON, INDEX><<<blocks, 128, 0, stream>>>(p);
 }
 
-template <int L>
+template <int W>
 DenseLaunchFn pick_dense(bool canon, bool index)
 {
-    if (canon) return index ? &launch_dense<L, true, true> : &launch_dense<L, true, false>;
-    return index ? &launch_dense<L, false, true> : &launch_dense<L, false, false>;
+    if (canon) return index ? &launch_dense<W, true, true> : &launch_dense<W, true, false>;
+    return index ? &launch_dense<W, false, true> : &launch_dense<W, false, false>;
 }
 
-DenseLaunchFn dense_launcher(int l, bool canon, bool index)
+template <int W = 1>
+DenseLaunchFn dense_launcher(int w, bool canon, bool index)
 {
-    switch (l) {
-    case 0: return pick_dense<0>(canon, index);
-    case 1: return pick_dense<1>(canon, index);
-    case 2: return pick_dense<2>(canon, index);
-    case 3: return pick_dense<3>(canon, index);
-    case 4: return pick_dense<4>(canon, index);
-    }
+    if (w == W) return pick_dense<W>(canon, index);
+    if constexpr (W < 31) return dense_launcher<W + 1>(w, canon, index);
     return nullptr;
 }
 
@@ -374,7 +370,7 @@ extern "C" int32_t kmc_minimizers(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, in
         d.out_hash = p.out_hash;
         d.out_index = p.out_index;
         d.index_base = p.index_base;
-        DenseLaunchFn fn = dense_launcher(l, p.canon != 0, p.out_index != nullptr);
+        DenseLaunchFn fn = dense_launcher<>(w, p.canon != 0, p.out_index != nullptr);
         if (!fn) return fail(ctx, KMC_E_UNSUPPORTED, "no dense minimizer kernel for this W");
         fn(d, static_cast<unsigned>((d.items + 127) / 128), stream);
     } else {
