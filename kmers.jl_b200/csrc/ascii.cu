@@ -12,6 +12,8 @@
 //   UnambiguousKmers (UnambiguousKmers.jl:109-132): ASCII_SKIPPING_LUT (iterators/common.jl:22-32):
 //     Aa Cc Gg TtUu -> 0..3 for both alphabets, "-MRSVWYHKDBN" in either case -> skip and
 //     restart, every other byte -> EncodeError.
+#include <mutex>
+
 #include "ascii_luts.h"
 #include "fourbit.h"
 
@@ -23,9 +25,14 @@ namespace {
 
 __constant__ uint8_t c_luts[5][256]; // strict DNA, strict RNA, skipping, 4-bit DNA, 4-bit RNA (ascii_luts.h)
 
-// 32 bytes -> 64 bits of 2-bit codes, 32 "not a base" flags, 32 error flags
+__device__ uint32_t g_pos[3][8][256]; // the positioned forms of the three 2-bit tables (ascii_luts.h: make_positioned)
+
+constexpr int kAsciiTiles = 4; // tiles of 256 groups a block recodes with one copy of the tables in shared memory
+
+// 32 bytes -> 64 bits of 2-bit codes, 32 "not a base" flags, 32 error flags.  s_pos: the positioned tables of the LUT in
+// shared memory, [8][256] words (a warp's look-ups fall into different banks unless two lanes hold bytes 32 apart).
 __device__ __forceinline__ void ascii_group(const uint8_t *__restrict__ bytes, uint64_t n_bytes, bool aligned, uint64_t g,
-                                            const uint8_t *s_lut, uint64_t &codes, uint32_t &fb, uint32_t &fe)
+                                            const uint32_t *s_pos, uint64_t &codes, uint32_t &fb, uint32_t &fe)
 {
     const uint64_t b0 = 32 * g;
     uint32_t v[8];
@@ -46,67 +53,82 @@ __device__ __forceinline__ void ascii_group(const uint8_t *__restrict__ bytes, u
             v[w] = t;
         }
     }
-    codes = 0;
-    fb = fe = 0;
+    uint32_t f[4]; // one result word per pair of words (eight bytes): see make_positioned
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int m = 0; m < 4; ++m) {
+        uint32_t acc = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t e = s_lut[(v[w] >> (8 * c)) & 0xffu];
-            const int sym = 4 * w + c;
-            codes |= static_cast<uint64_t>(e & 3u) << (2 * sym);
-            fb |= ((e >> 6) ? 1u : 0u) << sym; // skip or error: the symbol cannot be part of a k-mer
-            fe |= (e >> 7) << sym;
+        for (int par = 0; par < 2; ++par) {
+            const uint32_t x = v[2 * m + par];
+#pragma unroll
+            for (int pos = 0; pos < 4; ++pos) {
+                // byte offset of the entry: 4 * ((x >> 8 pos) & 0xff), as one shift and one mask
+                const uint32_t off = (pos == 0 ? (x << 2) : (x >> (8 * pos - 2))) & 0x3fcu;
+                acc |= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pos + (4 * par + pos) * 256) + off);
+            }
         }
+        f[m] = acc;
     }
+    codes = (static_cast<uint64_t>(__byte_perm(f[2], f[3], 0x7430)) << 32) | __byte_perm(f[0], f[1], 0x7430);
+    fb = __byte_perm(__byte_perm(f[0], f[1], 0x0051), __byte_perm(f[2], f[3], 0x0051), 0x5410);
+    fe = __byte_perm(__byte_perm(f[0], f[1], 0x0062), __byte_perm(f[2], f[3], 0x0062), 0x5410);
 }
 
 // One thread per group of 32 bytes: 2 x u32 of 2-bit codes, 1 x u32 of "not a base" flags, 1 x u32 of
 // error flags and, fused through shared memory (+ a recomputed 5-group halo), the valid-start word.
 // (rev: the codes once more in reversed symbol order, see recode_vstart_kernel in fourbit.cu)
+// A block recodes kAsciiTiles consecutive tiles of 256 groups.
 __global__ void __launch_bounds__(256) ascii_recode_kernel(const uint8_t *__restrict__ bytes, uint64_t n_bytes, int lut, int k,
                                                            uint32_t *__restrict__ rec, uint32_t *__restrict__ bad,
                                                            uint32_t *__restrict__ err, uint32_t *__restrict__ vstart,
                                                            uint64_t n_groups, uint64_t n_vstart, uint32_t *__restrict__ rev,
                                                            unsigned long long *__restrict__ any_err)
 {
-    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_pos[8 * 256];
     __shared__ uint32_t s_bad[256 + 8];
-    s_lut[threadIdx.x] = c_luts[lut][threadIdx.x];
+    {
+        const uint32_t *src = &g_pos[lut][0][0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_pos[i * 256 + threadIdx.x] = src[i * 256 + threadIdx.x];
+    }
     __syncthreads();
     const bool aligned = (reinterpret_cast<uintptr_t>(bytes) & 15) == 0;
-    const uint64_t g0 = static_cast<uint64_t>(blockIdx.x) * 256;
-    {
-        const uint64_t g = g0 + threadIdx.x;
-        uint32_t fb = 0, fe = 0;
-        if (g < n_groups) {
-            uint64_t codes;
-            ascii_group(bytes, n_bytes, aligned, g, s_lut, codes, fb, fe);
-            if (rec) reinterpret_cast<uint2 *>(rec)[g] = make_uint2(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32));
-            if (rev)
-                reinterpret_cast<uint2 *>(rev)[n_groups - 1 - g] =
-                    make_uint2(rev2_32(static_cast<uint32_t>(codes >> 32)), rev2_32(static_cast<uint32_t>(codes)));
-            if (bad) bad[g] = fb;
-            if (err) err[g] = fe;
-            if (fe && any_err) atomicOr(any_err, 1ull); // (rare: lets the per-sequence search for the first error return at once)
+    for (int tile = 0; tile < kAsciiTiles; ++tile) {
+        const uint64_t g0 = (static_cast<uint64_t>(blockIdx.x) * kAsciiTiles + tile) * 256;
+        if (g0 >= n_vstart) break; // block-uniform (n_vstart >= n_groups)
+        {
+            const uint64_t g = g0 + threadIdx.x;
+            uint32_t fb = 0, fe = 0;
+            if (g < n_groups) {
+                uint64_t codes;
+                ascii_group(bytes, n_bytes, aligned, g, s_pos, codes, fb, fe);
+                if (rec) reinterpret_cast<uint2 *>(rec)[g] = make_uint2(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32));
+                if (rev)
+                    reinterpret_cast<uint2 *>(rev)[n_groups - 1 - g] =
+                        make_uint2(rev2_32(static_cast<uint32_t>(codes >> 32)), rev2_32(static_cast<uint32_t>(codes)));
+                if (bad) bad[g] = fb;
+                if (err) err[g] = fe;
+                if (fe && any_err) atomicOr(any_err, 1ull); // (rare: lets the per-sequence search for the first error return at once)
+            }
+            s_bad[threadIdx.x] = fb;
         }
-        s_bad[threadIdx.x] = fb;
-    }
-    if (threadIdx.x < kRecodeHalo) {
-        const uint64_t g = g0 + 256 + threadIdx.x;
-        uint32_t fb = 0, fe = 0;
-        uint64_t codes;
-        if (g < n_groups) ascii_group(bytes, n_bytes, aligned, g, s_lut, codes, fb, fe);
-        s_bad[256 + threadIdx.x] = fb;
-    }
-    __syncthreads();
-    const uint64_t g = g0 + threadIdx.x;
-    if (g < n_vstart) {
-        uint32_t a[6];
+        if (threadIdx.x < kRecodeHalo) {
+            const uint64_t g = g0 + 256 + threadIdx.x;
+            uint32_t fb = 0, fe = 0;
+            uint64_t codes;
+            if (g < n_groups) ascii_group(bytes, n_bytes, aligned, g, s_pos, codes, fb, fe);
+            s_bad[256 + threadIdx.x] = fb;
+        }
+        __syncthreads();
+        const uint64_t g = g0 + threadIdx.x;
+        if (g < n_vstart) {
+            uint32_t a[6];
 #pragma unroll
-        for (int d = 0; d < 5; ++d) a[d] = s_bad[threadIdx.x + d];
-        a[5] = 0;
-        vstart[g] = valid_start_word(a, k);
+            for (int d = 0; d < 5; ++d) a[d] = s_bad[threadIdx.x + d];
+            a[5] = 0;
+            vstart[g] = valid_start_word(a, k);
+        }
+        __syncthreads(); // s_bad is rewritten by the next tile
     }
 }
 
@@ -247,6 +269,8 @@ __global__ void __launch_bounds__(256) resolve_ascii_error_kernel(ExtractParams 
 static cudaError_t upload_luts()
 {
     static bool uploaded[64] = {};
+    static std::mutex mu; // the device group calls in from one host thread per device
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -254,6 +278,12 @@ static cudaError_t upload_luts()
         const AsciiLuts l = make_luts();
         static_assert(sizeof(AsciiLuts) == sizeof(c_luts), "the constant-memory copy holds every table");
         e = cudaMemcpyToSymbol(c_luts, &l, sizeof l);
+        if (e != cudaSuccess) return e;
+        static uint32_t pos[3][8][256]; // (guarded by `uploaded`: filled before the flag of the first device is set)
+        make_positioned(l.strict_dna, pos[0]);
+        make_positioned(l.strict_rna, pos[1]);
+        make_positioned(l.skipping, pos[2]);
+        e = cudaMemcpyToSymbol(g_pos, pos, sizeof pos);
         if (e != cudaSuccess) return e;
         uploaded[dev] = true;
     }
@@ -285,7 +315,7 @@ cudaError_t ascii_recode(const uint8_t *bytes, uint64_t n_bytes, int lut, int k,
         e = cudaMemsetAsync(any_err, 0, 8, stream);
         if (e != cudaSuccess) return e;
     }
-    ascii_recode_kernel<<<static_cast<unsigned>((n_vstart + 255) / 256), 256, 0, stream>>>(bytes, n_bytes, lut, k, rec, bad, err,
+    ascii_recode_kernel<<<static_cast<unsigned>((n_vstart + 256 * kAsciiTiles - 1) / (256 * kAsciiTiles)), 256, 0, stream>>>(bytes, n_bytes, lut, k, rec, bad, err,
                                                                                           vstart, n_groups, n_vstart, rev, any_err);
     return cudaGetLastError();
 }

@@ -47,4 +47,23 @@ inline AsciiLuts make_luts()
     return l;
 }
 
+// The 2-bit tables once more, "positioned": eight 256-entry tables of 32-bit words, one per (byte position in a 32-bit
+// word, parity of the word within a pair).  The entry of byte c in table (pos, par) has the byte's three results already
+// in the place they take in the result F of an eight-byte pair -- OR-ing the eight entries of a pair IS the recoding:
+//   bits  0- 7  the four 2-bit codes of the even word   (code << 2 pos, if par == 0)
+//   bits 24-31  the four 2-bit codes of the odd word    (code << 2 pos, if par == 1)
+//   bits  8-15  "not a base" flags of the eight bytes   (bit 8 + 4 par + pos)
+//   bits 16-23  error flags of the eight bytes          (bit 16 + 4 par + pos)
+// so ascii_recode_kernel spends a shift, a mask and a shared-memory load per byte and a handful of byte permutes per 32
+// bytes instead of a dozen instructions per byte.
+inline void make_positioned(const uint8_t (&lut)[256], uint32_t (&out)[8][256])
+{
+    for (int par = 0; par < 2; ++par)
+        for (int pos = 0; pos < 4; ++pos)
+            for (int c = 0; c < 256; ++c) {
+                const uint32_t e = lut[c], code = e & 3u, fb = (e >> 6) ? 1u : 0u, fe = e >> 7;
+                out[4 * par + pos][c] = ((code << (2 * pos)) << (par ? 24 : 0)) | (fb << (8 + 4 * par + pos)) | (fe << (16 + 4 * par + pos));
+            }
+}
+
 } // namespace kmc
