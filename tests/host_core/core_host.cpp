@@ -147,6 +147,26 @@ extern "C" void core_ascii_luts(uint8_t *out)
     }
 }
 
+// The positioned tables of ascii_recode_kernel applied to 32 bytes on the host, exactly as the kernel combines them: the OR of
+// the eight entries of every byte pair, then the byte permutes.  which: 0 strict DNA, 1 strict RNA, 2 skipping.
+// out: codes (2 words), "not a base" flags, error flags.
+extern "C" void core_ascii_group_positioned(int which, const uint8_t *bytes32, uint32_t *out)
+{
+    const kmc::AsciiLuts l = kmc::make_luts();
+    static uint32_t pos[8][256];
+    kmc::make_positioned(which == 0 ? l.strict_dna : which == 1 ? l.strict_rna : l.skipping, pos);
+    uint32_t f[4];
+    for (int m = 0; m < 4; ++m) {
+        f[m] = 0;
+        for (int par = 0; par < 2; ++par)
+            for (int p = 0; p < 4; ++p) f[m] |= pos[4 * par + p][bytes32[8 * m + 4 * par + p]];
+    }
+    out[0] = __byte_perm(f[0], f[1], 0x7430);
+    out[1] = __byte_perm(f[2], f[3], 0x7430);
+    out[2] = __byte_perm(__byte_perm(f[0], f[1], 0x0051), __byte_perm(f[2], f[3], 0x0051), 0x5410);
+    out[3] = __byte_perm(__byte_perm(f[0], f[1], 0x0062), __byte_perm(f[2], f[3], 0x0062), 0x5410);
+}
+
 // the two 4-bit tables (k-mers over DNAAlphabet{4} / RNAAlphabet{4} from ASCII sources)
 extern "C" void core_ascii_luts4(uint8_t *out)
 {

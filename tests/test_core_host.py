@@ -200,6 +200,31 @@ def test_ascii_tables_follow_the_reference(core):
         assert rna[b] == ("ACGU".index(c.upper()) if c.upper() in "ACGU" and c.isalpha() else ERR), b
 
 
+def test_positioned_ascii_tables_recode_like_the_byte_tables(core):
+    """ascii_recode_kernel ORs eight pre-placed 32-bit entries per byte pair (ascii_luts.h: make_positioned) and assembles a
+    group of 32 bytes with byte permutes: the result must be what the plain byte tables say, symbol by symbol -- every byte
+    value in every position of a group, for the three tables."""
+    core.core_ascii_group_positioned.restype = None
+    core.core_ascii_group_positioned.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    luts = np.zeros(768, dtype=np.uint8)
+    core.core_ascii_luts(luts.ctypes.data)
+    rng = np.random.default_rng(11)
+    out = np.zeros(4, dtype=np.uint32)
+    for which in range(3):
+        lut = luts[256 * which:256 * which + 256]
+        groups = [np.roll(np.arange(256, dtype=np.uint8), s)[i:i + 32].copy() for s in range(32) for i in range(0, 256, 32)]
+        groups += [rng.integers(0, 256, size=32, dtype=np.uint8) for _ in range(200)]
+        groups += [np.frombuffer(b"ACGTNacgtnUu-RYKM" * 2, dtype=np.uint8)[:32].copy()]
+        for g in groups:
+            core.core_ascii_group_positioned(which, g.ctypes.data, out.ctypes.data)
+            codes = int(out[0]) | (int(out[1]) << 32)
+            for t in range(32):
+                e = int(lut[g[t]])
+                assert (codes >> (2 * t)) & 3 == e & 3, (which, t, g[t])
+                assert (int(out[2]) >> t) & 1 == (1 if e >> 6 else 0), (which, t, g[t])
+                assert (int(out[3]) >> t) & 1 == e >> 7, (which, t, g[t])
+
+
 def test_ascii_tables_of_the_4bit_alphabets(core):
     """The tables behind k-mers over DNAAlphabet{4} / RNAAlphabet{4} from ASCII bytes: every symbol of the alphabet -- the gap
     and A C M G R S V T/U W Y H K D B N, encodings 0..15 (BioSymbols) -- in either case; any other byte is an error.  Checked
