@@ -341,6 +341,15 @@ KMC_DEV void burst_prefetch(const ExtractParams &p, uint64_t n_items)
     for (int64_t o = b0 + (static_cast<int64_t>(kk) * kBlockThreads + threadIdx.x) * 128; o < b1;
          o += static_cast<int64_t>(kPfBlocks) * kBlockThreads * 128)
         asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + o));
+    if (BPS == 2 && p.vstart) {
+        // strict iteration over a recoded source: the valid-start bits of the chunk (one bit per symbol = half the bytes
+        // of the 2-bit stream) are a second trickle of reads; pull them in with the same burst
+        const char *vb = reinterpret_cast<const char *>(p.vstart);
+        const int64_t v0 = (b0 >> 1) & ~127ll, v1 = (b1 >> 1) + 128; // (the array has two spare words past the last symbol's)
+        for (int64_t o = v0 + (static_cast<int64_t>(kk) * kBlockThreads + threadIdx.x) * 128; o < v1;
+             o += static_cast<int64_t>(kPfBlocks) * kBlockThreads * 128)
+            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(vb + o));
+    }
 }
 
 // KMC_PREFETCH=0 switches the burst prefetch off (A/B measurements)
