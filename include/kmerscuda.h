@@ -210,11 +210,7 @@ int32_t kmc_bucket_count(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t 
  * caller all-reduces range i on a second stream that waits for events[i] while later ranges are still
  * being counted (tables beyond L2 are filled slice after slice; an L2-sized table is final only at the
  * end, and all events are recorded there).  result->n_written is set; result->kernel_ms is not.  The
- * call is complete when events[n_parts - 1] has completed (or after kmc_sync).  It returns before the
- * counting is finished but not always at once: for a table beyond L2 over an aligned uniform set of
- * one-limb k-mers it waits until the ids are binned (a third of the work) before it enqueues the
- * increments, because a bin that overflowed sends the call to the exact path -- callers that drive
- * several devices from one thread should give each device its own (kmc_group_bucket_count does). */
+ * call is complete when events[n_parts - 1] has completed (or after kmc_sync). */
 int32_t kmc_bucket_count_async(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t bucket_bits,
                                uint32_t *table, uint32_t n_parts, void *const *events, kmc_result *result);
 

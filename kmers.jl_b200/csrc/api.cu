@@ -342,9 +342,6 @@ int32_t kmc_ctx_destroy(kmc_ctx *ctx)
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
-    for (auto e : ctx->aux_events)
-        if (e) cudaEventDestroy(e);
     if (ctx->comm) comm_detach(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -665,86 +662,20 @@ int32_t bucket_count_impl(kmc_ctx *ctx, const kmc_seqs *seqs, int32_t k, int32_t
     if (want_binned) set_iteration_strides(pa, ge.g);
     if (want_binned && ge.n_limbs == 1 && L.uniform_len && binned_count_bin_bits(bucket_bits) == 6 && fused_bin_enabled() && pa.aligned &&
         pa.al_tail == 0 && pa.items < 0xffffffffull - kTileItems) {
-        // One-limb k-mers over an aligned uniform set (C5): ids and bins from one kernel, bins of a fixed capacity
-        // (buckets.cu).  The set is cut into pieces by read ranges: the bins of piece i are applied on a second stream
-        // while piece i + 1 is being binned on the first -- the increments are bound by the L2 atomic path, the binning
-        // by instruction issue and shared memory, and an SM has room for both.  A piece one of whose bins overflows (a
-        // set whose k-mers crowd into one range of buckets) is skipped by its apply kernels and counted on the exact path.
-        constexpr int kMaxPieces = 16;
-        int pieces = fused_bin_pieces(L.total);
-        if (static_cast<uint64_t>(pieces) > seqs->n_seqs) pieces = static_cast<int>(seqs->n_seqs);
-        st = ensure_host_small(ctx);
-        if (st) return st;
-        cudaStream_t s_apply = stream;
-        if (pieces > 1) {
-            if (!ctx->aux_stream) {
-                int lo = 0, hi = 0;
-                CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-                CU(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
-                for (auto &e : ctx->aux_events) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            }
-            s_apply = ctx->aux_stream;
-            CU(cudaEventRecord(ctx->aux_events[16], stream)); // what the caller enqueued before (the table's memset) comes first
-            CU(cudaStreamWaitEvent(s_apply, ctx->aux_events[16], 0));
-        }
-        struct Piece {
-            ExtractParams q;
-            uint64_t windows = 0, cap = 0;
-            AsyncBuf bins, cursor;
-        } piece[kMaxPieces];
-        const uint64_t stride32 = pa.read_bits / 32; // 32-bit words from one read to the next (read_bits is a multiple of 32)
-        bool have_mem = true;
-        for (int i = 0; i < pieces && have_mem; ++i) {
-            const uint64_t r0 = seqs->n_seqs * i / pieces, r1 = seqs->n_seqs * (i + 1) / pieces;
-            Piece &pc = piece[i];
-            pc.q = p;
-            pc.q.w32 = p.w32 + r0 * stride32;
-            pc.q.nw32 = p.nw32 - static_cast<int64_t>(r0 * stride32);
-            pc.q.n_seqs = r1 - r0;
-            pc.q.items = (r1 - r0) * L.gprm;
-            pc.windows = (r1 - r0) * L.wpr;
-            pc.cap = fused_bin_capacity(pc.windows);
-            cudaError_t e = pc.bins.alloc(ctx, (pc.cap * 64 + 4096) * 4, stream); // 64 bins + the dump area of one iteration
-            if (e == cudaSuccess) e = pc.cursor.alloc(ctx, 65 * 8, stream);
-            if (e != cudaSuccess) {
-                (void)cudaGetLastError();
-                have_mem = false;
-            }
-        }
-        if (have_mem) {
-            for (int i = 0; i < pieces; ++i) {
-                Piece &pc = piece[i];
-                CU(fused_bin_ids(pc.q, ge.nx, bucket_bits, pc.bins.as<uint32_t>(), pc.cap, pc.cursor.as<unsigned long long>(), stream));
-                CU(cudaMemcpyAsync(ctx->host_small + 64 + i, pc.cursor.as<unsigned long long>() + 64, 8, cudaMemcpyDeviceToHost, stream));
-                if (pieces > 1) CU(cudaEventRecord(ctx->aux_events[i], stream));
-                if (i > 0) { // the bins of the piece before: beside this piece's binning
-                    Piece &pv = piece[i - 1];
-                    CU(cudaStreamWaitEvent(s_apply, ctx->aux_events[i - 1], 0));
-                    CU(fused_bin_apply(pv.bins.as<uint32_t>(), pv.cap, pv.cursor.as<unsigned long long>(), bucket_bits, table, warm_sink(ctx),
-                                       ctx->sm_count, s_apply, 0, nullptr, true));
-                }
-            }
-            // every piece is binned once this returns (~10 us after the last binning kernel; the applies go on beside it):
-            // the range events below must not be recorded before every flagged piece has been counted
-            CU(cudaStreamSynchronize(stream));
-            if (pieces > 1) CU(cudaStreamWaitEvent(s_apply, ctx->aux_events[pieces - 1], 0));
-            for (int i = 0; i + 1 < pieces; ++i)
-                if (ctx->host_small[64 + i]) {
-                    st = count_exact(piece[i].q, piece[i].windows, s_apply, 0, nullptr);
-                    if (st) return st;
-                }
-            Piece &pl = piece[pieces - 1];
-            if (ctx->host_small[64 + pieces - 1]) {
-                st = count_exact(pl.q, pl.windows, s_apply, n_parts, events);
-                if (st) return st;
-            } else {
-                CU(fused_bin_apply(pl.bins.as<uint32_t>(), pl.cap, pl.cursor.as<unsigned long long>(), bucket_bits, table, warm_sink(ctx),
-                                   ctx->sm_count, s_apply, n_parts, events, false));
-            }
-            if (pieces > 1) { // later work on the context's stream (and the release of the pieces' buffers) comes after the applies
-                CU(cudaEventRecord(ctx->aux_events[17], s_apply));
-                CU(cudaStreamWaitEvent(stream, ctx->aux_events[17], 0));
-            }
+        // One-limb k-mers over an aligned uniform set (C5): ids and bins from one kernel, bins of a fixed capacity and a
+        // spill list for the runs of a bin that filled up (buckets.cu).  Asynchronous like the exact path.
+        AsyncBuf bins_buf, state_buf;
+        const uint64_t cap = fused_bin_capacity(L.total);
+        cudaError_t e = bins_buf.alloc(ctx, fused_bin_buffer_ids(L.total) * 4, stream);
+        if (e == cudaSuccess) e = state_buf.alloc(ctx, fused_bin_state_bytes(), stream);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError(); // not enough memory: the exact path (which may end at direct increments)
+        } else {
+            st = ensure_host_small(ctx); // allocates dev_small, where the warm-up kernel's sink lives
+            if (st) return st;
+            CU(fused_bin_ids(pa, ge.nx, bucket_bits, bins_buf.as<uint32_t>(), cap, state_buf.as<unsigned long long>(), stream));
+            CU(fused_bin_apply(bins_buf.as<uint32_t>(), cap, state_buf.as<unsigned long long>(), bucket_bits, table, warm_sink(ctx),
+                               ctx->sm_count, stream, n_parts, events));
             done = true;
         }
     }

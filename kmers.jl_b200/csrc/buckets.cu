@@ -75,15 +75,21 @@ __global__ void __launch_bounds__(256) bin_apply_kernel(const uint32_t *__restri
 // inside a bin, so here ONE kernel produces the ids and bins them: a block computes the canonical k-mers and hashes
 // of 4096 windows per iteration (16 per thread, in registers), runs the same shared-memory binning step
 // (binning.cuh: scatter64_iter) and reserves the place of each of its 64 runs with one atomicAdd on the bin's
-// cursor.  The bins have a fixed capacity, mean + 12.5 % + 8192: fx_hash spreads distinct k-mers evenly, and a set in
-// which one bucket range attracts that much more than its share (reads of one repeated k-mer, say) overflows a bin --
-// its runs go to a dump area, the flag is set, and the caller repeats the count on the exact path (tests/test_gpu_parity.py
-// forces that).  4.2 + 1.9 + 7.9 ms of the 30.6 ms per 3 G k-mers become one kernel.
+// cursor.  The bins have a fixed capacity, mean + 12.5 % + 8192 ids: fx_hash spreads distinct k-mers evenly.  A set in which
+// one bucket range attracts much more than its share (reads of one repeated k-mer, say) fills a bin; a run that no longer
+// fits goes to the SPILL list instead (one more atomicAdd; the list can hold every id of the call, so nothing is ever
+// dropped and there is nothing to fall back to), and the bin ends where that run would have begun.  The spilled ids are
+// applied to the table directly, before the bins -- they are few, or they are many and hit the same few counters.
+// 4.2 + 1.9 + 7.9 ms of the 30.6 ms per 3 G k-mers become one kernel of 9.7 ms, and the call stays asynchronous.
 // ---------------------------------------------------------------------------------------------
+constexpr int kStateBinEnd = binning::kTpBins;      // state[64 .. 128): where a full bin ends (~0: it never filled up)
+constexpr int kStateSpill = 2 * binning::kTpBins;   // state[128]: ids in the spill list
+constexpr int kStateWords = 2 * binning::kTpBins + 2;
+
 struct FusedBins {
-    uint32_t *binned;             // 64 bins of `cap` ids each, then a dump area of one iteration's ids (runs that found their bin full)
+    uint32_t *binned;             // 64 bins of `cap` ids each, then the spill list
     uint64_t cap;                 // a multiple of 4 (the apply kernel loads 16 bytes at a time)
-    unsigned long long *cursor;   // [64] ids reserved per bin, [64] = overflow flag
+    unsigned long long *state;    // [64] ids reserved per bin, [64] bin ends, [1] spill cursor
     int bin_shift;                // bin = id >> bin_shift
 };
 
@@ -103,13 +109,15 @@ __global__ void __launch_bounds__(binning::kBlock, 3) bucket_bin_kernel(const Ex
     const bool inside = items.template loads_inside<NX>(p, tile_end - 1u);
     const binning::IdBin bin_of{f.bin_shift};
     constexpr int kItemsPerIter = 2 * binning::kBlock;
-    // where the run of `count` ids of bin b goes; a run that does not fit is sent to the dump area behind the last bin
+    // where the run of `count` ids of bin b goes
     auto reserve = [&](int b, uint32_t count) -> uint64_t {
         if (count == 0) return 0;
-        const uint64_t at = atomicAdd(f.cursor + b, static_cast<unsigned long long>(count));
+        const uint64_t at = atomicAdd(f.state + b, static_cast<unsigned long long>(count));
         if (at + count > f.cap) {
-            f.cursor[binning::kTpBins] = 1; // the bin is full: the caller repeats the count on the exact path
-            return binning::kTpBins * f.cap;
+            // the bin is full: it ends where this run would have begun (every run reserved before it fits, every later
+            // one starts beyond the capacity too), and the run goes to the spill list
+            atomicMin(f.state + kStateBinEnd + b, static_cast<unsigned long long>(at));
+            return binning::kTpBins * f.cap + atomicAdd(f.state + kStateSpill, static_cast<unsigned long long>(count));
         }
         return static_cast<uint64_t>(b) * f.cap + at;
     };
@@ -149,10 +157,8 @@ __global__ void __launch_bounds__(binning::kBlock, 3) bucket_bin_kernel(const Ex
     }
 }
 
-// The ids of bin b are binned[b * cap .. b * cap + cursor[b]).  Does nothing when the piece's overflow flag (cursor[64]) is set:
-// the caller repeats that piece on the exact path.  The next 16 bytes of ids are loaded before the current four are
-// applied, so that a few warps per SM keep the increment path busy (the kernel also runs beside the binning kernel of
-// the next piece, in whatever that leaves free of an SM).
+// The ids of bin b are binned[b * cap .. b * cap + min(reserved, bin end)).  The next 16 bytes of ids are loaded before the
+// current four are applied.
 __device__ __forceinline__ uint4 ld_ids(const uint32_t *p)
 {
     uint4 v;
@@ -166,15 +172,16 @@ __device__ __forceinline__ void inc_counter(uint32_t *p)
     asm volatile("red.global.add.L2::cache_hint.u32 [%0], 1, %1;" ::"l"(p), "l"(0x14F0000000000000ull) : "memory");
 }
 
-__global__ void bin_apply_fused_kernel(const uint32_t *__restrict__ binned, uint64_t cap, const unsigned long long *__restrict__ cursor,
-                                       int bin, int bin_end, uint32_t *__restrict__ table)
+__global__ void __launch_bounds__(256) bin_apply_fused_kernel(const uint32_t *__restrict__ binned, uint64_t cap,
+                                                              const unsigned long long *__restrict__ state, int bin, int bin_end,
+                                                              uint32_t *__restrict__ table)
 {
-    if (cursor[binning::kTpBins] != 0) return;
     const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t step = static_cast<uint64_t>(gridDim.x) * blockDim.x * 4;
     for (int b = bin; b < bin_end; ++b) {
         const uint32_t *ids = binned + static_cast<uint64_t>(b) * cap; // 16-byte aligned: cap is a multiple of 4
-        const uint64_t n = cursor[b], n4 = n & ~3ull;
+        const uint64_t reserved = state[b], full_at = state[kStateBinEnd + b];
+        const uint64_t n = reserved < full_at ? reserved : full_at, n4 = n & ~3ull;
         uint64_t i = tid * 4;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (i < n4) v = ld_ids(ids + i);
@@ -191,6 +198,15 @@ __global__ void bin_apply_fused_kernel(const uint32_t *__restrict__ binned, uint
         }
         if (tid < n - n4) inc_counter(table + ids[n4 + tid]);
     }
+}
+
+// the spill list: ids whose bin was full, applied to the table as they come (no slice of it is resident for them)
+__global__ void __launch_bounds__(256) spill_apply_kernel(const uint32_t *__restrict__ spill, const unsigned long long *__restrict__ state,
+                                                          uint32_t *__restrict__ table)
+{
+    const uint64_t n = state[kStateSpill];
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        atomicAdd(table + spill[i], 1u);
 }
 
 } // namespace
@@ -237,10 +253,13 @@ uint64_t fused_bin_capacity(uint64_t n_ids)
     const uint64_t cap = n_ids / binning::kTpBins + n_ids / (8 * binning::kTpBins) + 8192;
     return (cap + 3) & ~3ull;
 }
+// ids the binned buffer holds: the 64 bins and a spill list long enough for every id of the call
+uint64_t fused_bin_buffer_ids(uint64_t n_ids) { return binning::kTpBins * fused_bin_capacity(n_ids) + n_ids + 4096; }
+uint64_t fused_bin_state_bytes() { return kStateWords * sizeof(unsigned long long); }
 
-// First half: cursor (65 u64) is zeroed, then one kernel bins the bucket ids of every window.  p: the parameter block of an
-// aligned uniform set of one-limb k-mers (the caller has checked that), bucket_shift set.
-cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *binned, uint64_t cap, unsigned long long *cursor,
+// First half: one kernel bins the bucket ids of every window.  p: the parameter block of an aligned uniform set of
+// one-limb k-mers with whole groups (the caller has checked that), bucket_shift set.
+cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *binned, uint64_t cap, unsigned long long *state,
                           cudaStream_t stream)
 {
     const int pbits = binned_count_bin_bits(bucket_bits);
@@ -255,9 +274,10 @@ cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *bi
         const uint64_t per_tile = static_cast<uint64_t>(p.nw32) * 4 / tiles + 1, t = kPfChunkBytes / per_tile;
         p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
     }
-    cudaError_t e = cudaMemsetAsync(cursor, 0, (binning::kTpBins + 1) * sizeof(unsigned long long), stream);
+    cudaError_t e = cudaMemsetAsync(state, 0, kStateWords * sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(state + kStateBinEnd, 0xff, binning::kTpBins * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    const FusedBins f{binned, cap, cursor, bucket_bits - pbits};
+    const FusedBins f{binned, cap, state, bucket_bits - pbits};
     constexpr int smem = static_cast<int>(sizeof(binning::Scatter64Smem<uint32_t>));
     auto launch = [&](auto tag) -> cudaError_t {
         constexpr int NX = decltype(tag)::value;
@@ -274,51 +294,28 @@ cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *bi
     return cudaErrorInvalidValue;
 }
 
-// Second half: the bins are applied in table order, as in binned_count (a piece whose overflow flag is set is skipped on the
-// device).  beside = the binning kernel of the next piece is running on another stream: smaller blocks, which fit into
-// what its three blocks per SM leave of the register file.
-cudaError_t fused_bin_apply(const uint32_t *binned, uint64_t cap, const unsigned long long *cursor, int bucket_bits, uint32_t *table,
-                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events, bool beside)
+// Second half: the spill list, then the bins in table order, as in binned_count.
+cudaError_t fused_bin_apply(const uint32_t *binned, uint64_t cap, const unsigned long long *state, int bucket_bits, uint32_t *table,
+                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events)
 {
     if (!events) n_parts = 0;
     const int pbits = binned_count_bin_bits(bucket_bits);
     const int n_bins = 1 << pbits, shift = bucket_bits - pbits;
     const uint64_t slice = 1ull << shift;
     const int group = apply_group(2);
-    static const int env_block = [] { const char *e = getenv("KMC_APPLY_BLOCK"); return e ? atoi(e) : 0; }();
-    static const int env_grid = [] { const char *e = getenv("KMC_APPLY_GRID"); return e ? atoi(e) : 0; }();
-    int block = beside ? 128 : 256, per_sm = beside ? 4 : 16;
-    if (beside && env_block >= 32 && env_block <= 1024 && env_block % 32 == 0) block = env_block;
-    if (beside && env_grid >= 1 && env_grid <= 64) per_sm = env_grid;
-    if (beside) {
-        // An SM holds blocks of two kernels at once only under one shared-memory carve-out: ask for the binning kernel's
-        // (it uses nearly all of it), or these kernels wait until an SM has drained.
-        cudaError_t e = cudaFuncSetAttribute(bin_apply_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(warm_slice_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-    }
+    spill_apply_kernel<<<static_cast<unsigned>(sm_count * 8), 256, 0, stream>>>(binned + static_cast<uint64_t>(n_bins) * cap, state, table);
     uint32_t parts_done = 0;
     for (int b = 0; b < n_bins; b += group) {
         const int b_end = b + group < n_bins ? b + group : n_bins;
         warm_slice_kernel<<<static_cast<unsigned>(sm_count * 8), 256, 0, stream>>>(table + static_cast<uint64_t>(b) * slice,
                                                                                   slice * (b_end - b), sink);
-        bin_apply_fused_kernel<<<static_cast<unsigned>(sm_count * per_sm), block, 0, stream>>>(binned, cap, cursor, b, b_end, table);
+        bin_apply_fused_kernel<<<static_cast<unsigned>(sm_count * 16), 256, 0, stream>>>(binned, cap, state, b, b_end, table);
         while (parts_done < n_parts && static_cast<uint64_t>(parts_done + 1) * n_bins <= static_cast<uint64_t>(b_end) * n_parts) {
             cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(events[parts_done++]), stream);
             if (e != cudaSuccess) return e;
         }
     }
     return cudaGetLastError();
-}
-
-// Pieces a fused count is cut into (KMC_BIN_PIECES overrides): the increments of piece i run beside the binning of piece i + 1.
-int fused_bin_pieces(uint64_t n_ids)
-{
-    static const int env = [] { const char *e = getenv("KMC_BIN_PIECES"); return e ? atoi(e) : 0; }();
-    int pieces = env > 0 ? (env > 16 ? 16 : env) : 1;
-    while (pieces > 1 && n_ids / pieces < (1ull << 26)) --pieces; // a piece of less than 64 M ids is not worth its launches
-    return pieces;
 }
 
 // KMC_FUSED_BIN=0 keeps every binned count on the exact three-pass path (A/B measurements, tests of both)

@@ -17,10 +17,6 @@ struct kmc_ctx {
     cudaEvent_t pipe_events[3] = {nullptr, nullptr, nullptr};   // phase-A completion per slot
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // kmc_timer_*
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;      // per-call kernel timing
-    // the fused bucket count applies the bins of one piece of the input on this (high-priority) stream while the next
-    // piece is being binned on `stream`; created on first use
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t aux_events[18] = {};
     // grow-only scratch (scans, recoded 4-bit streams, compaction counters)
     void *scratch = nullptr;
     uint64_t scratch_bytes = 0;
@@ -94,16 +90,17 @@ cudaError_t binned_count(const uint32_t *ids, uint64_t n, int bucket_bits, uint3
                          uint64_t *offs, uint64_t *scan_tmp, int sm_count, cudaStream_t stream, uint32_t n_parts = 0,
                          void *const *events = nullptr);
 
-// The same count for one-limb k-mers over an aligned uniform set, ids produced and binned by ONE kernel into bins of a fixed
-// capacity (buckets.cu): fused_bin_ids, then -- if cursor[64], the overflow flag, is still 0 -- fused_bin_apply.
+// The same count for one-limb k-mers over an aligned uniform set with whole groups, ids produced and binned by ONE kernel into
+// bins of a fixed capacity plus a spill list (buckets.cu): fused_bin_ids, then fused_bin_apply.  Nothing synchronises.
 struct ExtractParams;
 bool fused_bin_enabled();
-uint64_t fused_bin_capacity(uint64_t n_ids); // ids per bin; the binned buffer holds 64 of them
-cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *binned, uint64_t cap, unsigned long long *cursor,
+uint64_t fused_bin_capacity(uint64_t n_ids);   // ids per bin
+uint64_t fused_bin_buffer_ids(uint64_t n_ids); // ids of the binned buffer (64 bins + the spill list)
+uint64_t fused_bin_state_bytes();              // bytes of the cursor block
+cudaError_t fused_bin_ids(ExtractParams p, int nx, int bucket_bits, uint32_t *binned, uint64_t cap, unsigned long long *state,
                           cudaStream_t stream);
-cudaError_t fused_bin_apply(const uint32_t *binned, uint64_t cap, const unsigned long long *cursor, int bucket_bits, uint32_t *table,
-                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events, bool beside);
-int fused_bin_pieces(uint64_t n_ids);
+cudaError_t fused_bin_apply(const uint32_t *binned, uint64_t cap, const unsigned long long *state, int bucket_bits, uint32_t *table,
+                            uint32_t *sink, int sm_count, cudaStream_t stream, uint32_t n_parts, void *const *events);
 
 // misc_kernels.cu -----------------------------------------------------------------------------
 cudaError_t launch_fx_hash(const uint64_t *kmers, uint64_t n, int n_limbs, uint64_t h0, uint64_t *out, int sm_count,

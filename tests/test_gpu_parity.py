@@ -442,10 +442,11 @@ def test_bucket_count_binned_ragged(kc):
         assert np.array_equal(np.nonzero(table)[0], idx) and np.array_equal(table[idx], cnt.astype(np.uint32))
 
 
-def test_bucket_count_fused_bins_and_overflow_fallback(kc):
+def test_bucket_count_fused_bins_and_spill_list(kc):
     """Tables beyond L2, one-limb k-mers, aligned uniform set: ids and bins come from one kernel with bins of a fixed
-    capacity.  Random reads fit; a set dominated by one repeated k-mer overflows its bin and the call repeats the count
-    on the exact path -- the table is the same exact histogram either way."""
+    capacity.  Random reads fit; a set dominated by one repeated k-mer fills a bin, whose later runs go to the spill list
+    (the run that straddles the capacity included: the bin ends where it would have begun) -- the table is the exact
+    histogram either way."""
     rng = np.random.default_rng(99)
     n_reads, length, stride, k = 40_000, 150, 5, 31
     words = rng.integers(0, 2**64, size=n_reads * stride, dtype=np.uint64)
