@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call 3f (spill-list version, plain loop over the devices again): the C5 job from plain C after kmc_group_bucket_count starts the devices' counts from one host thread each
+# round 2, call 3f: the C5 job from plain C and the multi-GPU tests on two GPUs, spill-list version of the fused count (plain loop over the devices again)
 mkdir -p gpurun_out
 gcc -std=c99 -O2 -Iinclude examples/c5_group_count.c -Lkmers.jl_b200 -lkmerscuda -Wl,-rpath,$PWD/kmers.jl_b200 -o /tmp/c5_group_count && /tmp/c5_group_count 25000000 28 > gpurun_out/r3f_c5_example.txt 2>&1; cat gpurun_out/r3f_c5_example.txt
 (python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r3f_pytest_multi.log 2>&1; echo "pytest exit $?" >> gpurun_out/r3f_pytest_multi.log); tail -3 gpurun_out/r3f_pytest_multi.log
