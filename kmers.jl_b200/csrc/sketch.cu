@@ -94,9 +94,12 @@ constexpr int kSharedCompositionMax = 4096; // 4^6 counters = 16 KB of shared me
 constexpr int kSketchBits = 12;             // top hash bits of the sketch histogram (also kept in shared memory)
 static_assert((1 << kSketchBits) <= kSharedCompositionMax, "the sketch histogram lives in the same shared array");
 
-template <int N, int NX, bool RAGGED, bool CANON, int OP>
+// ALIGNED: the work items of an aligned uniform set or of a single sequence (extract_kernels.cuh: AlignedItems) -- no
+// cursor, one bounds test per tile, every slot a window except in the last group of a single sequence.
+template <int N, int NX, bool RAGGED, bool CANON, int OP, bool ALIGNED = false>
 __global__ void __launch_bounds__(kBlockThreads) consume_kernel(const ExtractParams p, const ConsumeParams c)
 {
+    static_assert(!(ALIGNED && RAGGED), "aligned sets are uniform");
     constexpr int G = GroupOf<N>::G;
     __shared__ TileShared<RAGGED> sh;
     constexpr bool SHARED_HIST = (OP == OP_COMPOSITION_SHARED || OP == OP_HASH_HIST);
@@ -106,20 +109,36 @@ __global__ void __launch_bounds__(kBlockThreads) consume_kernel(const ExtractPar
         for (uint32_t i = threadIdx.x; i < c.table_entries; i += kBlockThreads) s_hist[i] = 0;
     }
     TileCursor<RAGGED, G> cur;
-    cur.init(p, tile_base, sh, threadIdx.x); // (block-wide barriers inside: also orders the zeroing above)
+    if (!ALIGNED) cur.init(p, tile_base, sh, threadIdx.x); // (block-wide barriers inside: also orders the zeroing above)
     if (SHARED_HIST) __syncthreads();
     uint32_t n_new = 0; // OP_TABLE: keys this thread put into the table
+    const AlignedItems<G, 2> items(p);
+    const uint32_t n_items32 = static_cast<uint32_t>(p.items);
+    bool inside = false;
+    if (ALIGNED) {
+        const uint32_t tb = static_cast<uint32_t>(tile_base);
+        const uint32_t tile_last = (n_items32 - tb > static_cast<uint32_t>(kTileItems) ? tb + kTileItems : n_items32) - 1u;
+        inside = items.template loads_inside<NX>(p, tile_last);
+    }
 
 #pragma unroll 1
     for (int it = 0; it < kTileIters; ++it) {
         const uint32_t li = static_cast<uint32_t>(it) * kBlockThreads + threadIdx.x;
         const uint64_t item = tile_base + li;
         if (item >= p.items) break;
-        cur.locate(p, item, li, sh);
-        const int jlo = cur.jlo, jhi = cur.jhi;
+        int jlo, jhi;
+        uint32_t x[NX];
+        if (ALIGNED) {
+            jlo = 0;
+            jhi = (p.al_tail != 0 && static_cast<uint32_t>(item) == n_items32 - 1u) ? static_cast<int>(p.al_tail) : G;
+            load_block_at<NX>(p, items.bit_of(static_cast<uint32_t>(item)), inside, x);
+        } else {
+            cur.locate(p, item, li, sh);
+            jlo = cur.jlo;
+            jhi = cur.jhi;
+            if (jhi > jlo) load_block<NX>(p.w32, p.nw32, cur.bit(p), x);
+        }
         if (jhi > jlo) {
-            uint32_t x[NX];
-            load_block<NX>(p.w32, p.nw32, cur.bit(p), x);
             uint64_t fw[G][N], rv[G][N];
             block_kmers<N, NX, G, true, CANON>(x, p.s0, p.head_mask, fw, rv);
 #pragma unroll
@@ -149,7 +168,7 @@ __global__ void __launch_bounds__(kBlockThreads) consume_kernel(const ExtractPar
                 }
             }
         }
-        cur.advance(p);
+        if (!ALIGNED) cur.advance(p);
     }
     if (OP == OP_TABLE) add_distinct(c.distinct, n_new);
     if (SHARED_HIST) {
@@ -169,7 +188,16 @@ cudaError_t launch_consume(ExtractParams p, ConsumeParams c, cudaStream_t stream
     const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
     if (tiles == 0) return cudaSuccess;
     if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    set_iteration_strides(p);
+    set_iteration_strides(p, RAGGED ? 0 : GroupOf<N>::G);
+    if constexpr (!RAGGED) {
+        if (p.aligned && !p.items_dev && p.gprm < 0x80000000ull && p.items < 0xffffffffull - kTileItems && aligned_kernel_enabled()) {
+            p.al_magic = aligned_magic(p.gprm);
+            consume_kernel<N, NX, false, CANON, OP, true><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p, c);
+            return cudaGetLastError();
+        }
+        p.aligned = 0; // the general locator below must not take its aligned fast path for a partial tail it cannot see
+        p.al_tail = 0;
+    }
     consume_kernel<N, NX, RAGGED, CANON, OP><<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p, c);
     return cudaGetLastError();
 }
