@@ -201,6 +201,34 @@ int32_t extract_device(kmc_ctx *ctx, const kmc_seqs *s, int32_t k, int32_t mode,
     const int kmode = (mode == KMC_UNAMBIG) ? MODE_FW : mode; // 2-bit source: every window + its index (UnambiguousKmers.jl:64-77)
 
     if (sync) CU(cudaEventRecord(ctx->ev_k0, stream));
+    // The Julia tuple layouts of one-limb k-mers over a uniform set: Vector{Tuple{Kmer,Kmer}} (FwRvIterator) and
+    // Vector{Tuple{Kmer,Int}} (UnambiguousKmers over a 2-bit source) through the lean kernel with groups of two windows, so
+    // that one work item is one 32-byte sector of the output (extract_kernels.cuh: launch_extract_aos).
+    if ((flags & KMC_AOS) && (mode == KMC_FWRV || mode == KMC_UNAMBIG) && ge.n_limbs == 1 && !s->seq_len && !s->seq_word_offset) {
+        const Geometry g2 = geometry(k, 2, kAosGroup);
+        Layout L2;
+        int32_t st2 = plan_layout(ctx, s, k, g2, stream, known, scratch, &L2); // (uniform: arithmetic only)
+        if (st2) return st2;
+        AosLaunchFn afn = get_aos_launcher_n1(g2.nx, mode == KMC_FWRV, hash);
+        if (afn && L2.total > 0 && L2.total <= out->capacity) {
+            ExtractParams p2 = base_params(s, k, g2, L2, unit_bias);
+            st2 = bind_outputs(ctx, out, mode, flags, &p2);
+            if (st2) return st2;
+            const cudaError_t e = afn(p2, stream);
+            if (e == cudaSuccess) {
+                res->n_written = L2.total;
+                if (out->seq_out_offset) CU(fill_uniform_offsets(out->seq_out_offset, s->n_seqs + 1, L2.wpr, stream));
+                if (sync) {
+                    CU(cudaEventRecord(ctx->ev_k1, stream));
+                    CU(cudaStreamSynchronize(stream));
+                    CU(cudaEventElapsedTime(&res->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+                }
+                return KMC_OK;
+            }
+            if (e != cudaErrorNotSupported) return fail_cuda(ctx, e, "launch_extract_aos");
+            (void)cudaGetLastError();
+        }
+    }
     Layout L;
     int32_t st = plan_layout(ctx, s, k, ge, stream, known, scratch, &L);
     if (st) return st;

@@ -15,6 +15,7 @@
 //                   in shared memory), and a 0-2 step search per item inside its bucket's range
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 #include "kmer_core.cuh"
 
 namespace kmc {
@@ -604,15 +605,21 @@ template <int G, int BPS> struct AlignedItems {
           first_bits(static_cast<uint64_t>(BPS) * p.first)
     {
     }
-    // bit offset in the stream of the item's first symbol
-    KMC_DEV uint64_t bit_of(uint32_t item) const
+    // bit offset in the stream of the item's first symbol; gi = the item's group within its read
+    KMC_DEV uint64_t bit_of(uint32_t item, uint32_t &gi) const
     {
-        uint32_t r = __umulhi(item, magic), gi = item - r * gprm; // r is the quotient or one below it
+        uint32_t r = __umulhi(item, magic); // the quotient or one below it
+        gi = item - r * gprm;
         if (gi >= gprm) {
             gi -= gprm;
             ++r;
         }
         return static_cast<uint64_t>(r) * read_bits + (first_bits + gi * static_cast<uint32_t>(G * BPS));
+    }
+    KMC_DEV uint64_t bit_of(uint32_t item) const
+    {
+        uint32_t gi;
+        return bit_of(item, gi);
     }
     // Offsets grow with the item, so the last item of a tile bounds the block loads of all of them: true when NX + 1
     // words from there lie inside the buffer (all tiles but the one or two that reach the end of it).
@@ -649,11 +656,22 @@ template <int NX> KMC_DEV void load_block_at(const ExtractParams &p, uint64_t bi
 // The k-mer arithmetic is the shared block_kmers / limbs_less / fx_hash.  SINK_IDS writes the 32-bit bucket id of
 // every window (first pass of the binned count, buckets.cu).
 // ---------------------------------------------------------------------------------------------
-template <int N, int NX, int MODE, bool HASH, int SINK = SINK_STREAMS, int BPS = 2, bool DIGEST = false, bool STRICT4 = false>
+// AOS: the Julia tuple layouts.  A thread's windows must then fill whole 32-byte sectors that neighbouring lanes continue, or
+// a warp's store instruction touches 32 different lines: the group size GG is chosen so that one item IS 32 bytes of output
+// (one-limb k-mers: GG = 2 for both tuples) -- a quarter of the windows per block load, but one 256-bit store per lane and
+// every line written whole by four neighbouring lanes.
+enum : int { AOS_NONE = 0, AOS_FWRV = 1 /* Tuple{Kmer,Kmer} */, AOS_INDEX = 2 /* Tuple{Kmer,Int} */ };
+
+// INDEX: an SoA stream of the windows' 1-based starts beside the k-mers (UnambiguousKmers over a 2-bit source).
+template <int N, int NX, int MODE, bool HASH, int SINK = SINK_STREAMS, int BPS = 2, bool DIGEST = false, bool STRICT4 = false, int GG = 0,
+          int AOS = AOS_NONE, bool INDEX = false>
 __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const ExtractParams p)
 {
+    static_assert(!INDEX || (AOS == AOS_NONE && SINK == SINK_STREAMS), "the index stream of the SoA form");
     static_assert(SINK == SINK_STREAMS || (SINK == SINK_IDS && MODE == MODE_CANON && HASH), "bucket ids are hashes of canonical k-mers");
-    constexpr int G = GroupOf<N>::G;
+    static_assert(AOS == AOS_NONE || (SINK == SINK_STREAMS && !DIGEST), "tuple layouts are output streams");
+    static_assert(AOS != AOS_FWRV || MODE == MODE_FWRV, "Tuple{Kmer,Kmer} is the FwRvIterator's element");
+    constexpr int G = GG > 0 ? GG : GroupOf<N>::G;
     constexpr bool WANT_RV = (MODE != MODE_FW);
     uint64_t dg_xa = 0, dg_sa = 0, dg_xh = 0, dg_sh = 0;
     const uint32_t n_items = static_cast<uint32_t>(p.items);
@@ -667,7 +685,8 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
     for (int it = 0; it < kTileIters; ++it) {
         const uint32_t item = tile_base + static_cast<uint32_t>(it) * kBlockThreads + threadIdx.x;
         if (item >= n_items) break;
-        const uint64_t bit = items.bit_of(item);
+        uint32_t gi;
+        const uint64_t bit = items.bit_of(item, gi);
         // all G slots are windows, except in the last group of a single sequence whose window count is not a multiple of G
         const bool partial = p.al_tail != 0 && item == n_items - 1u;
         const int jhi = partial ? static_cast<int>(p.al_tail) : G;
@@ -719,6 +738,28 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
             } else if (G == 8) st_v4(dst, w[0], w[1 % (G / 2)], w[2 % (G / 2)], w[3 % (G / 2)]);
             else if (G == 4) st_v2(dst, w[0], w[1 % (G / 2)]);
             else st_u64(dst, w[0]);
+        } else if constexpr (AOS != AOS_NONE) {
+            constexpr int E = AOS == AOS_FWRV ? 2 * N : N + 1; // words per element
+            uint64_t buf[G * E];
+            const int64_t ibase = static_cast<int64_t>(gi * static_cast<uint32_t>(G)) + 1 + p.index_base; // 1-based start of slot 0
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) buf[j * E + i] = AOS == AOS_FWRV ? fw[j][i] : a[j][i];
+                if (AOS == AOS_FWRV) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) buf[j * E + N + i] = rv[j][i];
+                } else {
+                    buf[j * E + N] = static_cast<uint64_t>(ibase + j);
+                }
+            }
+            if (partial) {
+                store_words<G * E>(p.out_a + static_cast<uint64_t>(item) * (G * E), buf, 0, jhi * E, false, true);
+                if (HASH) store_words<G>(p.out_hash + static_cast<uint64_t>(item) * G, h, 0, jhi, false, true);
+                continue;
+            }
+            store_run<G * E>(p.out_a + static_cast<uint64_t>(item) * (G * E), buf, true);
+            if (HASH) store_run<G>(p.out_hash + static_cast<uint64_t>(item) * G, h, false);
         } else {
             uint64_t buf[G * N];
 #pragma unroll
@@ -735,6 +776,12 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
                     store_words<G * N>(p.out_b + static_cast<uint64_t>(item) * (G * N), buf, 0, jhi * N, false, true);
                 }
                 if (HASH) store_words<G>(p.out_hash + static_cast<uint64_t>(item) * G, h, 0, jhi, false, true);
+                if (INDEX) {
+                    uint64_t ib[G];
+#pragma unroll
+                    for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(static_cast<int64_t>(gi * static_cast<uint32_t>(G)) + 1 + j + p.index_base);
+                    store_words<G>(reinterpret_cast<uint64_t *>(p.out_index) + static_cast<uint64_t>(item) * G, ib, 0, jhi, false, true);
+                }
                 continue;
             }
             store_run<G * N>(p.out_a + static_cast<uint64_t>(item) * (G * N), buf, true);
@@ -746,6 +793,12 @@ __global__ void __launch_bounds__(kBlockThreads) extract_aligned_kernel(const Ex
                 store_run<G * N>(p.out_b + static_cast<uint64_t>(item) * (G * N), buf, true);
             }
             if (HASH) store_run<G>(p.out_hash + static_cast<uint64_t>(item) * G, h, true);
+            if (INDEX) { // UnambiguousKmers over a 2-bit source: every window, with its 1-based start (SoA index stream)
+                uint64_t ib[G];
+#pragma unroll
+                for (int j = 0; j < G; ++j) ib[j] = static_cast<uint64_t>(static_cast<int64_t>(gi * static_cast<uint32_t>(G)) + 1 + j + p.index_base);
+                store_run<G>(reinterpret_cast<uint64_t *>(p.out_index) + static_cast<uint64_t>(item) * G, ib, true);
+            }
         }
     }
     if (DIGEST) digest_epilogue(p.digest, dg_xa, dg_sa, dg_xh, dg_sh);
@@ -791,7 +844,9 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
     }
 #endif
     if constexpr (!RAGGED && SINK != SINK_BUCKETS && !KMC_TMA_STORE) {
-        const bool plain_soa = SINK == SINK_IDS || (!p.aos && !p.out_index);
+        // the index stream exists for the plain forward form only (UnambiguousKmers over a 2-bit source)
+        constexpr bool kCanIndex = MODE == MODE_FW && SINK == SINK_STREAMS && !DIGEST && !STRICT4 && BPS == 2;
+        const bool plain_soa = SINK == SINK_IDS || (!p.aos && (kCanIndex || !p.out_index));
         if (p.aligned && p.vec_ok && plain_soa && !p.items_dev && p.gprm < 0x80000000ull &&
             p.items < 0xffffffffull - kTileItems && aligned_kernel_enabled()) {
             p.al_magic = aligned_magic(p.gprm);
@@ -805,20 +860,54 @@ cudaError_t launch_extract(ExtractParams p, int /*sm_count*/, cudaStream_t strea
                 const int v = e ? atoi(e) : (SINK == SINK_STREAMS ? 72 * 1024 : 0);
                 return v < 0 ? 0 : (v > 200 * 1024 ? 200 * 1024 : v);
             }();
-            if (pad > 0) {
-                cudaError_t e = cudaFuncSetAttribute(extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST, STRICT4>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-                if (e != cudaSuccess) return e;
+            auto go = [&](auto index_tag) -> cudaError_t {
+                constexpr bool IDX = decltype(index_tag)::value;
+                auto kernel = extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST, STRICT4, 0, AOS_NONE, IDX>;
+                if (pad > 0) {
+                    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+                    if (e != cudaSuccess) return e;
+                }
+                kernel<<<static_cast<unsigned>(tiles), kBlockThreads, pad, stream>>>(p);
+                return cudaGetLastError();
+            };
+            if constexpr (kCanIndex) {
+                if (p.out_index) return go(std::true_type());
             }
-            extract_aligned_kernel<N, NX, MODE, HASH, SINK, BPS, DIGEST, STRICT4>
-                <<<static_cast<unsigned>(tiles), kBlockThreads, pad, stream>>>(p);
-            return cudaGetLastError();
+            return go(std::false_type());
         }
     }
     extract_kernel<N, NX, MODE, HASH, RAGGED, SINK, STRICT4, BPS, DIGEST>
         <<<static_cast<unsigned>(tiles), kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
+
+// The tuple layouts of one-limb k-mers over an aligned uniform set (or a single sequence) whose layout was planned with groups
+// of two windows (geometry(k, 2, 2)): Tuple{Kmer,Kmer} (fwrv) or Tuple{Kmer,Int} (every window with its index).  Returns
+// cudaErrorNotSupported when the set does not qualify; the caller then plans the ordinary layout and takes extract_kernel.
+using AosLaunchFn = cudaError_t (*)(ExtractParams, cudaStream_t);
+constexpr int kAosGroup = 2;
+
+template <int NX, int AOS, bool HASH>
+cudaError_t launch_extract_aos(ExtractParams p, cudaStream_t stream)
+{
+    constexpr int MODE = AOS == AOS_FWRV ? MODE_FWRV : MODE_FW;
+    const uint64_t tiles = (p.items + kTileItems - 1) / kTileItems;
+    if (tiles == 0) return cudaSuccess;
+    set_iteration_strides(p, kAosGroup);
+    if (!p.aligned || !p.vec_ok || p.items_dev || p.gprm >= 0x80000000ull || p.items >= 0xffffffffull - kTileItems || tiles > 0x7fffffffull ||
+        !aligned_kernel_enabled())
+        return cudaErrorNotSupported;
+    p.al_magic = aligned_magic(p.gprm);
+    p.pf_tiles = 0;
+    if (prefetch_enabled()) {
+        const uint64_t per_tile = static_cast<uint64_t>(p.nw32) * 4 / tiles + 1, t = kPfChunkBytes / per_tile;
+        p.pf_tiles = static_cast<uint32_t>(t < 2 * kPfLead ? 2 * kPfLead : (t > (1u << 20) ? (1u << 20) : t));
+    }
+    extract_aligned_kernel<1, NX, MODE, HASH, SINK_STREAMS, 2, false, false, kAosGroup, AOS>
+        <<<static_cast<unsigned>(tiles), kBlockThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+AosLaunchFn get_aos_launcher_n1(int nx, bool fwrv, bool hash); // extract_n1.cu
 
 // table lookup implemented in extract_n{1,2,3,4}.cu
 ExtractLaunchFn get_extract_launcher_n1(int nx, int mode, bool hash, bool ragged);

@@ -49,11 +49,12 @@ struct Geometry {
 };
 
 // src/kmer.jl:117-137 (N = cld(K * bps, 64)) and :603-605 (get_mask); bps = bits per symbol of the k-mer alphabet
-inline Geometry geometry(int k, int bps = 2)
+// g = 0: the group size of the limb count (group_of); otherwise the given one (the AoS kernels use smaller groups)
+inline Geometry geometry(int k, int bps = 2, int g = 0)
 {
     Geometry ge;
     ge.n_limbs = (bps * k + 63) / 64;
-    ge.g = group_of(ge.n_limbs);
+    ge.g = g > 0 ? g : group_of(ge.n_limbs);
     ge.nx = (bps * k + bps * ge.g - bps + 31) / 32;
     ge.s0 = static_cast<uint32_t>(32 * ge.nx - bps * k - bps * (ge.g - 1));
     int used = bps * k - 64 * (ge.n_limbs - 1); // bits used in the head limb, bps..64

@@ -205,6 +205,20 @@ def test_aligned_uniform_sets(kc, k, length):
             assert np.array_equal(e.hash, h)
         if b is not None:
             assert np.array_equal(e.rv, b)
+    # the Julia tuple layouts (one-limb k-mers with an even window count: the lean kernel with groups of two windows)
+    a, b, h, _ = ko.batch_iterate(words, n_reads, k, ko.FWRV, uniform_len=length, uniform_stride=stride, want_hash=True)
+    N = a.shape[1]
+    for hash_ in (False, True):
+        e = kc.extract(MODES["fwrv"], rs, k, aos=True, hash=hash_)
+        assert e.n == a.shape[0] and np.array_equal(e.kmers[:, 0, :], a) and np.array_equal(e.kmers[:, 1, :], b)
+        if hash_:
+            assert np.array_equal(e.hash, h)
+        e = kc.extract(MODES["unambig"], rs, k, aos=True, hash=hash_)
+        wpr = length - k + 1
+        assert e.n == a.shape[0] and np.array_equal(e.kmers[:, :N], a)
+        assert np.array_equal(e.kmers[:, N].astype(np.int64), np.tile(np.arange(1, wpr + 1, dtype=np.int64), n_reads))
+        if hash_:
+            assert np.array_equal(e.hash, h)
 
 
 def test_aligned_single_sequence_and_views(kc):
@@ -224,6 +238,11 @@ def test_aligned_single_sequence_and_views(kc):
             f, r, _ = ko.iterate(w, n, k, ko.FWRV, first=first, want_hash=False)
             e = kc.extract(MODES["fwrv"], rs, k)
             assert e.n == f.shape[0] and np.array_equal(e.kmers, f) and np.array_equal(e.rv, r)
+            e = kc.extract(MODES["fwrv"], rs, k, aos=True)
+            assert e.n == f.shape[0] and np.array_equal(e.kmers[:, 0, :], f) and np.array_equal(e.kmers[:, 1, :], r)
+            e = kc.extract(MODES["unambig"], rs, k, aos=True)
+            N = f.shape[1]
+            assert np.array_equal(e.kmers[:, :N], f) and np.array_equal(e.kmers[:, N].astype(np.int64), np.arange(1, f.shape[0] + 1))
 
 
 def test_subsequence_views(kc):
