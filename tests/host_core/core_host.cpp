@@ -101,6 +101,31 @@ extern "C" int core_item_windows(const uint32_t *w32, int64_t nw32, int64_t bit,
     return rc < 0 ? rc : ge.g;
 }
 
+// The same for the tuple-layout kernels (extract_kernels.cuh: launch_extract_aos): one-limb 2-bit k-mers in groups of TWO
+// windows, geometry(k, 2, 2), block widths 1..3.  fw / rv are [2] words; returns 2, or -1.
+template <int NX> static void windows_g2(const uint32_t *w32, int64_t nw32, int64_t bit, const kmc::Geometry &ge, uint64_t *fw, uint64_t *rv)
+{
+    uint32_t x[NX];
+    kmc::load_block<NX>(w32, nw32, bit, x);
+    uint64_t f[2][1], r[2][1];
+    kmc::block_kmers<1, NX, 2, true, true, 2>(x, ge.s0, ge.head_mask, f, r);
+    for (int j = 0; j < 2; ++j) {
+        fw[j] = f[j][0];
+        rv[j] = r[j][0];
+    }
+}
+extern "C" int core_item_windows_g2(const uint32_t *w32, int64_t nw32, int64_t bit, int k, uint64_t *fw, uint64_t *rv)
+{
+    if (k < 1 || k > 32) return -1;
+    const kmc::Geometry ge = kmc::geometry(k, 2, 2);
+    switch (ge.nx) {
+    case 1: windows_g2<1>(w32, nw32, bit, ge, fw, rv); return 2;
+    case 2: windows_g2<2>(w32, nw32, bit, ge, fw, rv); return 2;
+    case 3: windows_g2<3>(w32, nw32, bit, ge, fw, rv); return 2;
+    }
+    return -1;
+}
+
 // FourToTwo primitives (fourbit_core.cuh): one source word of 16 nibbles -> 32 bits of 2-bit codes + 16 flags
 extern "C" void core_recode_word(uint64_t w, uint32_t *codes, uint32_t *flags) { kmc::recode_word(w, *codes, *flags); }
 

@@ -75,6 +75,24 @@ def test_two_bit_items_match_the_oracle(core, k):
         assert np.array_equal(c[:m], ca[p:p + m]) and np.array_equal(hh[:m], h[p:p + m]), (k, p)
 
 
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_two_window_items_of_the_tuple_kernels_match_the_oracle(core, k):
+    """The Julia tuple layouts run the lean kernel with groups of two windows (geometry(k, 2, 2)): a block shape of its own
+    (NX = 1, 2, 3; the half-width head mask for K >= 31), every K of a one-limb k-mer, every alignment of the block."""
+    core.core_item_windows_g2.restype = C.c_int
+    core.core_item_windows_g2.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(3000 + k)
+    n = 300
+    words = rng.integers(0, 2**64, size=(n + 31) // 32 + 1, dtype=np.uint64)
+    w32 = np.ascontiguousarray(words).view(np.uint32)
+    fw, rv, _ = ko.iterate(words, n, k, ko.FWRV)
+    nwin = n - k + 1
+    f, r = np.zeros(2, dtype=np.uint64), np.zeros(2, dtype=np.uint64)
+    for p in range(0, min(nwin - 1, 130)):
+        assert core.core_item_windows_g2(w32.ctypes.data, w32.size, 2 * p, k, f.ctypes.data, r.ctypes.data) == 2
+        assert np.array_equal(f, fw[p:p + 2, 0]) and np.array_equal(r, rv[p:p + 2, 0]), (k, p)
+
+
 @pytest.mark.parametrize("k", [1, 3, 8, 15, 16, 17, 24, 31, 32, 33, 40, 47, 48, 49, 63, 64])
 def test_four_bit_alphabet_items_match_the_oracle(core, k):
     """Kmer{DNAAlphabet{4}}: rev4 / comp4 (any IUPAC symbol, N and gap are legal symbols of the k-mer)."""
