@@ -596,39 +596,19 @@ __global__ void __launch_bounds__(kBlockThreads) extract_kernel(const ExtractPar
 }
 
 // The work items of an aligned uniform set (ExtractParams::aligned): item i is flat group i of G windows, wholly inside
-// read i / gprm.  The quotient comes from a multiply-high by floor(2^32 / gprm) (al_magic) and one correction step.
-template <int G, int BPS> struct AlignedItems {
-    uint32_t gprm, magic, read_bits;
-    uint64_t first_bits;
+// read i / gprm (kmer_core.cuh: AlignedLocator, which the CPU tests also drive).
+template <int G, int BPS> struct AlignedItems : AlignedLocator<G, BPS> {
     KMC_DEV explicit AlignedItems(const ExtractParams &p)
-        : gprm(static_cast<uint32_t>(p.gprm)), magic(p.al_magic), read_bits(static_cast<uint32_t>(p.read_bits)),
-          first_bits(static_cast<uint64_t>(BPS) * p.first)
+        : AlignedLocator<G, BPS>(static_cast<uint32_t>(p.gprm), p.al_magic, static_cast<uint32_t>(p.read_bits), p.first)
     {
-    }
-    // bit offset in the stream of the item's first symbol; gi = the item's group within its read
-    KMC_DEV uint64_t bit_of(uint32_t item, uint32_t &gi) const
-    {
-        uint32_t r = __umulhi(item, magic); // the quotient or one below it
-        gi = item - r * gprm;
-        if (gi >= gprm) {
-            gi -= gprm;
-            ++r;
-        }
-        return static_cast<uint64_t>(r) * read_bits + (first_bits + gi * static_cast<uint32_t>(G * BPS));
-    }
-    KMC_DEV uint64_t bit_of(uint32_t item) const
-    {
-        uint32_t gi;
-        return bit_of(item, gi);
     }
     // Offsets grow with the item, so the last item of a tile bounds the block loads of all of them: true when NX + 1
     // words from there lie inside the buffer (all tiles but the one or two that reach the end of it).
     template <int NX> KMC_DEV bool loads_inside(const ExtractParams &p, uint32_t last_item) const
     {
-        return static_cast<int64_t>(bit_of(last_item) >> 5) + NX < p.nw32;
+        return static_cast<int64_t>(this->bit_of(last_item) >> 5) + NX < p.nw32;
     }
 };
-inline uint32_t aligned_magic(uint64_t gprm) { return gprm == 1 ? 0xffffffffu : static_cast<uint32_t>(0x100000000ull / gprm); }
 
 // the aligned x-stream of the block at `bit`; inside = loads_inside() of the tile (no clamping needed)
 template <int NX> KMC_DEV void load_block_at(const ExtractParams &p, uint64_t bit, bool inside, uint32_t (&x)[NX])

@@ -62,6 +62,37 @@ inline Geometry geometry(int k, int bps = 2, int g = 0)
     return ge;
 }
 
+// Work item -> (read, group within the read) -> stream bit for an aligned uniform set: every read owns gprm groups of G
+// windows, none of which straddles two reads.  The quotient item / gprm comes from a multiply-high by
+// magic = floor(2^32 / gprm) (2^32 - 1 for gprm = 1) and one correction step: the estimate is the quotient or one below
+// it for every item < 2^32 and gprm < 2^31.
+inline uint32_t aligned_magic(uint64_t gprm) { return gprm == 1 ? 0xffffffffu : static_cast<uint32_t>(0x100000000ull / gprm); }
+
+template <int G, int BPS> struct AlignedLocator {
+    uint32_t gprm, magic, read_bits;
+    uint64_t first_bits;
+    KMC_DEV AlignedLocator(uint32_t gprm_, uint32_t magic_, uint32_t read_bits_, uint32_t first_symbol)
+        : gprm(gprm_), magic(magic_), read_bits(read_bits_), first_bits(static_cast<uint64_t>(BPS) * first_symbol)
+    {
+    }
+    // bit offset in the stream of the item's first symbol; gi = the item's group within its read
+    KMC_DEV uint64_t bit_of(uint32_t item, uint32_t &gi) const
+    {
+        uint32_t r = __umulhi(item, magic); // the quotient or one below it
+        gi = item - r * gprm;
+        if (gi >= gprm) {
+            gi -= gprm;
+            ++r;
+        }
+        return static_cast<uint64_t>(r) * read_bits + (first_bits + gi * static_cast<uint32_t>(G * BPS));
+    }
+    KMC_DEV uint64_t bit_of(uint32_t item) const
+    {
+        uint32_t gi;
+        return bit_of(item, gi);
+    }
+};
+
 // reversebits(x, BitsPerSymbol{2}) on a 32-bit word: reverse the order of the 16 two-bit groups.
 KMC_DEV uint32_t rev2_32(uint32_t x)
 {

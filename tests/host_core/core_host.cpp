@@ -30,6 +30,7 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s)
     return s ? (lo >> s) | (hi << (32u - s)) : lo;
 }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32); }
 
 #include "../../kmers.jl_b200/csrc/ascii_luts.h"
 #include "../../kmers.jl_b200/csrc/fourbit_core.cuh"
@@ -124,6 +125,13 @@ extern "C" int core_item_windows_g2(const uint32_t *w32, int64_t nw32, int64_t b
     case 3: windows_g2<3>(w32, nw32, bit, ge, fw, rv); return 2;
     }
     return -1;
+}
+
+// The locator of the lean kernels (kmer_core.cuh: AlignedLocator, G = 8, 2-bit symbols): stream bit and group of a work item
+extern "C" uint64_t core_aligned_bit(uint32_t item, uint32_t gprm, uint32_t read_bits, uint32_t first, uint32_t *gi)
+{
+    const kmc::AlignedLocator<8, 2> loc(gprm, kmc::aligned_magic(gprm), read_bits, first);
+    return loc.bit_of(item, *gi);
 }
 
 // FourToTwo primitives (fourbit_core.cuh): one source word of 16 nibbles -> 32 bits of 2-bit codes + 16 flags

@@ -75,6 +75,34 @@ def test_two_bit_items_match_the_oracle(core, k):
         assert np.array_equal(c[:m], ca[p:p + m]) and np.array_equal(hh[:m], h[p:p + m]), (k, p)
 
 
+def test_aligned_locator_divides_exactly(core):
+    """extract_aligned_kernel finds the read of a work item with a multiply-high by floor(2^32 / gprm) and one correction step
+    (kmer_core.cuh: AlignedLocator).  Against divmod for group counts from 1 to 2^31 - 1 -- powers of two and their
+    neighbours, primes, C2's 15 -- and items up to 2^32 - 1, incl. the multiples of gprm and their neighbours."""
+    core.core_aligned_bit.restype = C.c_uint64
+    core.core_aligned_bit.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(77)
+    gprms = {1, 2, 3, 5, 7, 15, 16, 17, 120, 255, 256, 257, 1000003, 2**31 - 1, 2**30, 2**30 + 1, 3 * 2**29, 12345678, 250_000_000}
+    gprms |= {int(x) for x in rng.integers(1, 2**31, size=40)} | {2**b + d for b in range(1, 31) for d in (-1, 0, 1) if 2**b + d >= 1}
+    gi = C.c_uint32(0)
+    for gprm in sorted(gprms):
+        items = {0, 1, gprm - 1, gprm, gprm + 1, 2**32 - 1, 2**32 - 2, 2**31, 2**31 - 1}
+        top = (2**32 - 1) // gprm
+        for q in {1, 2, top, top - 1, max(top // 2, 1), int(rng.integers(0, top + 1))}:
+            items |= {q * gprm - 1, q * gprm, q * gprm + 1}
+        items |= {int(x) for x in rng.integers(0, 2**32, size=50)}
+        read_bits, first = int(rng.integers(1, 2**32)), int(rng.integers(0, 2**20))
+        for item in items:
+            if not 0 <= item < 2**32:
+                continue
+            r, g = divmod(item, gprm)
+            if g * 16 >= 2**32:
+                continue  # (the launcher only takes sets whose windows per read fit the 32-bit arithmetic)
+            bit = core.core_aligned_bit(item, gprm, read_bits, first, C.byref(gi))
+            assert gi.value == g, (gprm, item)
+            assert bit == (r * read_bits + 2 * first + g * 16) % 2**64, (gprm, item)
+
+
 @pytest.mark.parametrize("k", list(range(1, 33)))
 def test_two_window_items_of_the_tuple_kernels_match_the_oracle(core, k):
     """The Julia tuple layouts run the lean kernel with groups of two windows (geometry(k, 2, 2)): a block shape of its own
